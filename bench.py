@@ -1,0 +1,296 @@
+"""bench.py -- CTC fwd+bwd frames/s on B200 (BASELINE.json metric), one JSON line on stdout.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--workload C3] [--impl b200|reference]
+
+A "step" is one fused loss+gradient evaluation (softmax rows -> lattice -> cost sum; the backward
+of the op is an elementwise scale of the gradient computed here) over one mini-batch
+of synthetic logits of the named shape.  N > 1: one process per GPU (torchrun), every rank owns a
+mini-batch of the same shape (data-parallel training: utterances never cross GPUs) and the scalar
+loss is all-reduced over NCCL every step -- weak scaling.
+"""
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "ctc_fwd_bwd_frames_per_sec"
+UNIT = "frames/s"
+N_ROTATE = 16          # distinct acts/grads buffer sets cycled through the timed loop (> L2 in total)
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--workload", default="C3", choices=["C1", "C2", "C3", "C4", "C5"])
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    return ap.parse_args()
+
+
+def peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured"
+    except Exception:
+        return 6650.0, "fallback"
+
+
+class ClockSampler(threading.Thread):
+    """Samples SM clocks and throttle reasons during the timed region (NVML; nvidia-smi fallback)."""
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index = index
+        self.stop_flag = threading.Event()
+        self.sm, self.reasons, self.sm_max = [], set(), None
+
+    def run(self):
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            h = pynvml.nvmlDeviceGetHandleByIndex(self.index)
+            self.sm_max = pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM)
+            names = {
+                getattr(pynvml, "nvmlClocksThrottleReasonHwSlowdown", 0x8): "hw_slowdown",
+                getattr(pynvml, "nvmlClocksThrottleReasonHwThermalSlowdown", 0x40): "hw_thermal_slowdown",
+                getattr(pynvml, "nvmlClocksThrottleReasonSwThermalSlowdown", 0x20): "sw_thermal_slowdown",
+                getattr(pynvml, "nvmlClocksThrottleReasonSwPowerCap", 0x4): "sw_power_cap",
+            }
+            while not self.stop_flag.is_set():
+                self.sm.append(pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM))
+                try:
+                    r = pynvml.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+                    for bit, name in names.items():
+                        if r & bit:
+                            self.reasons.add(name)
+                except Exception:
+                    pass
+                time.sleep(0.02)
+        except Exception:
+            self._smi()
+
+    def _smi(self):
+        import subprocess
+        q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        while not self.stop_flag.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q,
+                                      "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
+                f = [x.strip() for x in out.strip().split(",")]
+                self.sm.append(int(f[0])); self.sm_max = int(f[1])
+                for n, v in zip(names, f[2:]):
+                    if v.lower().startswith("active"):
+                        self.reasons.add(n)
+            except Exception:
+                break
+            time.sleep(0.1)
+
+    def result(self):
+        self.stop_flag.set()
+        self.join(timeout=5)
+        return {"sm_mhz": float(np.median(self.sm)) if self.sm else None, "sm_max_mhz": self.sm_max,
+                "reasons": sorted(self.reasons), "samples": len(self.sm)}
+
+
+def cpu_baseline(wl, acts_np, budget_s=12.0, kind_note=""):
+    """The oracle's C++/OpenMP restatement of the warp-ctc CPU path (float), timed on this host."""
+    from oracle import ctc_cpu
+    threads = ctc_cpu.max_threads()
+    ctc_cpu.ctc_cpu(acts_np[:, :min(8, wl.B)], *_slice(wl, min(8, wl.B)))      # warm-up (page in, build)
+    reps, t0 = 0, time.perf_counter()
+    while True:
+        ctc_cpu.ctc_cpu(acts_np, wl.labels, wl.act_lens, wl.label_lens, precision="f32")
+        reps += 1
+        dt = time.perf_counter() - t0
+        if dt > budget_s or reps >= 20:
+            break
+    frames = int(wl.act_lens.sum())
+    return {"value": frames * reps / dt, "unit": UNIT, "cores": threads, "kind": "port",
+            "sample": "%d full mini-batches of %s (%d frames each), C++/OpenMP fp32 restatement of the "
+                      "warp-ctc CPU path%s" % (reps, wl.name, frames, kind_note)}
+
+
+def _slice(wl, nb):
+    L = int(wl.label_lens[:nb].sum())
+    return wl.labels[:L], wl.act_lens[:nb], wl.label_lens[:nb]
+
+
+def run_reference(args):
+    """--impl reference: the reference's CPU implementation of the path.  warp-ctc itself is not in
+    /root/reference (un-vendored, un-pinned), so the oracle's C++/OpenMP port is timed, with all the
+    host threads, on the same workload, one full mini-batch per step."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from pytorch_end2end_speech_recognition_b200 import workloads
+    from oracle import ctc_cpu
+    wl = workloads.make_lengths_and_labels(args.workload)
+    acts = workloads.make_acts(wl).numpy()
+    frames = int(wl.act_lens.sum())
+    for _ in range(max(args.warmup, 1)):
+        ctc_cpu.ctc_cpu(acts, wl.labels, wl.act_lens, wl.label_lens, precision="f32")
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        ctc_cpu.ctc_cpu(acts, wl.labels, wl.act_lens, wl.label_lens, precision="f32")
+    dt = time.perf_counter() - t0
+    value = frames * args.steps / dt
+    total, strict, _ = workloads.algorithmic_bytes(wl)
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": wl.name, "frames_per_step": frames, "algorithmic_bytes_per_step": total},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": ctc_cpu.max_threads(), "kind": "port",
+                         "sample": "one full mini-batch per step; C++/OpenMP fp32 restatement of the warp-ctc CPU path "
+                                   "(warp-ctc is not vendored in the reference)"},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }))
+
+
+def main():
+    args = parse()
+    if args.impl == "reference":
+        return run_reference(args)
+
+    import torch
+    import torch.distributed as dist
+    import pytorch_end2end_speech_recognition_b200 as b200
+    from pytorch_end2end_speech_recognition_b200 import ctc as ctc_mod
+    from pytorch_end2end_speech_recognition_b200 import workloads
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the engine has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    wl = workloads.make_lengths_and_labels(args.workload)
+    frames = int(wl.act_lens.sum())
+    total_bytes, strict_bytes, _ = workloads.algorithmic_bytes(wl)
+    lattice_bytes = total_bytes - int(np.sum(8 * wl.act_lens.astype(np.int64) * wl.V))
+    acts_bytes = wl.T * wl.B * wl.V * 4
+    n_rot = max(2, min(N_ROTATE, int(np.ceil(160e6 / acts_bytes)))) if acts_bytes < 160e6 else 2
+    acts_host = [workloads.make_acts(wl, copy_index=rank * N_ROTATE + i) for i in range(n_rot)]
+    acts_dev = [a.to(dev) for a in acts_host]
+    grads_dev = [torch.empty_like(a) for a in acts_dev]
+    costs = torch.empty(wl.B, device=dev)
+    loss = torch.empty(1, device=dev)
+
+    def step(i):
+        j = i % n_rot
+        b200.ctc_loss_and_grad(acts_dev[j], wl.labels, wl.act_lens, wl.label_lens, grads=grads_dev[j],
+                               costs=costs, loss_sum=loss)
+        if world > 1:
+            dist.all_reduce(loss)        # the one exchange step of the path: the scalar loss
+        return loss
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps):
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        ev0.record()
+        for i in range(steps):
+            fn(i)
+        ev1.record()
+        barrier()
+        ms = ev0.elapsed_time(ev1)
+        if world > 1:
+            t = torch.tensor([ms], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t[0])
+        return ms
+
+    for i in range(max(args.warmup, 3)):
+        step(i)
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    ms = timed(step, args.steps)
+    clocks = sampler.result()
+    ms_per_step = ms / args.steps
+    value = frames * world / (ms_per_step * 1e-3)
+
+    # ---- per-kernel device time (events inside the C library, separate pass) ----
+    ctc_mod.set_profiling(True)
+    k_ms = np.zeros(3)
+    n_prof = min(args.steps, 20)
+    for i in range(n_prof):
+        step(i)
+        k_ms += np.array(ctc_mod.last_kernel_ms())
+    ctc_mod.set_profiling(False)
+    k_ms /= n_prof
+    peak, peak_kind = peaks()
+    lattice_gbs = lattice_bytes / (k_ms[1] * 1e-3) / 1e9 if k_ms[1] > 0 else 0.0
+    roofline = {"bound": "hbm", "kernel": "lattice (alpha/beta recursion + occupancy update)",
+                "achieved": lattice_gbs, "peak": peak, "peak_kind": peak_kind + " hbm copy GB/s", "unit": "GB/s",
+                "frac": lattice_gbs / peak, "traffic": None,
+                "kernel_ms": {"softmax_rows": k_ms[0], "lattice": k_ms[1], "cost_sum": k_ms[2]},
+                "algorithmic_bytes_per_launch": lattice_bytes,
+                "whole_step": {"algorithmic_bytes": total_bytes, "strict_dram_bytes": strict_bytes,
+                               "achieved": total_bytes / (ms_per_step * 1e-3) / 1e9,
+                               "frac": total_bytes / (ms_per_step * 1e-3) / 1e9 / peak,
+                               "frac_of_8000": total_bytes / (ms_per_step * 1e-3) / 1e9 / 8000.0}}
+
+    # ---- end to end: host buffers, H2D of the step's inputs and D2H of the loss inside the timed region ----
+    pinned = [a.pin_memory() for a in acts_host]
+    stage = [torch.empty_like(a) for a in acts_dev[:2]]
+    h2d = acts_bytes + wl.labels.nbytes + wl.act_lens.nbytes + wl.label_lens.nbytes
+    e2e_loss = []
+
+    def e2e_step(i):
+        j = i % n_rot
+        d = stage[i % 2]
+        d.copy_(pinned[j], non_blocking=True)                      # H2D of this step's logits
+        b200.ctc_loss_and_grad(d, wl.labels, wl.act_lens, wl.label_lens, grads=grads_dev[j], costs=costs,
+                               loss_sum=loss)                       # labels/lens go host -> device inside the call
+        if world > 1:
+            dist.all_reduce(loss)
+        e2e_loss.append(float(loss.cpu()[0]))                       # D2H read of the step's result
+
+    for i in range(3):
+        e2e_step(i)
+    e2e_ms = timed(e2e_step, args.steps) / args.steps
+    e2e = {"value": frames * world / (e2e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": int(h2d),
+           "d2h_bytes_per_step": 4, "ms_per_step": e2e_ms}
+
+    out = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+        "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": wl.name, "per_gpu_batch": wl.B, "frames_per_step_per_gpu": frames,
+                   "utterances_per_sec": wl.B * world / (ms_per_step * 1e-3),
+                   "l2": "rotating %d acts/grads buffer sets (%.0f MB > L2)" % (n_rot, 2 * n_rot * acts_bytes / 1e6),
+                   "parallelism": "utterance-sharded dp%d, scalar loss all-reduce" % world},
+        "roofline": roofline, "e2e": e2e, "gpu_launches": 3 * args.steps, "clocks": clocks,
+    }
+    if rank == 0 and not args.no_cpu_baseline and world == 1:
+        out["cpu_baseline"] = cpu_baseline(wl, acts_host[0].numpy())
+    if rank == 0:
+        print(json.dumps(out))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

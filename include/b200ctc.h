@@ -1,0 +1,143 @@
+/*
+ * b200ctc.h -- C ABI of the B200-native CTC loss-and-gradient engine.
+ *
+ * This is the drop-in boundary for the CTC path of
+ * carolinebear/pytorch_end2end_speech_recognition.  The reference reaches its
+ * CTC arithmetic through the un-vendored warp-ctc binding
+ * (tools/install_warpctc_pytorch.sh:7-18):
+ *
+ *   models/pytorch_v3/ctc/ctc.py:35,39-45   warpctc_pytorch.gpu_ctc(acts, grads,
+ *                                           labels, label_lens, act_lens,
+ *                                           minibatch_size, costs)
+ *   models/pytorch_v3/ctc/ctc.py:30-52      _CTC.forward (costs.sum(), ctx.grads)
+ *   models/pytorch_v3/ctc/decoders/greedy_decoder.py:19-47   GreedyDecoder.__call__
+ *
+ * warp-ctc's own C interface has the two-call shape
+ * get_workspace_size(...) / compute_ctc_loss(...) [recollection -- the source is
+ * not under /root/reference]; the entry points below keep that shape so that
+ * the reference-side binding is a one-to-one replacement.
+ *
+ * Conventions
+ *   - plain C types only; no exceptions cross this boundary; every function
+ *     returns a b200ctc_status_t (0 == success).
+ *   - the caller owns every buffer, including the device workspace (the
+ *     PyTorch binding takes it from the caching allocator: no cudaMalloc per
+ *     call).  The library keeps no global mutable state; the only state is the
+ *     handle, which owns a small ring of pinned host staging buffers.  Calls on
+ *     one handle must be serialised by the caller; different handles are
+ *     independent (two CTC calls per step with different shapes --
+ *     models/pytorch_v3/ctc/hierarchical_ctc.py:323-330 -- may share a handle
+ *     because they are issued from one thread in order).
+ *   - all device work is enqueued on `stream` (a cudaStream_t passed as
+ *     void*); nothing synchronises the host unless stated.
+ *   - there is NO CPU fallback: if no CUDA device is usable the calls fail
+ *     with B200CTC_STATUS_EXECUTION_FAILED.
+ */
+#ifndef B200CTC_H_
+#define B200CTC_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define B200CTC_VERSION 100 /* 0.1.0 */
+
+#if defined(__GNUC__)
+#define B200CTC_API __attribute__((visibility("default")))
+#else
+#define B200CTC_API
+#endif
+
+typedef enum {
+  B200CTC_STATUS_SUCCESS = 0,
+  B200CTC_STATUS_INVALID_VALUE = 1,     /* bad argument: shape, length, label range, null pointer */
+  B200CTC_STATUS_EXECUTION_FAILED = 2,  /* CUDA runtime / launch error */
+  B200CTC_STATUS_UNSUPPORTED = 3,       /* size outside what the kernels handle */
+  B200CTC_STATUS_WORKSPACE_TOO_SMALL = 4
+} b200ctc_status_t;
+
+typedef struct b200ctc_handle b200ctc_handle;
+
+/* Replaces warp-ctc's get_warpctc_version(). */
+B200CTC_API int b200ctc_version(void);
+
+/* Replaces warp-ctc's ctcGetStatusString(). */
+B200CTC_API const char* b200ctc_status_string(int status);
+
+/* Handle life cycle.  `device` is the CUDA device ordinal the handle is used with. */
+B200CTC_API int b200ctc_create(b200ctc_handle** handle, int device);
+B200CTC_API int b200ctc_destroy(b200ctc_handle* handle);
+
+/*
+ * Replaces warp-ctc's get_workspace_size(label_lengths, input_lengths,
+ * alphabet_size, minibatch, options, &bytes).
+ * label_lens/act_lens: HOST int32 [B].  T: padded number of frames of acts.
+ */
+B200CTC_API int b200ctc_get_workspace_size(const int* label_lens, const int* act_lens,
+                               int T, int V, int B, size_t* bytes);
+
+/*
+ * Replaces warp-ctc's compute_ctc_loss(activations, gradients, flat_labels,
+ * label_lengths, input_lengths, alphabet_size, minibatch, costs, workspace,
+ * options) as called by pytorch_binding's gpu_ctc
+ * (reference call site: models/pytorch_v3/ctc/ctc.py:35,39-45).
+ *
+ *   acts        DEVICE fp32 unnormalised logits, logical shape [T,B,V]; element
+ *               (t,b,v) lives at acts[t*acts_stride_t + b*acts_stride_b + v]
+ *               (strides in elements).  A [B,T,V] batch-major tensor viewed as
+ *               transpose(0,1) is accepted as is, which removes the
+ *               acts.contiguous() copy of ctc.py:34.
+ *   grads       DEVICE fp32 [T,B,V] contiguous, or NULL for cost only.  Fully
+ *               overwritten: rows t >= act_lens[b] are set to zero (the
+ *               reference wrapper pre-zeros them, ctc.py:36), so the caller
+ *               need not clear it.
+ *   flat_labels HOST int32 [sum(label_lens)], values in [0,V) and != blank.
+ *   label_lens  HOST int32 [B];  act_lens HOST int32 [B], 0 <= act_lens[b] <= T.
+ *   blank       blank symbol index (the reference uses 0, ctc.py:267-269).
+ *   costs       DEVICE fp32 [B]: -log p(labels_b | acts_b) per utterance.  An
+ *               utterance with no valid alignment (L_b + repeats_b > T_b) gets
+ *               +inf and an all-zero gradient.
+ *   loss_sum    DEVICE fp32 [1] or NULL: sum_b costs[b] (ctc.py:50), fixed
+ *               summation order.
+ *   workspace   DEVICE, >= b200ctc_get_workspace_size bytes, 256-byte aligned.
+ */
+B200CTC_API int b200ctc_loss_and_grad(b200ctc_handle* handle,
+                          const float* acts, int64_t acts_stride_t, int64_t acts_stride_b,
+                          float* grads,
+                          const int* flat_labels, const int* label_lens, const int* act_lens,
+                          int T, int V, int B, int blank,
+                          float* costs, float* loss_sum,
+                          void* workspace, size_t workspace_bytes, void* stream);
+
+/*
+ * Batched best-path decoder; replaces the numpy loops of
+ * models/pytorch_v3/ctc/decoders/greedy_decoder.py:32-45 (per-frame argmax with
+ * first-index tie break, collapse repeats, then drop blanks).
+ *
+ *   logits      DEVICE fp32, logical [B,T,V]; element (b,t,v) at
+ *               logits[b*stride_b + t*stride_t + v].
+ *   lens        DEVICE int32 [B] (x_lens), 0 <= lens[b] <= T.
+ *   out_tokens  DEVICE int32 [B,T]: hypothesis of utterance b in
+ *               out_tokens[b*T .. b*T+out_lens[b]); the rest of the row is -1.
+ *   out_lens    DEVICE int32 [B].
+ */
+B200CTC_API int b200ctc_greedy_decode(const float* logits, int64_t stride_b, int64_t stride_t,
+                          const int* lens, int T, int V, int B, int blank,
+                          int* out_tokens, int* out_lens, void* stream);
+
+/*
+ * Measurement hooks (no counterpart in the reference; used by bench.py for the roofline line).
+ * With profiling enabled every b200ctc_loss_and_grad call on this handle brackets each of its
+ * kernels with CUDA events on `stream`; b200ctc_get_last_kernel_ms waits for the last call and
+ * returns the device time of {softmax rows, lattice, cost sum} in milliseconds.
+ */
+B200CTC_API int b200ctc_set_profiling(b200ctc_handle* handle, int enable);
+B200CTC_API int b200ctc_get_last_kernel_ms(b200ctc_handle* handle, float* ms3);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B200CTC_H_ */

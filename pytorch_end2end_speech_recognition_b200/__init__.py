@@ -1,0 +1,9 @@
+"""B200-native CTC loss-and-gradient engine: drop-in for the ``warpctc_pytorch`` path of
+carolinebear/pytorch_end2end_speech_recognition."""
+
+from ._lib import B200CTCError  # noqa: F401
+from .ctc import CTCLoss, _CTC, cpu_ctc, ctc_loss, ctc_loss_and_grad, gpu_ctc, workspace_bytes  # noqa: F401
+from .decode import GreedyDecoder, greedy_decode  # noqa: F401
+from .shard import allreduce_loss, balance_shards, shard_batch, sharded_ctc_loss  # noqa: F401
+
+__version__ = "0.1.0"

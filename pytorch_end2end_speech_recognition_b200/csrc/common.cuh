@@ -1,0 +1,84 @@
+// Shared definitions for the B200 CTC engine (internal; the public boundary is include/b200ctc.h).
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "b200ctc.h"
+
+namespace b200ctc {
+
+// ---------------------------------------------------------------------------------------------
+// Per-utterance plan, produced on the host (api.cu: plan_batch) and uploaded with the labels in
+// one pinned->device copy.  "Lattice" vocabulary: S = 2L+1 blank-extended states, grouped four to
+// a float4 ("group"); J = ceil(S/4) groups per frame.
+// ---------------------------------------------------------------------------------------------
+struct UttMeta {
+  int T;            // frames of this utterance (act_lens[b])
+  int L;            // labels of this utterance (label_lens[b])
+  int lab_off;      // offset of its labels in the flat label vector
+  int feasible;     // 1 iff L + repeats <= T (and T > 0 or L == 0)
+  int J;            // ceil((2L+1)/4)
+  int W;            // emission-row width in gathered mode: round_up(L+1, 4)
+  long long scratch_off;  // offset of its alpha/beta scratch, in 32-byte units (one unit per group per frame)
+  long long em_off;       // offset of its gathered emission rows, in floats (gathered mode only)
+};
+
+// Device views of one call, shared by all kernels.
+struct CallParams {
+  const float* acts;      // [T,B,V] logits, element (t,b,v) at acts[t*as_t + b*as_b + v]
+  long long as_t, as_b;
+  float* grads;           // [T,B,V] contiguous or nullptr
+  int T, B, V, blank;
+  const UttMeta* meta;    // [B]
+  const int* order;       // [B] utterances sorted by decreasing lattice work (longest first)
+  const int* labels;      // flat labels (device copy)
+  int* flags;             // [B] per-utterance flags written by the kernels
+  float* lse;             // [T*B] row log-sum-exp, natural log, time-major (t*B+b)
+  float* em;              // gathered emissions (gathered mode) or nullptr
+  unsigned char* scratch; // alpha/beta scratch
+  float* costs;           // [B]
+  float* loss_sum;        // [1] or nullptr
+  int gathered;           // 1: lattice reads emissions from `em`, 0: from the softmax rows in `grads`
+};
+
+enum UttFlags : int {
+  FLAG_EXTREME_ROW = 1,   // some softmax probability of the utterance is below 2^-100: use the safe lattice
+  FLAG_PRECISION_LOST = 2 // the block-exponent lattice saw a live state lose range: redo with the safe lattice
+};
+
+constexpr int kGroupBytes = 32;  // scratch bytes per (frame, group): the safe lattice stores 4 doubles
+
+// host launchers (each in its own .cu)
+cudaError_t launch_softmax_rows(const CallParams& p, cudaStream_t stream);
+cudaError_t launch_lattice(const CallParams& p, int max_L, cudaStream_t stream);
+cudaError_t launch_cost_sum(const CallParams& p, cudaStream_t stream);
+cudaError_t launch_greedy(const float* logits, long long stride_b, long long stride_t, const int* lens,
+                          int T, int V, int B, int blank, int* out_tokens, int* out_lens,
+                          cudaStream_t stream);
+
+// ---------------------------------------------------------------------------------------------
+// small device helpers
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+__device__ __forceinline__ float warp_min(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fminf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+}  // namespace b200ctc

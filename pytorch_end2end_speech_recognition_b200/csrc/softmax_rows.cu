@@ -1,0 +1,245 @@
+// K1: row-wise softmax over the vocabulary.
+//
+// One pass over acts[T,B,V]: for every frame row (t,b) with t < act_lens[b] it computes the row
+// log-sum-exp, writes the softmax probabilities y into the gradient buffer (the lattice kernel
+// later subtracts the posterior occupancy from exactly those entries, so that
+// grad = softmax - occupancy), stores lse[t,b], and -- in gathered mode, for
+// large vocabularies -- also writes the label-indexed emission row
+//   em[t][0] = y[blank], em[t][i] = y[label_i]
+// so that the lattice kernel never touches the V-wide rows again.  Rows t >= act_lens[b] and rows
+// of utterances with no valid alignment are zero-filled (the reference wrapper pre-zeros grads,
+// models/pytorch_v3/ctc/ctc.py:36; here that fill is fused into this pass).
+//
+// Bound: HBM.  Algorithmic bytes per row: 4V read + 4V written.
+#include "common.cuh"
+
+namespace b200ctc {
+
+namespace {
+
+constexpr float kExtremeLogProb = -69.0f;  // y < 2^-100 (natural log -69.3): outside the fast lattice's range
+
+// ---- small vocabulary: one warp per row, the row lives in registers ----------------------------
+template <int NV>  // values per lane, V <= 32*NV
+__global__ void __launch_bounds__(256) softmax_rows_warp_kernel(CallParams p) {
+  const int lane = threadIdx.x & 31;
+  const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const long long n_rows = (long long)p.T * p.B;
+  if (row >= n_rows) return;
+  const int t = (int)(row / p.B);
+  const int b = (int)(row - (long long)t * p.B);
+  const UttMeta m = p.meta[b];
+  float* grow = p.grads ? p.grads + row * p.V : nullptr;
+  if (t >= m.T || !m.feasible) {
+    if (grow) {
+#pragma unroll
+      for (int i = 0; i < NV; ++i) {
+        int v = lane + 32 * i;
+        if (v < p.V) grow[v] = 0.f;
+      }
+    }
+    return;
+  }
+  const float* arow = p.acts + (long long)t * p.as_t + (long long)b * p.as_b;
+  float x[NV];
+  float mx = -INFINITY, mn = INFINITY;
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    int v = lane + 32 * i;
+    x[i] = (v < p.V) ? __ldg(arow + v) : -INFINITY;
+    mx = fmaxf(mx, x[i]);
+    if (v < p.V) mn = fminf(mn, x[i]);
+  }
+  mx = warp_max(mx);
+  mn = warp_min(mn);
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    x[i] = __expf(x[i] - mx);  // exp(-inf) = 0 for the padding lanes
+    s += x[i];
+  }
+  s = warp_sum(s);
+  const float inv = 1.0f / s;
+  const float lse = mx + logf(s);
+  if (lane == 0) {
+    p.lse[row] = lse;
+    if (mn - lse < kExtremeLogProb) atomicOr(p.flags + b, FLAG_EXTREME_ROW);
+  }
+  if (grow) {
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      int v = lane + 32 * i;
+      if (v < p.V) grow[v] = x[i] * inv;
+    }
+  }
+  if (p.gathered) {
+    // label-indexed emissions, taken from the register-resident row by shuffle
+    float* erow = p.em + m.em_off + (long long)t * m.W;
+    const int* lab = p.labels + m.lab_off;
+    for (int base = 0; base < m.W; base += 32) {
+      int i = base + lane;
+      int sym = (i == 0) ? p.blank : ((i <= m.L) ? lab[i - 1] : -1);
+      float val = 0.f;
+#pragma unroll
+      for (int k = 0; k < NV; ++k) {
+        // every lane asks lane (sym & 31) for its k-th value; keep the one whose slot matches
+        float cand = __shfl_sync(0xffffffffu, x[k], sym & 31);
+        if (sym >= 0 && (sym >> 5) == k) val = cand * inv;
+      }
+      if (i < m.W) erow[i] = val;
+    }
+  }
+}
+
+// ---- large vocabulary: one CTA per row, the row is staged in shared memory ----------------------
+constexpr int kRowThreads = 256;
+
+__device__ __forceinline__ float block_reduce_max(float v, float* red) {
+  v = warp_max(v);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
+  __syncthreads();
+  float r = red[0];
+#pragma unroll
+  for (int i = 1; i < kRowThreads / 32; ++i) r = fmaxf(r, red[i]);
+  __syncthreads();
+  return r;
+}
+__device__ __forceinline__ float block_reduce_min(float v, float* red) {
+  v = warp_min(v);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
+  __syncthreads();
+  float r = red[0];
+#pragma unroll
+  for (int i = 1; i < kRowThreads / 32; ++i) r = fminf(r, red[i]);
+  __syncthreads();
+  return r;
+}
+__device__ __forceinline__ float block_reduce_sum(float v, float* red) {
+  v = warp_sum(v);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
+  __syncthreads();
+  float r = 0.f;
+#pragma unroll
+  for (int i = 0; i < kRowThreads / 32; ++i) r += red[i];
+  __syncthreads();
+  return r;
+}
+
+__global__ void __launch_bounds__(kRowThreads) softmax_rows_cta_kernel(CallParams p) {
+  extern __shared__ __align__(16) float srow[];  // V floats (+3 slack for the aligned window)
+  __shared__ float red[kRowThreads / 32];
+  const long long row = blockIdx.x;
+  const int t = (int)(row / p.B);
+  const int b = (int)(row - (long long)t * p.B);
+  const UttMeta m = p.meta[b];
+  const int V = p.V;
+  const int tid = threadIdx.x;
+  float* grow = p.grads ? p.grads + row * V : nullptr;
+
+  if (t >= m.T || !m.feasible) {
+    if (grow) {
+      // zero fill with 128-bit stores on the aligned body
+      int head = (int)(((16 - ((uintptr_t)grow & 15)) & 15) >> 2);
+      if (head > V) head = V;
+      for (int v = tid; v < head; v += kRowThreads) grow[v] = 0.f;
+      int nvec = (V - head) >> 2;
+      float4* g4 = reinterpret_cast<float4*>(grow + head);
+      for (int v = tid; v < nvec; v += kRowThreads) g4[v] = make_float4(0.f, 0.f, 0.f, 0.f);
+      for (int v = head + (nvec << 2) + tid; v < V; v += kRowThreads) grow[v] = 0.f;
+    }
+    return;
+  }
+
+  const float* arow = p.acts + (long long)t * p.as_t + (long long)b * p.as_b;
+  // ---- load: scalar head up to 16-byte alignment, 128-bit body, scalar tail.  The row is placed
+  // in shared memory at the same 16-byte phase as in global memory so both sides stay aligned.
+  const int phase = (int)(((uintptr_t)arow & 15) >> 2);  // 0..3 floats past an aligned address
+  float* s = srow + phase;                                // s[v] <-> arow[v]
+  int head = (4 - phase) & 3;
+  if (head > V) head = V;
+  float mx = -INFINITY, mn = INFINITY;
+  for (int v = tid; v < head; v += kRowThreads) {
+    float x = __ldg(arow + v);
+    s[v] = x;
+    mx = fmaxf(mx, x);
+    mn = fminf(mn, x);
+  }
+  const int nvec = (V - head) >> 2;
+  const float4* a4 = reinterpret_cast<const float4*>(arow + head);
+  float4* s4 = reinterpret_cast<float4*>(s + head);
+  for (int v = tid; v < nvec; v += kRowThreads) {
+    float4 x = __ldg(a4 + v);
+    s4[v] = x;
+    mx = fmaxf(fmaxf(mx, fmaxf(x.x, x.y)), fmaxf(x.z, x.w));
+    mn = fminf(fminf(mn, fminf(x.x, x.y)), fminf(x.z, x.w));
+  }
+  for (int v = head + (nvec << 2) + tid; v < V; v += kRowThreads) {
+    float x = __ldg(arow + v);
+    s[v] = x;
+    mx = fmaxf(mx, x);
+    mn = fminf(mn, x);
+  }
+  mx = block_reduce_max(mx, red);  // barriers inside also publish the staged row
+  mn = block_reduce_min(mn, red);
+  float sum = 0.f;
+  for (int v = tid; v < V; v += kRowThreads) {
+    float e = __expf(s[v] - mx);
+    s[v] = e;
+    sum += e;
+  }
+  sum = block_reduce_sum(sum, red);
+  const float inv = 1.0f / sum;
+  const float lse = mx + logf(sum);
+  if (tid == 0) {
+    p.lse[row] = lse;
+    if (mn - lse < kExtremeLogProb) atomicOr(p.flags + b, FLAG_EXTREME_ROW);
+  }
+  if (grow) {
+    int ghead = (int)(((16 - ((uintptr_t)grow & 15)) & 15) >> 2);
+    if (ghead > V) ghead = V;
+    for (int v = tid; v < ghead; v += kRowThreads) grow[v] = s[v] * inv;
+    int gvec = (V - ghead) >> 2;
+    float4* g4 = reinterpret_cast<float4*>(grow + ghead);
+    for (int v = tid; v < gvec; v += kRowThreads) {
+      int o = ghead + (v << 2);
+      g4[v] = make_float4(s[o] * inv, s[o + 1] * inv, s[o + 2] * inv, s[o + 3] * inv);
+    }
+    for (int v = ghead + (gvec << 2) + tid; v < V; v += kRowThreads) grow[v] = s[v] * inv;
+  }
+  if (p.gathered) {
+    float* erow = p.em + m.em_off + (long long)t * m.W;
+    const int* lab = p.labels + m.lab_off;
+    for (int i = tid; i < m.W; i += kRowThreads) {
+      float val = 0.f;
+      if (i == 0) val = s[p.blank] * inv;
+      else if (i <= m.L) val = s[__ldg(lab + i - 1)] * inv;
+      erow[i] = val;
+    }
+  }
+}
+
+}  // namespace
+
+cudaError_t launch_softmax_rows(const CallParams& p, cudaStream_t stream) {
+  const long long n_rows = (long long)p.T * p.B;
+  if (n_rows == 0) return cudaSuccess;
+  if (p.V <= 256) {
+    const int warps = 8;
+    const unsigned grid = (unsigned)((n_rows + warps - 1) / warps);
+    if (p.V <= 32) softmax_rows_warp_kernel<1><<<grid, warps * 32, 0, stream>>>(p);
+    else if (p.V <= 64) softmax_rows_warp_kernel<2><<<grid, warps * 32, 0, stream>>>(p);
+    else if (p.V <= 128) softmax_rows_warp_kernel<4><<<grid, warps * 32, 0, stream>>>(p);
+    else softmax_rows_warp_kernel<8><<<grid, warps * 32, 0, stream>>>(p);
+  } else {
+    const size_t smem = (size_t)(p.V + 4) * sizeof(float);
+    if (smem > 48 * 1024) {
+      cudaError_t e = cudaFuncSetAttribute(softmax_rows_cta_kernel,
+                                           cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      if (e != cudaSuccess) return e;
+    }
+    softmax_rows_cta_kernel<<<(unsigned)n_rows, kRowThreads, smem, stream>>>(p);
+  }
+  return cudaGetLastError();
+}
+
+}  // namespace b200ctc

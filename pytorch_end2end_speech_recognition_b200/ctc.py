@@ -1,0 +1,250 @@
+"""Host-side mirror of the ``warpctc_pytorch`` call surface used by the reference
+(models/pytorch_v3/ctc/ctc.py:30-69, identical in models/pytorch/ctc/ctc.py), on top of the
+C ABI in include/b200ctc.h.
+
+Surface kept (same names, argument order and meaning):
+  * ``gpu_ctc(acts, grads, labels, label_lens, act_lens, minibatch_size, costs[, blank])``
+        fills ``grads`` (CUDA) and ``costs`` (CPU, per utterance) in place; note the order
+        label_lens BEFORE act_lens (reference call, ctc.py:39-45).
+  * ``cpu_ctc(...)``   raises: the product has no CPU path (the CPU restatement lives in oracle/).
+  * ``_CTC``           autograd.Function; ``forward`` may be overridden by a subclass that only
+        stashes ``ctx.grads`` (exactly what the reference does, ctc.py:30-52) while ``backward``
+        is inherited from here.
+  * ``CTCLoss(size_average=False, length_average=False, blank=0)``  nn.Module front end.
+Native additions: ``ctc_loss_and_grad`` (device-resident results, no host sync) and
+``ctc_loss`` (autograd, device scalar).
+"""
+
+import ctypes
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import B200CTCError
+
+_HANDLES = {}
+
+
+def _handle(device_index):
+    h = _HANDLES.get(device_index)
+    if h is None:
+        lib = _lib.load()
+        hp = ctypes.c_void_p()
+        _lib.check(lib.b200ctc_create(ctypes.byref(hp), int(device_index)), "b200ctc_create")
+        h = _HANDLES[device_index] = hp
+    return h
+
+
+def set_profiling(enable, device_index=None):
+    """Bracket each kernel of the following ctc_loss_and_grad calls with CUDA events (bench only)."""
+    if device_index is None:
+        device_index = torch.cuda.current_device()
+    _lib.check(_lib.load().b200ctc_set_profiling(_handle(device_index), 1 if enable else 0), "b200ctc_set_profiling")
+
+
+def last_kernel_ms(device_index=None):
+    """Device time (ms) of the last call's kernels: (softmax rows, lattice, cost sum)."""
+    if device_index is None:
+        device_index = torch.cuda.current_device()
+    ms = (ctypes.c_float * 3)()
+    _lib.check(_lib.load().b200ctc_get_last_kernel_ms(_handle(device_index), ms), "b200ctc_get_last_kernel_ms")
+    return tuple(float(x) for x in ms)
+
+
+def _host_i32(x, name):
+    """labels / lengths arrive as CPU int32 tensors in the reference (ctc.py:295-297,321);
+    numpy arrays and lists are accepted too.  Returns a C-contiguous int32 numpy array."""
+    if isinstance(x, torch.Tensor):
+        if x.is_cuda:
+            x = x.cpu()  # the warp-ctc contract keeps these on the host; tolerate device tensors
+        x = x.detach().numpy()
+    arr = np.ascontiguousarray(np.asarray(x), dtype=np.int32)
+    if arr.ndim != 1:
+        raise B200CTCError("%s must be 1-dimensional" % name)
+    return arr
+
+
+def _i32_ptr(arr):
+    return arr.ctypes.data_as(ctypes.POINTER(ctypes.c_int))
+
+
+def _require_cuda(acts):
+    if not isinstance(acts, torch.Tensor) or not acts.is_cuda:
+        raise B200CTCError("acts must be a CUDA tensor: this engine has no CPU path "
+                           "(the CPU restatement lives in oracle/ for tests only)")
+    if acts.dtype != torch.float32:
+        raise B200CTCError("acts must be float32, got %s" % acts.dtype)
+    if acts.dim() != 3:
+        raise B200CTCError("acts must be [T, B, V]")
+
+
+def workspace_bytes(label_lens, act_lens, T, V):
+    lib = _lib.load()
+    label_lens = _host_i32(label_lens, "label_lens")
+    act_lens = _host_i32(act_lens, "act_lens")
+    n = ctypes.c_size_t()
+    _lib.check(lib.b200ctc_get_workspace_size(_i32_ptr(label_lens), _i32_ptr(act_lens), int(T), int(V),
+                                              len(act_lens), ctypes.byref(n)), "b200ctc_get_workspace_size")
+    return n.value
+
+
+def ctc_loss_and_grad(acts, labels, act_lens, label_lens, blank=0, grads=None, need_grad=True,
+                      costs=None, loss_sum=None):
+    """One fused cost-and-gradient evaluation on the current CUDA stream.
+
+    acts [T,B,V] CUDA fp32 logits (any strides with a unit vocabulary stride, e.g. the
+    ``logits.transpose(0, 1)`` view the reference passes, ctc.py:319 -- no copy is made);
+    labels / act_lens / label_lens on the host.  Returns device tensors
+    ``(costs[B], loss_sum[1], grads[T,B,V] or None)``; nothing synchronises the host.
+    """
+    _require_cuda(acts)
+    lib = _lib.load()
+    if acts.stride(2) != 1 and acts.size(2) > 1:
+        acts = acts.contiguous()
+    T, B, V = acts.shape
+    labels = _host_i32(labels, "labels")
+    act_lens = _host_i32(act_lens, "act_lens")
+    label_lens = _host_i32(label_lens, "label_lens")
+    if len(act_lens) != B or len(label_lens) != B:
+        raise B200CTCError("act_lens and label_lens must have one entry per utterance (B=%d)" % B)
+    if int(label_lens.sum()) != len(labels):
+        raise B200CTCError("sum(label_lens)=%d does not match len(labels)=%d" % (int(label_lens.sum()), len(labels)))
+    dev = acts.device
+    with torch.cuda.device(dev):
+        if need_grad:
+            if grads is None:
+                grads = torch.empty((T, B, V), dtype=torch.float32, device=dev)
+            elif (not grads.is_cuda or grads.dtype != torch.float32 or tuple(grads.shape) != (T, B, V)
+                  or not grads.is_contiguous()):
+                raise B200CTCError("grads must be a contiguous CUDA float32 tensor shaped like acts")
+        else:
+            grads = None
+        if costs is None:
+            costs = torch.empty(B, dtype=torch.float32, device=dev)
+        if loss_sum is None:
+            loss_sum = torch.empty(1, dtype=torch.float32, device=dev)
+        nbytes = ctypes.c_size_t()
+        _lib.check(lib.b200ctc_get_workspace_size(_i32_ptr(label_lens), _i32_ptr(act_lens), T, V, B,
+                                                  ctypes.byref(nbytes)), "b200ctc_get_workspace_size")
+        workspace = torch.empty(max(nbytes.value, 1), dtype=torch.uint8, device=dev)  # caching allocator
+        stream = torch.cuda.current_stream(dev).cuda_stream
+        st = lib.b200ctc_loss_and_grad(
+            _handle(dev.index if dev.index is not None else torch.cuda.current_device()),
+            acts.data_ptr(), acts.stride(0), acts.stride(1),
+            grads.data_ptr() if grads is not None else None,
+            _i32_ptr(labels), _i32_ptr(label_lens), _i32_ptr(act_lens),
+            T, V, B, int(blank),
+            costs.data_ptr(), loss_sum.data_ptr(),
+            workspace.data_ptr(), nbytes.value, stream)
+        _lib.check(st, "b200ctc_loss_and_grad")
+    return costs, loss_sum, grads
+
+
+# ------------------------------------------------------------------------------------------------
+# warpctc_pytorch surface
+# ------------------------------------------------------------------------------------------------
+
+def gpu_ctc(acts, grads, labels, label_lens, act_lens, minibatch_size, costs, blank=0):
+    """Drop-in for ``warpctc_pytorch.gpu_ctc`` (reference call: ctc.py:35,39-45).
+    ``grads`` (CUDA, same shape as acts) and ``costs`` (CPU float32 [B]) are filled in place."""
+    _require_cuda(acts)
+    if int(minibatch_size) != acts.size(1):
+        raise B200CTCError("minibatch_size=%d does not match acts.size(1)=%d" % (minibatch_size, acts.size(1)))
+    dev_costs, _, _ = ctc_loss_and_grad(acts, labels, act_lens, label_lens, blank=blank, grads=grads)
+    costs.copy_(dev_costs)  # device -> host: the legacy surface returns per-utterance costs on the CPU
+    return 0
+
+
+def cpu_ctc(*_args, **_kwargs):
+    raise B200CTCError("cpu_ctc: this engine is CUDA-only (sm_100a); there is no CPU fallback")
+
+
+class _CTC(torch.autograd.Function):
+    """``warpctc_pytorch._CTC``: cost in forward, gradient stashed on ``ctx.grads``."""
+
+    # True reproduces the oldest upstream revision, which ignored grad_output
+    legacy_ignore_grad_output = False
+
+    @staticmethod
+    def forward(ctx, acts, labels, act_lens, label_lens, size_average=False, length_average=False, blank=0):
+        if not acts.is_cuda:
+            cpu_ctc()
+        minibatch_size = acts.size(1)
+        costs, loss_sum, grads = ctc_loss_and_grad(acts, labels, act_lens, label_lens, blank=blank)
+        loss = loss_sum.cpu()  # FloatTensor[1] on the host, as upstream returns it
+        if length_average:
+            total_length = float(_host_i32(act_lens, "act_lens").sum())
+            grads = grads / total_length
+            loss = loss / total_length
+        elif size_average:
+            grads = grads / minibatch_size
+            loss = loss / minibatch_size
+        ctx.grads = grads
+        return loss
+
+    @staticmethod
+    def backward(ctx, grad_output):
+        grads = ctx.grads
+        if isinstance(grads, torch.Tensor) and not _CTC.legacy_ignore_grad_output:
+            grads = grads * grad_output.to(grads.device).reshape(-1)[0]
+        # one slot per forward input: 7 here, 5 for the reference's override (ctc.py:32)
+        return (grads,) + (None,) * (len(ctx.needs_input_grad) - 1)
+
+
+class CTCLoss(torch.nn.Module):
+    """``warpctc_pytorch.CTCLoss`` (instantiated by the reference at ctc.py:69).
+
+    size_average: divide cost and gradient by the mini-batch size;
+    length_average: divide by the total number of frames; blank: blank symbol index.
+    """
+
+    def __init__(self, size_average=False, length_average=False, blank=0):
+        super().__init__()
+        self.ctc = _CTC.apply
+        self.size_average = size_average
+        self.length_average = length_average
+        self.blank = blank
+
+    def forward(self, acts, labels, act_lens, label_lens):
+        if labels.dim() != 1:
+            raise B200CTCError("labels must be 1 dimensional")
+        for name, x in (("labels", labels), ("act_lens", act_lens), ("label_lens", label_lens)):
+            if isinstance(x, torch.Tensor) and x.requires_grad:
+                raise B200CTCError("%s must not require gradients" % name)
+        return self.ctc(acts, labels, act_lens, label_lens, self.size_average, self.length_average, self.blank)
+
+
+# ------------------------------------------------------------------------------------------------
+# native API: device-resident loss, no host synchronisation
+# ------------------------------------------------------------------------------------------------
+
+class _CTCDevice(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, acts, labels, act_lens, label_lens, blank, reduction):
+        costs, loss_sum, grads = ctc_loss_and_grad(acts, labels, act_lens, label_lens, blank=blank,
+                                                   need_grad=acts.requires_grad)
+        ctx.grads = grads
+        ctx.reduction = reduction
+        if reduction == "none":
+            return costs
+        if reduction == "mean":
+            return loss_sum / acts.size(1)
+        return loss_sum
+
+    @staticmethod
+    def backward(ctx, grad_output):
+        if ctx.reduction == "none":
+            g = ctx.grads * grad_output.reshape(1, -1, 1)
+        elif ctx.reduction == "mean":
+            g = ctx.grads * (grad_output.reshape(-1)[0] / ctx.grads.size(1))
+        else:
+            g = ctx.grads * grad_output.reshape(-1)[0]
+        return g, None, None, None, None, None
+
+
+def ctc_loss(acts, labels, act_lens, label_lens, blank=0, reduction="sum"):
+    """Device-resident CTC loss: returns a CUDA tensor ([1] for 'sum'/'mean', [B] for 'none')."""
+    if reduction not in ("sum", "mean", "none"):
+        raise B200CTCError("reduction must be 'sum', 'mean' or 'none'")
+    return _CTCDevice.apply(acts, labels, act_lens, label_lens, blank, reduction)
