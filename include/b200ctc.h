@@ -136,6 +136,13 @@ B200CTC_API int b200ctc_greedy_decode(const float* logits, int64_t stride_b, int
  */
 B200CTC_API int b200ctc_set_profiling(b200ctc_handle* handle, int enable);
 B200CTC_API int b200ctc_get_last_kernel_ms(b200ctc_handle* handle, float* ms3);
+/*
+ * Diagnostics: number of utterances of the LAST call on this handle that were evaluated by the
+ * fp64 safe lattice instead of the block-exponent fast lattice (counts[0]: flagged by the softmax
+ * pass for extreme probabilities, counts[1]: the fast lattice lost range and was redone).
+ * Synchronises `stream`; the workspace of that call must still be alive.
+ */
+B200CTC_API int b200ctc_get_last_fallbacks(b200ctc_handle* handle, int* counts2, void* stream);
 
 #ifdef __cplusplus
 }

@@ -26,6 +26,7 @@ EXPORTED_SYMBOLS = (
     "b200ctc_greedy_decode",
     "b200ctc_set_profiling",
     "b200ctc_get_last_kernel_ms",
+    "b200ctc_get_last_fallbacks",
 )
 
 
@@ -66,6 +67,8 @@ def _declare(lib):
     lib.b200ctc_set_profiling.argtypes = [ctypes.c_void_p, ctypes.c_int]
     lib.b200ctc_get_last_kernel_ms.restype = ctypes.c_int
     lib.b200ctc_get_last_kernel_ms.argtypes = [ctypes.c_void_p, ctypes.POINTER(ctypes.c_float)]
+    lib.b200ctc_get_last_fallbacks.restype = ctypes.c_int
+    lib.b200ctc_get_last_fallbacks.argtypes = [ctypes.c_void_p, ctypes.POINTER(ctypes.c_int), ctypes.c_void_p]
     return lib
 
 

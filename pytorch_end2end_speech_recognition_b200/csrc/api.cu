@@ -81,6 +81,8 @@ struct b200ctc_handle {
   bool profiling = false;
   cudaEvent_t prof[4] = {nullptr, nullptr, nullptr, nullptr};  // before softmax / lattice / cost sum, after
   bool prof_valid = false;
+  const int* last_flags = nullptr;  // device pointer into the last call's workspace
+  int last_B = 0;
 };
 
 extern "C" {
@@ -251,6 +253,8 @@ int b200ctc_loss_and_grad(b200ctc_handle* h, const float* acts, int64_t acts_str
   p.loss_sum = loss_sum;
   p.gathered = (V >= kGatherMinV || grads == nullptr) ? 1 : 0;
 
+  h->last_flags = p.flags;
+  h->last_B = B;
   const bool prof = h->profiling;
   if (prof) cudaEventRecord(h->prof[0], stream);
   cudaError_t e = launch_softmax_rows(p, stream);
@@ -288,6 +292,23 @@ int b200ctc_get_last_kernel_ms(b200ctc_handle* h, float* ms3) {
   for (int i = 0; i < 3; ++i)
     if (cudaEventElapsedTime(ms3 + i, h->prof[i], h->prof[i + 1]) != cudaSuccess)
       return B200CTC_STATUS_EXECUTION_FAILED;
+  return B200CTC_STATUS_SUCCESS;
+}
+
+int b200ctc_get_last_fallbacks(b200ctc_handle* h, int* counts2, void* stream_v) {
+  if (!h || !counts2 || !h->last_flags) return B200CTC_STATUS_INVALID_VALUE;
+  std::vector<int> host((size_t)h->last_B);
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_v);
+  if (cudaMemcpyAsync(host.data(), h->last_flags, host.size() * sizeof(int), cudaMemcpyDeviceToHost, stream) != cudaSuccess ||
+      cudaStreamSynchronize(stream) != cudaSuccess) {
+    cudaGetLastError();
+    return B200CTC_STATUS_EXECUTION_FAILED;
+  }
+  counts2[0] = counts2[1] = 0;
+  for (int f : host) {
+    if (f & FLAG_EXTREME_ROW) ++counts2[0];
+    if (f & FLAG_PRECISION_LOST) ++counts2[1];
+  }
   return B200CTC_STATUS_SUCCESS;
 }
 

@@ -1,15 +1,20 @@
 // K2: alpha/beta lattice recursion + posterior occupancy update of the gradient rows.
 // K3: fixed-order sum of the per-utterance costs.
 #include "common.cuh"
+#include "lattice_fast.cuh"
 #include "lattice_safe.cuh"
 
 namespace b200ctc {
 
 namespace {
 
-constexpr int kSafeThreads = 256;
+constexpr int kChunk = 4;  // frames between halo exchanges (K)
 
-__global__ void __launch_bounds__(kSafeThreads) lattice_safe_kernel(CallParams p) {
+// One CTA per utterance, longest lattice first (p.order).  The block-exponent fast path runs unless
+// the utterance was flagged by K1 or is too long for the lattice window; when the fast path gives
+// up (range lost, zero probability) the same CTA redoes the utterance with the fp64 safe path.
+template <int K, int NWMAX>
+__global__ void __launch_bounds__(2 * NWMAX * 32, 1) lattice_kernel(CallParams p) {
   extern __shared__ __align__(16) unsigned char smem[];
   const int b = p.order[blockIdx.x];
   const UttMeta m = p.meta[b];
@@ -21,7 +26,21 @@ __global__ void __launch_bounds__(kSafeThreads) lattice_safe_kernel(CallParams p
     if (threadIdx.x == 0) p.costs[b] = 0.f;
     return;
   }
-  lattice_safe_utterance(p, b, smem, /*rows_dirty=*/false);
+  bool use_safe = (p.flags[b] & FLAG_EXTREME_ROW) != 0 || fast_warps_needed<K>(m.L) > NWMAX;
+  bool dirty = false;
+  if (!use_safe) {
+    int* abort_word = nullptr;
+    lattice_fast_utterance<K, NWMAX>(p, b, smem, &abort_word);
+    __syncthreads();
+    use_safe = *abort_word != 0;
+    if (use_safe) {
+      dirty = p.grads != nullptr;  // part of the occupancy may already have been subtracted
+      if (threadIdx.x == 0) atomicOr(p.flags + b, FLAG_PRECISION_LOST);
+      __threadfence();             // order this thread's REDs before the rows are rebuilt
+      __syncthreads();
+    }
+  }
+  if (use_safe) lattice_safe_utterance(p, b, smem, dirty);
 }
 
 // Single CTA, fixed summation tree: the returned loss is bit-reproducible run to run.
@@ -39,18 +58,31 @@ __global__ void __launch_bounds__(256) cost_sum_kernel(const float* __restrict__
   if (threadIdx.x == 0) *loss_sum = (float)part[0];
 }
 
+template <int K, int NWMAX>
+cudaError_t launch_lattice_t(const CallParams& p, int max_L, cudaStream_t stream) {
+  // longest label sequence the fast path's lattice window holds with NWMAX warps per side
+  int l_cap = max_L;
+  while (l_cap > 0 && fast_warps_needed<K>(l_cap) > NWMAX) --l_cap;
+  const int rw = p.gathered ? (l_cap + 1 + 3) / 4 * 4 : (p.V + 3) / 4 * 4;
+  size_t smem = fast_smem_bytes<K, NWMAX>(l_cap, rw);
+  smem = smem > safe_smem_bytes(max_L) ? smem : safe_smem_bytes(max_L);
+  if (smem > 48 * 1024) {
+    cudaError_t e = cudaFuncSetAttribute(lattice_kernel<K, NWMAX>,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+  }
+  lattice_kernel<K, NWMAX><<<p.B, 2 * NWMAX * 32, smem, stream>>>(p);
+  return cudaGetLastError();
+}
+
 }  // namespace
 
 cudaError_t launch_lattice(const CallParams& p, int max_L, cudaStream_t stream) {
   if (p.B == 0) return cudaSuccess;
-  const size_t smem = safe_smem_bytes(max_L);
-  if (smem > 48 * 1024) {
-    cudaError_t e = cudaFuncSetAttribute(lattice_safe_kernel,
-                                         cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return e;
-  }
-  lattice_safe_kernel<<<p.B, kSafeThreads, smem, stream>>>(p);
-  return cudaGetLastError();
+  const int nw = fast_warps_needed<kChunk>(max_L);
+  if (nw <= 2) return launch_lattice_t<kChunk, 2>(p, max_L, stream);
+  if (nw <= 4) return launch_lattice_t<kChunk, 4>(p, max_L, stream);
+  return launch_lattice_t<kChunk, 8>(p, max_L, stream);
 }
 
 cudaError_t launch_cost_sum(const CallParams& p, cudaStream_t stream) {

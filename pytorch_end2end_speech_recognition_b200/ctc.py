@@ -24,6 +24,7 @@ from . import _lib
 from ._lib import B200CTCError
 
 _HANDLES = {}
+_LAST_WORKSPACE = None
 
 
 def _handle(device_index):
@@ -50,6 +51,17 @@ def last_kernel_ms(device_index=None):
     ms = (ctypes.c_float * 3)()
     _lib.check(_lib.load().b200ctc_get_last_kernel_ms(_handle(device_index), ms), "b200ctc_get_last_kernel_ms")
     return tuple(float(x) for x in ms)
+
+
+def last_fallbacks(device_index=None):
+    """(extreme_rows, range_lost): utterances of the last call that took the fp64 safe lattice."""
+    if device_index is None:
+        device_index = torch.cuda.current_device()
+    c = (ctypes.c_int * 2)()
+    _lib.check(_lib.load().b200ctc_get_last_fallbacks(_handle(device_index), c,
+                                                      torch.cuda.current_stream().cuda_stream),
+               "b200ctc_get_last_fallbacks")
+    return int(c[0]), int(c[1])
 
 
 def _host_i32(x, name):
@@ -138,6 +150,8 @@ def ctc_loss_and_grad(acts, labels, act_lens, label_lens, blank=0, grads=None, n
             costs.data_ptr(), loss_sum.data_ptr(),
             workspace.data_ptr(), nbytes.value, stream)
         _lib.check(st, "b200ctc_loss_and_grad")
+        global _LAST_WORKSPACE
+        _LAST_WORKSPACE = workspace   # keeps the diagnostics (last_fallbacks) valid until the next call
     return costs, loss_sum, grads
 
 

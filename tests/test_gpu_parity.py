@@ -11,6 +11,7 @@ import torch
 import pytorch_end2end_speech_recognition_b200 as b200
 from oracle import ctc_ref
 from oracle.ctc_cpu import ctc_cpu
+from pytorch_end2end_speech_recognition_b200 import ctc as ctc_mod
 from pytorch_end2end_speech_recognition_b200 import workloads
 
 pytestmark = pytest.mark.gpu
@@ -85,6 +86,7 @@ def test_extreme_logits_stability():
     acts = (rng.randn(30, 3, 8) * 50).astype(np.float32)
     c, g = check(acts, [1, 2, 2, 3, 7, 7, 1], [30, 20, 25], [3, 2, 2])
     assert np.all(np.isfinite(c)) and np.all(np.isfinite(g))
+    assert sum(ctc_mod.last_fallbacks()) > 0        # +-50 logits: handled by the fp64 safe lattice
     acts = rng.randn(40, 2, 5).astype(np.float32)
     acts[::3, :, 1] += 50; acts[1::3, :, 2] -= 50
     check(acts, [1, 2, 1, 2, 3], [40, 33], [3, 2])
@@ -163,6 +165,8 @@ def test_full_size_configs(key):
     acts_t = workloads.make_acts(wl)
     acts = acts_t.numpy()
     c, g = check(acts, wl.labels, wl.act_lens, wl.label_lens, oracle="cpp")
+    # the block-exponent fast lattice must be what ran: no utterance may have needed the fp64 safe path
+    assert ctc_mod.last_fallbacks() == (0, 0)
     T_b = wl.act_lens
     t_idx = np.arange(wl.T)[:, None]
     valid = t_idx < T_b[None, :]
