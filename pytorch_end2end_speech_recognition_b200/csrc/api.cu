@@ -15,7 +15,7 @@ namespace {
 
 constexpr size_t kAlign = 256;
 constexpr int kStagingSlots = 4;
-constexpr int kGatherMinV = 129;  // V above this: emission rows are gathered by label position
+constexpr int kGatherMinV = 129;  // V above this: the lattice reads gathered emission rows
 
 inline size_t align_up(size_t x) { return (x + kAlign - 1) / kAlign * kAlign; }
 
@@ -28,33 +28,21 @@ struct WorkspaceLayout {
 
 struct BatchTotals {
   long long sum_labels = 0;
-  long long em_doubles = 0;      // sum_b T_b * W_b
-  long long scratch_units = 0;   // sum_b scratch_units_of(T_b, L_b)
+  long long em_floats = 0;       // sum_b T_b * W_b
+  long long scratch_units = 0;   // sum_b T_b * J_b
 };
 
 inline int groups_of(int L) { return (2 * L + 1 + 3) / 4; }
-// emission row width in doubles (even).  The gathered layout is used for large vocabularies.
-inline int em_width_of(int L, int V) { return V >= kGatherMinV ? (L + 1 + 1) / 2 * 2 : (V + 1) / 2 * 2; }
-// scratch of one utterance in 32-byte units: the larger of the safe lattice's alpha matrix
-// (T x 4J doubles) and the fast lattice's checkpoints (one 64-byte slot per lane per chunk and side,
-// plus one exponent per warp).
-inline long long scratch_units_of(int T, int L) {
-  const long long safe_bytes = (long long)T * groups_of(L) * kGroupBytes;
-  const long long nw = dp_warps_needed<kChunk>(L);
-  const long long chunks = (long long)T / kChunk + 4;
-  const long long dp_bytes = chunks * nw * (32 * 64 + 4) + 64;
-  const long long bytes = safe_bytes > dp_bytes ? safe_bytes : dp_bytes;
-  return (bytes + kGroupBytes - 1) / kGroupBytes;
-}
+inline int em_width_of(int L) { return (L + 1 + 3) / 4 * 4; }
 
-int totals_from_lens(const int* label_lens, const int* act_lens, int T, int V, int B, BatchTotals* out) {
+int totals_from_lens(const int* label_lens, const int* act_lens, int T, int B, BatchTotals* out) {
   BatchTotals t;
   for (int b = 0; b < B; ++b) {
     const int L = label_lens[b], Tb = act_lens[b];
     if (L < 0 || Tb < 0 || Tb > T) return B200CTC_STATUS_INVALID_VALUE;
     t.sum_labels += L;
-    t.em_doubles += (long long)Tb * em_width_of(L, V);
-    t.scratch_units += scratch_units_of(Tb, L);
+    t.em_floats += (long long)Tb * em_width_of(L);
+    t.scratch_units += (long long)Tb * groups_of(L);
   }
   *out = t;
   return B200CTC_STATUS_SUCCESS;
@@ -69,7 +57,7 @@ WorkspaceLayout make_layout(const BatchTotals& t, int T, int B) {
   w.off_labels = off; off += align_up((size_t)t.sum_labels * sizeof(int));
   w.blob_bytes = off;
   w.off_lse = off;    off += align_up((size_t)T * B * sizeof(float));
-  w.off_em = off;     off += align_up((size_t)t.em_doubles * sizeof(double));
+  w.off_em = off;     off += align_up((size_t)t.em_floats * sizeof(float));
   w.off_scratch = off; off += align_up((size_t)t.scratch_units * kGroupBytes);
   w.total = off;
   return w;
@@ -146,7 +134,7 @@ int b200ctc_get_workspace_size(const int* label_lens, const int* act_lens, int T
   if (!bytes || T < 0 || V < 1 || B < 0 || (B > 0 && (!label_lens || !act_lens)))
     return B200CTC_STATUS_INVALID_VALUE;
   BatchTotals t;
-  int st = totals_from_lens(label_lens, act_lens, T, V, B, &t);
+  int st = totals_from_lens(label_lens, act_lens, T, B, &t);
   if (st != B200CTC_STATUS_SUCCESS) return st;
   *bytes = make_layout(t, T, B).total + kAlign;
   return B200CTC_STATUS_SUCCESS;
@@ -169,7 +157,7 @@ int b200ctc_loss_and_grad(b200ctc_handle* h, const float* acts, int64_t acts_str
 
   // ---- plan on the host ----------------------------------------------------------------------
   BatchTotals tot;
-  int st = totals_from_lens(label_lens, act_lens, T, V, B, &tot);
+  int st = totals_from_lens(label_lens, act_lens, T, B, &tot);
   if (st != B200CTC_STATUS_SUCCESS) return st;
   if (tot.sum_labels > 0 && !flat_labels) return B200CTC_STATUS_INVALID_VALUE;
   if (tot.sum_labels > 0x7fffffffLL) return B200CTC_STATUS_UNSUPPORTED;
@@ -223,12 +211,12 @@ int b200ctc_loss_and_grad(b200ctc_handle* h, const float* acts, int64_t acts_str
     m.lab_off = (int)lab_off;
     m.feasible = (L + repeats <= Tb) ? 1 : 0;
     m.J = groups_of(L);
-    m.W = em_width_of(L, V);
+    m.W = em_width_of(L);
     m.scratch_off = scratch_off;
     m.em_off = em_off;
     lab_off += L;
     em_off += (long long)Tb * m.W;
-    scratch_off += scratch_units_of(Tb, L);
+    scratch_off += (long long)Tb * m.J;
     if (m.feasible) max_L = std::max(max_L, L);
     order[b] = b;
     flags[b] = 0;
@@ -259,11 +247,11 @@ int b200ctc_loss_and_grad(b200ctc_handle* h, const float* acts, int64_t acts_str
   p.flags = reinterpret_cast<int*>(ws + lay.off_flags);
   p.labels = reinterpret_cast<const int*>(ws + lay.off_labels);
   p.lse = reinterpret_cast<float*>(ws + lay.off_lse);
-  p.em = reinterpret_cast<double*>(ws + lay.off_em);
+  p.em = reinterpret_cast<float*>(ws + lay.off_em);
   p.scratch = ws + lay.off_scratch;
   p.costs = costs;
   p.loss_sum = loss_sum;
-  p.gathered = (V >= kGatherMinV) ? 1 : 0;
+  p.gathered = (V >= kGatherMinV || grads == nullptr) ? 1 : 0;
 
   h->last_flags = p.flags;
   h->last_B = B;

@@ -19,9 +19,9 @@ struct UttMeta {
   int lab_off;      // offset of its labels in the flat label vector
   int feasible;     // 1 iff L + repeats <= T (and T > 0 or L == 0)
   int J;            // ceil((2L+1)/4)
-  int W;            // emission-row width in doubles (even): gathered mode round_up(L+1, 2), else round_up(V, 2)
+  int W;            // emission-row width in gathered mode: round_up(L+1, 4)
   long long scratch_off;  // offset of its alpha/beta scratch, in 32-byte units (one unit per group per frame)
-  long long em_off;       // offset of its emission rows [T][W], in doubles
+  long long em_off;       // offset of its gathered emission rows, in floats (gathered mode only)
 };
 
 // Device views of one call, shared by all kernels.
@@ -35,11 +35,11 @@ struct CallParams {
   const int* labels;      // flat labels (device copy)
   int* flags;             // [B] per-utterance flags written by the kernels
   float* lse;             // [T*B] row log-sum-exp, natural log, time-major (t*B+b)
-  double* em;             // per-utterance emission rows [T_b][W_b] (softmax probabilities as doubles)
+  float* em;              // gathered emissions (gathered mode) or nullptr
   unsigned char* scratch; // alpha/beta scratch
   float* costs;           // [B]
   float* loss_sum;        // [1] or nullptr
-  int gathered;           // 1: emission rows are indexed by label position (0 = blank, i = label i-1); 0: by symbol
+  int gathered;           // 1: lattice reads emissions from `em`, 0: from the softmax rows in `grads`
 };
 
 enum UttFlags : int {
@@ -47,18 +47,7 @@ enum UttFlags : int {
   FLAG_PRECISION_LOST = 2 // the block-exponent lattice saw a live state lose range: redo with the safe lattice
 };
 
-constexpr int kGroupBytes = 32;  // scratch unit; the safe lattice stores 4 doubles per (frame, 4 states)
-constexpr int kChunk = 4;        // frames between halo exchanges / checkpoints of the fast lattice (K)
-
-// Fast-lattice geometry (shared by the host planner and the kernel): eight lattice states per lane,
-// 256 positions per warp window, consecutive windows overlap by a halo of 2K positions.
-__host__ __device__ inline int dp_positions(int L) { return 8 * ((2 * L + 1 + 7) / 8); }
-template <int K>
-__host__ __device__ inline int dp_warps_needed(int L) {
-  const int P = dp_positions(L);
-  const int own = 256 - 2 * K;
-  return P <= 256 ? 1 : 1 + (P - 256 + own - 1) / own;
-}
+constexpr int kGroupBytes = 32;  // scratch bytes per (frame, group): the safe lattice stores 4 doubles
 
 // host launchers (each in its own .cu)
 cudaError_t launch_softmax_rows(const CallParams& p, cudaStream_t stream);

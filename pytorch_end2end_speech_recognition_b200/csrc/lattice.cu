@@ -1,14 +1,16 @@
 // K2: alpha/beta lattice recursion + posterior occupancy update of the gradient rows.
 // K3: fixed-order sum of the per-utterance costs.
 #include "common.cuh"
-#include "lattice_dp.cuh"
+#include "lattice_fast.cuh"
 #include "lattice_safe.cuh"
 
 namespace b200ctc {
 
 namespace {
 
-// One CTA per utterance, longest lattice first (p.order).  The fp64 fast path runs unless
+constexpr int kChunk = 4;  // frames between halo exchanges (K)
+
+// One CTA per utterance, longest lattice first (p.order).  The block-exponent fast path runs unless
 // the utterance was flagged by K1 or is too long for the lattice window; when the fast path gives
 // up (range lost, zero probability) the same CTA redoes the utterance with the fp64 safe path.
 template <int K, int NWMAX>
@@ -24,11 +26,11 @@ __global__ void __launch_bounds__(2 * NWMAX * 32, 1) lattice_kernel(CallParams p
     if (threadIdx.x == 0) p.costs[b] = 0.f;
     return;
   }
-  bool use_safe = (p.flags[b] & FLAG_EXTREME_ROW) != 0 || dp_warps_needed<K>(m.L) > NWMAX;
+  bool use_safe = (p.flags[b] & FLAG_EXTREME_ROW) != 0 || fast_warps_needed<K>(m.L) > NWMAX;
   bool dirty = false;
   if (!use_safe) {
     int* abort_word = nullptr;
-    lattice_dp_utterance<K, NWMAX>(p, b, smem, &abort_word);
+    lattice_fast_utterance<K, NWMAX>(p, b, smem, &abort_word);
     __syncthreads();
     use_safe = *abort_word != 0;
     if (use_safe) {
@@ -60,9 +62,9 @@ template <int K, int NWMAX>
 cudaError_t launch_lattice_t(const CallParams& p, int max_L, cudaStream_t stream) {
   // longest label sequence the fast path's lattice window holds with NWMAX warps per side
   int l_cap = max_L;
-  while (l_cap > 0 && dp_warps_needed<K>(l_cap) > NWMAX) --l_cap;
-  const int w = p.gathered ? (l_cap + 1 + 1) / 2 * 2 : (p.V + 1) / 2 * 2;
-  size_t smem = dp_smem_bytes<K, NWMAX>(l_cap, w);
+  while (l_cap > 0 && fast_warps_needed<K>(l_cap) > NWMAX) --l_cap;
+  const int rw = p.gathered ? (l_cap + 1 + 3) / 4 * 4 : (p.V + 3) / 4 * 4;
+  size_t smem = fast_smem_bytes<K, NWMAX>(l_cap, rw);
   smem = smem > safe_smem_bytes(max_L) ? smem : safe_smem_bytes(max_L);
   if (smem > 48 * 1024) {
     cudaError_t e = cudaFuncSetAttribute(lattice_kernel<K, NWMAX>,
@@ -77,8 +79,7 @@ cudaError_t launch_lattice_t(const CallParams& p, int max_L, cudaStream_t stream
 
 cudaError_t launch_lattice(const CallParams& p, int max_L, cudaStream_t stream) {
   if (p.B == 0) return cudaSuccess;
-  const int nw = dp_warps_needed<kChunk>(max_L);
-  if (nw <= 1) return launch_lattice_t<kChunk, 1>(p, max_L, stream);
+  const int nw = fast_warps_needed<kChunk>(max_L);
   if (nw <= 2) return launch_lattice_t<kChunk, 2>(p, max_L, stream);
   if (nw <= 4) return launch_lattice_t<kChunk, 4>(p, max_L, stream);
   return launch_lattice_t<kChunk, 8>(p, max_L, stream);

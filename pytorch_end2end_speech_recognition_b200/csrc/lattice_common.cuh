@@ -16,8 +16,7 @@ struct SymbolIndex {
   int* sorted;
   int* seg_start;
   int* seg_sym;
-  int* n_seg;   // single int in shared memory
-  int* rank_of; // optional [L]: slot of label position i in sorted[] (inverse permutation), or nullptr
+  int* n_seg;  // single int in shared memory
 };
 
 // All threads of the CTA call this; lab[] must already be in shared memory and visible.
@@ -33,7 +32,6 @@ __device__ __forceinline__ void build_symbol_index(const int* lab, int L, Symbol
       rank += (lj < li) || (lj == li && j < i);
     }
     ix.sorted[rank] = i;
-    if (ix.rank_of) ix.rank_of[i] = rank;
   }
   __syncthreads();
   if (tid == 0) {

@@ -50,7 +50,6 @@ __device__ __forceinline__ SafeSmem carve_safe_smem(unsigned char* base, int L) 
   s.ix.seg_start = s.ix.sorted + L;
   s.ix.seg_sym = s.ix.seg_start + L + 1;
   s.ix.n_seg = s.ix.seg_sym + L + 1;
-  s.ix.rank_of = nullptr;
   return s;
 }
 

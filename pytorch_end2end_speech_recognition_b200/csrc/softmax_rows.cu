@@ -3,11 +3,10 @@
 // One pass over acts[T,B,V]: for every frame row (t,b) with t < act_lens[b] it computes the row
 // log-sum-exp, writes the softmax probabilities y into the gradient buffer (the lattice kernel
 // later subtracts the posterior occupancy from exactly those entries, so that
-// grad = softmax - occupancy), stores lse[t,b], and writes the utterance's
-// emission row for the lattice kernel as doubles, contiguous per utterance:
-//   small vocabularies:          em[t][k] = y[k]                         (indexed by symbol)
-//   large vocabularies (gathered): em[t][0] = y[blank], em[t][i] = y[label_i]
-// so that the lattice kernel streams short contiguous rows and never touches the V-wide rows.  Rows t >= act_lens[b] and rows
+// grad = softmax - occupancy), stores lse[t,b], and -- in gathered mode, for
+// large vocabularies -- also writes the label-indexed emission row
+//   em[t][0] = y[blank], em[t][i] = y[label_i]
+// so that the lattice kernel never touches the V-wide rows again.  Rows t >= act_lens[b] and rows
 // of utterances with no valid alignment are zero-filled (the reference wrapper pre-zeros grads,
 // models/pytorch_v3/ctc/ctc.py:36; here that fill is fused into this pass).
 //
@@ -73,9 +72,9 @@ __global__ void __launch_bounds__(256) softmax_rows_warp_kernel(CallParams p) {
       if (v < p.V) grow[v] = x[i] * inv;
     }
   }
-  double* erow = p.em + m.em_off + (long long)t * m.W;
   if (p.gathered) {
     // label-indexed emissions, taken from the register-resident row by shuffle
+    float* erow = p.em + m.em_off + (long long)t * m.W;
     const int* lab = p.labels + m.lab_off;
     for (int base = 0; base < m.W; base += 32) {
       int i = base + lane;
@@ -87,13 +86,7 @@ __global__ void __launch_bounds__(256) softmax_rows_warp_kernel(CallParams p) {
         float cand = __shfl_sync(0xffffffffu, x[k], sym & 31);
         if (sym >= 0 && (sym >> 5) == k) val = cand * inv;
       }
-      if (i < m.W) erow[i] = (double)val;
-    }
-  } else {
-#pragma unroll
-    for (int i = 0; i < NV; ++i) {
-      int v = lane + 32 * i;
-      if (v < m.W) erow[v] = (v < p.V) ? (double)(x[i] * inv) : 0.0;
+      if (i < m.W) erow[i] = val;
     }
   }
 }
@@ -213,18 +206,14 @@ __global__ void __launch_bounds__(kRowThreads) softmax_rows_cta_kernel(CallParam
     }
     for (int v = ghead + (gvec << 2) + tid; v < V; v += kRowThreads) grow[v] = s[v] * inv;
   }
-  {
-    double* erow = p.em + m.em_off + (long long)t * m.W;
-    if (p.gathered) {
-      const int* lab = p.labels + m.lab_off;
-      for (int i = tid; i < m.W; i += kRowThreads) {
-        float val = 0.f;
-        if (i == 0) val = s[p.blank] * inv;
-        else if (i <= m.L) val = s[__ldg(lab + i - 1)] * inv;
-        erow[i] = (double)val;
-      }
-    } else {
-      for (int v = tid; v < m.W; v += kRowThreads) erow[v] = (v < V) ? (double)(s[v] * inv) : 0.0;
+  if (p.gathered) {
+    float* erow = p.em + m.em_off + (long long)t * m.W;
+    const int* lab = p.labels + m.lab_off;
+    for (int i = tid; i < m.W; i += kRowThreads) {
+      float val = 0.f;
+      if (i == 0) val = s[p.blank] * inv;
+      else if (i <= m.L) val = s[__ldg(lab + i - 1)] * inv;
+      erow[i] = val;
     }
   }
 }
