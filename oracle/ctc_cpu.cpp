@@ -3,7 +3,9 @@
 // Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may load
 // this library; the product never does.
 //
-// Parity status: "parity unpinned" (see oracle/ctc_ref.py).  The reference's CTC arithmetic is the
+// Parity status: pinned to the reference's in-tree Chainer CTC through the golden vectors of
+// tests/golden/ctc_reference_golden.npz (see oracle/ctc_ref.py); warp-ctc itself cannot be run:
+// the reference's PyTorch-path CTC arithmetic is the
 // un-vendored, un-pinned warp-ctc (tools/install_warpctc_pytorch.sh:7), whose source is absent from
 // /root/reference, so this file restates the published algorithm with the structure of warp-ctc's
 // CPU path as far as it is known [recollection]: per (t,b) column a max-subtracted softmax over the

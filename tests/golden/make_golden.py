@@ -8,6 +8,15 @@
                       implementation independent of oracle/ -- on small seeded cases.  The
                       reference's own loss (warp-ctc) cannot be run: it is not vendored.
 
+  ctc_reference_golden.npz : per-utterance costs and gradients from the REFERENCE'S OWN in-tree CTC,
+                      ``models/chainer/ctc/ctc_loss_from_chainer.py`` (class
+                      ConnectionistTemporalClassification, numpy branch, float32, reduce='no'),
+                      imported from /root/reference and run here.  The file only needs the
+                      ``chainer`` package for a base class, ``cuda.get_array_module`` and
+                      ``type_check``; chainer is not installed, so a ten-line stub module stands in
+                      for those three names -- every line of CTC arithmetic that runs is the
+                      reference's.  This is what pins oracle/ to the reference.
+
 Usage: python tests/golden/make_golden.py
 """
 import os
@@ -88,7 +97,83 @@ def ctc_cases():
     np.savez_compressed(os.path.join(HERE, "ctc_golden.npz"), **out)
 
 
+def _import_reference_chainer_ctc():
+    """Import models/chainer/ctc/ctc_loss_from_chainer.py from /root/reference with a stub for the
+    (absent) chainer package: Function base class, cuda.get_array_module -> numpy, type_check,
+    utils.force_array, is_debug.  No arithmetic lives in the stub."""
+    import collections
+    import collections.abc
+    import importlib.util
+    import types
+    if not hasattr(collections, "Sequence"):          # the 2018 file uses the pre-3.10 alias
+        collections.Sequence = collections.abc.Sequence
+    chainer = types.ModuleType("chainer")
+    chainer.is_debug = lambda: False
+    backends = types.ModuleType("chainer.backends")
+    cuda = types.ModuleType("chainer.backends.cuda")
+    cuda.get_array_module = lambda *a: np
+    function = types.ModuleType("chainer.function")
+    function.Function = type("Function", (object,), {})
+    utils = types.ModuleType("chainer.utils")
+    utils.force_array = lambda x, dtype=None: np.asarray(x, dtype=dtype)
+    type_check = types.ModuleType("chainer.utils.type_check")
+    type_check.expect = lambda *a, **k: None
+    chainer.backends, backends.cuda = backends, cuda
+    chainer.function, chainer.utils, utils.type_check = function, utils, type_check
+    for name, mod in (("chainer", chainer), ("chainer.backends", backends), ("chainer.backends.cuda", cuda),
+                      ("chainer.function", function), ("chainer.utils", utils),
+                      ("chainer.utils.type_check", type_check)):
+        sys.modules[name] = mod
+    spec = importlib.util.spec_from_file_location(
+        "reference_chainer_ctc", "/root/reference/models/chainer/ctc/ctc_loss_from_chainer.py")
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod
+
+
+def reference_ctc_cases():
+    """Costs and gradients of the reference's in-tree CTC on seeded cases: variable input lengths,
+    L=0, adjacent repeats, L+repeats == T (tight), a V=62 phone-sized and a V=200 case."""
+    ref = _import_reference_chainer_ctc()
+    rng = np.random.RandomState(2018)
+    out = {}
+    shapes = [(1, 1, 3, 1), (1, 2, 4, 1), (3, 12, 5, 4), (4, 40, 30, 12), (3, 31, 62, 14), (2, 30, 200, 8),
+              (2, 64, 7, 30), (4, 96, 30, 40)]
+    for i, (B, T, V, Lmax) in enumerate(shapes):
+        acts = (rng.randn(T, B, V) * (2.5 if i == 4 else 1.0)).astype(np.float32)
+        act_lens = rng.randint(max(1, T // 2), T + 1, size=B)
+        act_lens[0] = T
+        padded = np.zeros((B, max(Lmax, 1)), dtype=np.int32)
+        label_lens = []
+        for b in range(B):
+            L = rng.randint(0 if i == 2 else 1, Lmax + 1)
+            if i == 6 and b == 0:
+                L = Lmax
+            lab = rng.randint(1, V, size=L)
+            for j in range(1, L):
+                if rng.uniform() < 0.2:
+                    lab[j] = lab[j - 1]
+            while L + int(np.sum(lab[1:L] == lab[:L - 1])) > act_lens[b]:
+                L -= 1
+            padded[b, :L] = lab[:L]
+            label_lens.append(L)
+        label_lens = np.array(label_lens, dtype=np.int32)
+        fn = ref.ConnectionistTemporalClassification(0, reduce="no")       # blank = 0 as in ctc.py:267-269
+        inputs = (act_lens.astype(np.int32), label_lens, padded, acts.copy())
+        loss, = fn.forward(inputs)
+        grad = fn.backward(inputs, (np.ones(B, dtype=np.float32),))[3]
+        out["acts_%d" % i] = acts
+        out["labels_%d" % i] = np.concatenate([padded[b, :label_lens[b]] for b in range(B)]).astype(np.int32)
+        out["act_lens_%d" % i] = act_lens.astype(np.int32)
+        out["label_lens_%d" % i] = label_lens
+        out["costs_%d" % i] = np.asarray(loss, dtype=np.float32)
+        out["grads_%d" % i] = np.asarray(grad, dtype=np.float32)
+    out["n_cases"] = np.array(len(shapes))
+    np.savez_compressed(os.path.join(HERE, "ctc_reference_golden.npz"), **out)
+
+
 if __name__ == "__main__":
     greedy_cases()
     ctc_cases()
+    reference_ctc_cases()
     print("golden fixtures written to", HERE)

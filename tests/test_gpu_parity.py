@@ -54,6 +54,21 @@ def test_golden_vectors(golden_dir):
         assert np.max(np.abs(g - z["grads_%d" % i])) < GRAD_ATOL, i
 
 
+def test_reference_chainer_golden_vectors(golden_dir):
+    """Costs/gradients produced by the reference's own in-tree CTC
+    (models/chainer/ctc/ctc_loss_from_chainer.py, run by tests/golden/make_golden.py).  That code is a
+    float32 log-space recursion with -1e10 padding, so the fixture itself carries up to ~1.3e-4 of
+    rounding error against exact arithmetic at T=96 (measured against the fp64 oracle); the
+    gradient tolerance is 1e-4 up to T=64 and 5e-4 beyond for that reason."""
+    z = np.load(os.path.join(golden_dir, "ctc_reference_golden.npz"))
+    for i in range(int(z["n_cases"])):
+        acts = z["acts_%d" % i]
+        c, _, g = run_gpu(acts, z["labels_%d" % i], z["act_lens_%d" % i], z["label_lens_%d" % i])
+        assert np.allclose(c, z["costs_%d" % i], rtol=LOSS_RTOL), i
+        tol = GRAD_ATOL if acts.shape[0] <= 64 else 5e-4
+        assert np.max(np.abs(g - z["grads_%d" % i])) < tol, i
+
+
 def test_kats():
     acts = np.array([[[0.3, -1.2, 2.0]]], np.float32)
     check(acts, [], [1], [0])                       # T=1, L=0

@@ -148,6 +148,29 @@ def test_ctc_golden_vectors(golden_dir):
         assert np.max(np.abs(g2 - z["grads_%d" % i])) < 1e-6, i
 
 
+def test_reference_chainer_golden_vectors(golden_dir):
+    """PINS THE ORACLE TO THE REFERENCE: costs and gradients computed by the reference's own in-tree
+    CTC (models/chainer/ctc/ctc_loss_from_chainer.py:214-304, float32, imported from /root/reference
+    by tests/golden/make_golden.py).  The reference code is a float32 log-space recursion, so its
+    gradients differ from exact arithmetic by up to ~1.3e-4 at T=96; tolerances: cost 1e-5 relative,
+    gradient 1e-4 absolute up to T=64 and 5e-4 beyond."""
+    z = np.load(os.path.join(golden_dir, "ctc_reference_golden.npz"))
+    assert int(z["n_cases"]) >= 8
+    for i in range(int(z["n_cases"])):
+        acts = z["acts_%d" % i]
+        args = (acts, z["labels_%d" % i], z["act_lens_%d" % i], z["label_lens_%d" % i])
+        tol = 1e-4 if acts.shape[0] <= 64 else 5e-4
+        c, g = ctc_ref.ctc_cost_and_grad(*args)
+        assert np.allclose(c, z["costs_%d" % i], rtol=1e-5), i
+        assert np.max(np.abs(g - z["grads_%d" % i])) < tol, i
+        c2, g2 = ctc_cpu(*args, precision="f64")
+        assert np.allclose(c2, z["costs_%d" % i], rtol=1e-5), i
+        assert np.max(np.abs(g2 - z["grads_%d" % i])) < tol, i
+        c3, g3 = ctc_cpu(*args, precision="f32")       # the timed CPU baseline
+        assert np.allclose(c3, z["costs_%d" % i], rtol=1e-4), i
+        assert np.max(np.abs(g3 - z["grads_%d" % i])) < 2e-3, i
+
+
 def test_cpp_restatement_fp32_close():
     # the float instantiation (warp-ctc's ProbT=float) is only accurate to ~1e-3: loose bound
     rng = np.random.RandomState(8)
