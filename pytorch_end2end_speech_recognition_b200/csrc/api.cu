@@ -32,7 +32,13 @@ struct BatchTotals {
   long long scratch_units = 0;   // sum_b T_b * J_b
 };
 
-inline int groups_of(int L) { return (2 * L + 1 + 3) / 4; }
+// scratch units (32 bytes) per frame: the safe lattice stores 4 doubles per group of four states,
+// the fast lattice 36 bytes per group of eight states
+inline int groups_of(int L) {
+  const int j4 = (2 * L + 1 + 3) / 4, j8 = (2 * L + 1 + 7) / 8;
+  const int fast_units = (36 * j8 + 31) / 32;
+  return j4 > fast_units ? j4 : fast_units;
+}
 inline int em_width_of(int L) { return (L + 1 + 3) / 4 * 4; }
 
 int totals_from_lens(const int* label_lens, const int* act_lens, int T, int B, BatchTotals* out) {

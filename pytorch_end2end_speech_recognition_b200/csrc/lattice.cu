@@ -10,11 +10,12 @@ namespace {
 
 constexpr int kChunk = 4;  // frames between halo exchanges (K)
 
-// One CTA per utterance, longest lattice first (p.order).  The block-exponent fast path runs unless
+// One CTA per utterance, longest lattice first (p.order): per side NWMAX lattice warps and one reducer
+// warp (lattice_fast.cuh).  The block-exponent fast path runs unless
 // the utterance was flagged by K1 or is too long for the lattice window; when the fast path gives
 // up (range lost, zero probability) the same CTA redoes the utterance with the fp64 safe path.
 template <int K, int NWMAX>
-__global__ void __launch_bounds__(2 * NWMAX * 32, 1) lattice_kernel(CallParams p) {
+__global__ void __launch_bounds__(2 * (NWMAX + 1) * 32, 1) lattice_kernel(CallParams p) {
   extern __shared__ __align__(16) unsigned char smem[];
   const int b = p.order[blockIdx.x];
   const UttMeta m = p.meta[b];
@@ -64,14 +65,20 @@ cudaError_t launch_lattice_t(const CallParams& p, int max_L, cudaStream_t stream
   int l_cap = max_L;
   while (l_cap > 0 && fast_warps_needed<K>(l_cap) > NWMAX) --l_cap;
   const int rw = p.gathered ? (l_cap + 1 + 3) / 4 * 4 : (p.V + 3) / 4 * 4;
-  size_t smem = fast_smem_bytes<K, NWMAX>(l_cap, rw);
+  // the posterior row is not monotonic in L (its slot width steps): size for the worst L <= l_cap
+  size_t smem = 0;
+  for (int L = 0; L <= l_cap; ++L) {
+    const size_t s = fast_smem_bytes<K, NWMAX>(L, rw, p.V);
+    smem = s > smem ? s : smem;
+  }
   smem = smem > safe_smem_bytes(max_L) ? smem : safe_smem_bytes(max_L);
+  if (smem > 227 * 1024) return cudaErrorInvalidConfiguration;
   if (smem > 48 * 1024) {
     cudaError_t e = cudaFuncSetAttribute(lattice_kernel<K, NWMAX>,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
   }
-  lattice_kernel<K, NWMAX><<<p.B, 2 * NWMAX * 32, smem, stream>>>(p);
+  lattice_kernel<K, NWMAX><<<p.B, 2 * (NWMAX + 1) * 32, smem, stream>>>(p);
   return cudaGetLastError();
 }
 
@@ -80,9 +87,9 @@ cudaError_t launch_lattice_t(const CallParams& p, int max_L, cudaStream_t stream
 cudaError_t launch_lattice(const CallParams& p, int max_L, cudaStream_t stream) {
   if (p.B == 0) return cudaSuccess;
   const int nw = fast_warps_needed<kChunk>(max_L);
+  if (nw <= 1) return launch_lattice_t<kChunk, 1>(p, max_L, stream);
   if (nw <= 2) return launch_lattice_t<kChunk, 2>(p, max_L, stream);
-  if (nw <= 4) return launch_lattice_t<kChunk, 4>(p, max_L, stream);
-  return launch_lattice_t<kChunk, 8>(p, max_L, stream);
+  return launch_lattice_t<kChunk, 4>(p, max_L, stream);   // longer label sequences (L > 499) take the safe lattice
 }
 
 cudaError_t launch_cost_sum(const CallParams& p, cudaStream_t stream) {

@@ -1,35 +1,44 @@
-// Fast lattice: block-exponent fp32 alpha/beta recursion, forward and backward sweeps running
-// concurrently in one CTA and meeting in the middle.
+// Fast lattice (v4): block-exponent fp32 alpha/beta recursion, eight lattice states per lane,
+// packed f32x2 arithmetic, forward and backward sweeps running concurrently in one CTA and meeting
+// in the middle, posterior reduction and gradient-row write-back on dedicated reducer warps.
 //
 // Arithmetic.  The recursion of SURVEY Appendix A is evaluated in the LINEAR domain:
 //     alpha_t(s) = y_t(l'_s) * (alpha_{t-1}(s) + alpha_{t-1}(s-1) + [skip] alpha_{t-1}(s-2))
-// Each lane owns four consecutive lattice states as fp32 mantissas plus ONE shared int32
-// power-of-two exponent that is renormalised after every frame, so the representable range is
-// unbounded while the inner loop is pure FADD/FMUL + integer exponent arithmetic: no exp/log at
-// all (the softmax probabilities y come from K1).  Relative rounding error is ~6e-8 per operation
-// independent of |log alpha| -- this is what keeps T=1500 utterances inside the 1e-4 gradient
-// tolerance where an fp32 log-space recursion does not ("numerics").
-// The one weakness -- a state more than ~2^-110 below its group's largest state loses bits -- is
-// harmless unless that state could carry posterior mass; phase 2 bounds that mass for every group
-// and frame, and if the bound is not negligible (FLAG_PRECISION_LOST) the utterance is redone by
-// the fp64 safe lattice in the same CTA.
+// Each lane owns eight consecutive lattice positions as fp32 mantissas plus ONE int32 power-of-two
+// exponent that is renormalised after every frame, so the representable range is unbounded while
+// the inner loop is FADD2/FMUL2/FFMA2 + integer exponent arithmetic: no exp/log at all (the softmax
+// probabilities y come from K1).  Relative rounding error is ~6e-8 per operation independent of
+// |log alpha| -- this is what keeps T=1500 utterances inside the 1e-4 gradient tolerance where an
+// fp32 log-space recursion does not ("numerics").  The one weakness -- a state more than
+// ~2^-110 below its lane's largest state loses bits -- is harmless unless that state could carry
+// posterior mass; phase 2 bounds that mass for every lane and frame, and if the bound is not
+// negligible (FLAG_PRECISION_LOST) the utterance is redone by the fp64 safe lattice in the same CTA.
 //
-// Schedule.  One CTA per utterance.  Warps [0,NW) sweep forward (alpha, t = 0,1,..), warps
-// [NWMAX, NWMAX+NW) sweep backward (beta, t = T-1,T-2,..; beta is the same recursion on the
-// reversed label sequence).  Phase 1: each side covers half of the frames and stores its
-// pre-emission values to the scratch.  Phase 2 (after one CTA barrier): each side continues through
-// the other half, multiplies its fresh values with the stored ones of the opposite side --
-// posterior(t,s) = alpha_t(s) * beta'_t(s) / P -- and subtracts the per-symbol occupancy from the
-// gradient row (which K1 filled with the softmax) with one RED per (frame, symbol).  Sequential
-// depth is T frames instead of 2T and only half of alpha and beta ever goes through HBM.
+// Packing.  The eight values of a lane live in four 64-bit registers, pair j = elements (j, j+4)
+// (forward side: low word = element j; backward side: low word = element j+4).  With that pairing
+// the neighbour terms of the recursion are again whole pairs -- element j-1 of pair j is pair j-1 --
+// so one FADD2/FFMA2/FMUL2 (sm_100 packed fp32) advances two lattice states, and the mirrored pairing
+// of the two sides makes the stored values of one side load as ready-made pairs on the other.
 //
-// Lattice layout.  Lane l of warp w holds positions base_w + 4l .. +3 (a "group"), base_w =
-// w*(128-2K): consecutive warp windows overlap by a halo of 2K positions.  Dependencies only point
-// downwards (s-1, s-2), so a warp can run K frames without talking to its neighbour while the
+// Schedule.  One CTA per utterance, 2*(NWMAX+1) warps.  Per side: NW lattice warps (forward: alpha,
+// t = 0,1,..; backward: beta on the reversed label sequence, t = T-1,T-2,..) and one reducer warp.
+// Phase 1: each side covers half of the frames and stores its pre-emission values to the scratch.
+// Phase 2 (after one CTA barrier): each side continues through the other half, multiplies its fresh
+// values with the stored ones of the opposite side -- posterior(t,s) = alpha_t(s) * beta'_t(s) / P --
+// and scatters the label posteriors into a symbol-sorted shared-memory row.  The reducer warp of the
+// side sums that row per symbol one chunk behind the lattice warps (named-barrier hand-off, double
+// buffered) and writes  grad[t,b,:] = y - occupancy  as ONE coalesced V-wide row per frame (small
+// vocabularies), or one RED per (frame, symbol) into the softmax rows K1 left (gathered mode).
+// Sequential depth is T frames instead of 2T, only half of alpha and beta ever goes through HBM, and
+// nothing but the recursion itself is on the critical path.
+//
+// Lattice layout.  Lane l of warp w holds positions base_w + 8l .. +7, base_w = w*(256-2K):
+// consecutive warp windows overlap by a halo of 2K positions (one lane for K = 4).  Dependencies only
+// point downwards (s-1, s-2), so a warp can run K frames without talking to its neighbour while the
 // garbage creeping up from its window bottom stays inside the halo; every K frames ("chunk") the
-// warps exchange halos through shared memory -- ONE block barrier per K frames.  Neighbour states
-// inside a warp travel by __shfl_up.  Emission rows and the opposite side's stored groups for
-// chunk c+1 are prefetched with cp.async while chunk c computes.
+// lattice warps of a side exchange halos through shared memory -- ONE named barrier per K frames.
+// Neighbour states inside a warp travel by __shfl_up.  Emission rows are staged two chunks ahead and
+// the opposite side's stored records seven frames ahead with cp.async.
 #pragma once
 
 #include "lattice_common.cuh"
@@ -37,10 +46,19 @@
 
 namespace b200ctc {
 
-constexpr int kEZero = -(1 << 28);  // exponent of an all-zero group
+constexpr int kEZero = -(1 << 28);  // exponent of an all-zero lane
+constexpr int kRowsRing = 4;        // emission-row chunks in flight (staged two chunks ahead + reducer lag)
+constexpr int kOthRing = 8;         // per-thread ring of the opposite side's records (frames)
+constexpr int kOthAhead = 7;        // prefetch distance in frames (must be <= 2K so that row groups retire in time)
 
-__device__ __forceinline__ void named_bar(int id, int count) {
+// ---------------------------------------------------------------------------------------------
+// PTX helpers
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void named_bar_sync(int id, int count) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory");
+}
+__device__ __forceinline__ void named_bar_arrive(int id, int count) {
+  asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(count) : "memory");
 }
 __device__ __forceinline__ void cp_async_4(void* smem, const void* gmem) {
   unsigned s = (unsigned)__cvta_generic_to_shared(smem);
@@ -55,139 +73,254 @@ __device__ __forceinline__ void cp_async_16(void* smem, const void* gmem) {
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(s), "l"(gmem) : "memory");
 }
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
 // 2^d for d <= 0 (0 when d < -126)
 __device__ __forceinline__ float pow2_neg(int d) { return __int_as_float(max(d + 127, 0) << 23); }
 // 2^d clamped to [2^-127 -> 0, 2^127]
 __device__ __forceinline__ float pow2_clamped(int d) { return __int_as_float(min(max(d + 127, 0), 254) << 23); }
 
-template <int K>
-__host__ __device__ inline int fast_warps_needed(int L) {
-  const int P = 4 * ((2 * L + 1 + 3) / 4);
-  const int own = 128 - 2 * K;
-  return P <= 128 ? 1 : 1 + (P - 128 + own - 1) / own;
+// ---- packed fp32 pairs (FADD2 / FMUL2 / FFMA2 on sm_100) ----
+typedef unsigned long long f2;
+__device__ __forceinline__ f2 f2_pack(float lo, float hi) {
+  f2 r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+  return r;
+}
+__device__ __forceinline__ float f2_lo(f2 v) {
+  float a, b;
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(v));
+  return a;
+}
+__device__ __forceinline__ float f2_hi(f2 v) {
+  float a, b;
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(v));
+  return b;
+}
+__device__ __forceinline__ f2 f2_add(f2 a, f2 b) {
+  f2 r;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+__device__ __forceinline__ f2 f2_mul(f2 a, f2 b) {
+  f2 r;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+__device__ __forceinline__ f2 f2_fma(f2 a, f2 b, f2 c) {
+  f2 r;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+  return r;
+}
+__device__ __forceinline__ float fmax3(float a, float b, float c) {
+  float r;
+  asm("max.f32 %0, %1, %2, %3;" : "=f"(r) : "f"(a), "f"(b), "f"(c));
+  return r;
+}
+// pair (element j, element j+4) in the packing of SIDE
+template <int SIDE>
+__device__ __forceinline__ f2 mk(float xj, float xj4) { return SIDE ? f2_pack(xj4, xj) : f2_pack(xj, xj4); }
+template <int SIDE>
+__device__ __forceinline__ float el_j(f2 p) { return SIDE ? f2_hi(p) : f2_lo(p); }
+template <int SIDE>
+__device__ __forceinline__ float el_j4(f2 p) { return SIDE ? f2_lo(p) : f2_hi(p); }
+__device__ __forceinline__ float f2_max(f2 a, f2 b) {  // max over the four floats of two pairs
+  return fmaxf(fmaxf(f2_lo(a), f2_hi(a)), fmaxf(f2_lo(b), f2_hi(b)));
 }
 
 // ---------------------------------------------------------------------------------------------
-// shared memory
+// geometry shared by host (shared-memory sizing) and device
 // ---------------------------------------------------------------------------------------------
+template <int K>
+__host__ __device__ inline int fast_warps_needed(int L) {
+  const int P = 8 * ((2 * L + 1 + 7) / 8);
+  const int own = 256 - 2 * K;
+  return P <= 256 ? 1 : 1 + (P - 256 + own - 1) / own;
+}
+// Symbol-sorted posterior row: every symbol of the label sequence owns whole rows of C slots.
+__host__ __device__ inline int post_row_width(int L, int V) {
+  const int n_sym = L < V - 1 ? L : V - 1;
+  const int avg = n_sym > 0 ? (L + n_sym - 1) / n_sym : 1;
+  const int want = avg + avg / 2 + 2;
+  return want <= 4 ? 4 : want <= 12 ? 12 : want <= 20 ? 20 : 28;  // odd number of 16-byte chunks: conflict-free LDS.128
+}
+__host__ __device__ inline int post_rows_max(int L, int V) {
+  const int n_sym = L < V - 1 ? L : V - 1;
+  return L / post_row_width(L, V) + n_sym + 1;
+}
+
 struct FastSideSmem {
-  float* rows;    // [2][K][RWS]     staged emission rows (+ a zero slot at index RW)
-  float4* oth_m;  // [2][K][NT]      opposite side's stored mantissas, one slot per thread
-  int* oth_e;     // [2][K][NT]      opposite side's stored exponents
-  float* post;    // [2][K][P]       posteriors of the frames of a chunk
-  float4* halo_m; // [2][NWMAX][K/2] halo groups
-  int* halo_e;    // [2][NWMAX][K/2]
-  float* red_m;   // [NWMAX]
-  int* red_e;     // [NWMAX]
-  int* pos;       // [L]             post-row position of the k-th label in symbol order
+  float* rows;      // [kRowsRing][K][RWS]  staged emission rows (+ a zero slot at index RW)
+  float4* oth_a;    // [kOthRing][NT]       opposite side's stored pairs 0,1 of this thread's group
+  float4* oth_b;    // [kOthRing][NT]       ... pairs 2,3
+  int* oth_e;       // [kOthRing][NT]       ... exponent
+  float* post;      // [2][K][PS]           symbol-sorted label posteriors + blank partials + dump slot
+  float4* halo_a;   // [2][NWMAX]           halo lanes (one per warp for K = 4)
+  float4* halo_b;   // [2][NWMAX]
+  int* halo_e;      // [2][NWMAX]
+  float* red_m;     // [NWMAX]
+  int* red_e;       // [NWMAX]
+  float* rowsum;    // [Rmax]               reducer scratch
+  float* occ_row;   // [Vpad]               reducer scratch (small vocabularies)
 };
 
+template <int NWMAX>
+__host__ __device__ inline int post_stride(int L, int V) {  // floats per frame in the post buffer
+  return post_row_width(L, V) * post_rows_max(L, V) + NWMAX * 32 + 4;
+}
+
 template <int K, int NWMAX>
-__host__ __device__ inline size_t fast_side_bytes(int L, int RW) {
-  const size_t J = (size_t)(2 * L + 1 + 3) / 4, P = 4 * J, NT = NWMAX * 32;
+__host__ __device__ inline size_t fast_side_bytes(int L, int RW, int V) {
+  const size_t NT = NWMAX * 32;
   size_t b = 0;
-  b += 2 * K * NT * 16;                   // oth_m
-  b += 2 * NWMAX * (K / 2) * 16;          // halo_m
-  b += 2 * K * (size_t)(RW + 4) * 4;      // rows
-  b += 2 * K * P * 4;                     // post
-  b += 2 * K * NT * 4;                    // oth_e
-  b += 2 * NWMAX * (K / 2) * 4;           // halo_e
-  b += NWMAX * 8;                         // red
-  b += (size_t)(L + 4) * 4;               // pos
+  b += (size_t)kOthRing * NT * 16 * 2;                       // oth_a, oth_b
+  b += 2 * NWMAX * 16 * 2;                                   // halo_a, halo_b
+  b += (size_t)kRowsRing * K * (size_t)(RW + 4) * 4;         // rows
+  b += 2 * (size_t)K * post_stride<NWMAX>(L, V) * 4;         // post
+  b += (size_t)kOthRing * NT * 4;                            // oth_e
+  b += 2 * NWMAX * 4;                                        // halo_e
+  b += NWMAX * 8;                                            // red
+  b += (size_t)(post_rows_max(L, V) + 4) * 4;                // rowsum
+  b += (size_t)((V + 3) / 4 * 4 + 4) * 4;                    // occ_row
   return (b + 15) / 16 * 16;
 }
 template <int K, int NWMAX>
-__host__ __device__ inline size_t fast_smem_bytes(int L, int RW) {
-  size_t common = (size_t)(8 + 4 * L + 8) * 4;  // control words, lab, sorted, seg_start, seg_sym
+__host__ __device__ inline size_t fast_smem_bytes(int L, int RW, int V) {
+  // control words, lab, sorted, seg_start, seg_sym, slot_of_label, row_start
+  size_t common = (size_t)(16 + 6 * L + 16) * 4;
   common = (common + 15) / 16 * 16;
-  return common + 2 * fast_side_bytes<K, NWMAX>(L, RW) + 16;
+  return common + 2 * fast_side_bytes<K, NWMAX>(L, RW, V) + 16;
 }
 
 template <int K, int NWMAX>
-__device__ __forceinline__ FastSideSmem carve_fast_side(unsigned char* base, int L, int RW) {
-  const size_t J = (size_t)(2 * L + 1 + 3) / 4, P = 4 * J, NT = NWMAX * 32;
+__device__ __forceinline__ FastSideSmem carve_fast_side(unsigned char* base, int L, int RW, int V) {
+  const size_t NT = NWMAX * 32;
   FastSideSmem s;
   unsigned char* p = base;
-  s.oth_m = reinterpret_cast<float4*>(p);  p += 2 * K * NT * 16;
-  s.halo_m = reinterpret_cast<float4*>(p); p += 2 * NWMAX * (K / 2) * 16;
-  s.rows = reinterpret_cast<float*>(p);    p += 2 * K * (size_t)(RW + 4) * 4;
-  s.post = reinterpret_cast<float*>(p);    p += 2 * K * P * 4;
-  s.oth_e = reinterpret_cast<int*>(p);     p += 2 * K * NT * 4;
-  s.halo_e = reinterpret_cast<int*>(p);    p += 2 * NWMAX * (K / 2) * 4;
+  s.oth_a = reinterpret_cast<float4*>(p);  p += (size_t)kOthRing * NT * 16;
+  s.oth_b = reinterpret_cast<float4*>(p);  p += (size_t)kOthRing * NT * 16;
+  s.halo_a = reinterpret_cast<float4*>(p); p += 2 * NWMAX * 16;
+  s.halo_b = reinterpret_cast<float4*>(p); p += 2 * NWMAX * 16;
+  s.rows = reinterpret_cast<float*>(p);    p += (size_t)kRowsRing * K * (size_t)(RW + 4) * 4;
+  s.post = reinterpret_cast<float*>(p);    p += 2 * (size_t)K * post_stride<NWMAX>(L, V) * 4;
+  s.oth_e = reinterpret_cast<int*>(p);     p += (size_t)kOthRing * NT * 4;
+  s.halo_e = reinterpret_cast<int*>(p);    p += 2 * NWMAX * 4;
   s.red_m = reinterpret_cast<float*>(p);   p += NWMAX * 4;
   s.red_e = reinterpret_cast<int*>(p);     p += NWMAX * 4;
-  s.pos = reinterpret_cast<int*>(p);
+  s.rowsum = reinterpret_cast<float*>(p);  p += (size_t)(post_rows_max(L, V) + 4) * 4;
+  s.occ_row = reinterpret_cast<float*>(p);
   return s;
 }
 
+// Utterance-wide tables (shared by both sides).
+struct FastCommon {
+  int* abort_flag;     // set by any thread: the fast result cannot be trusted / used
+  int* lab;            // [L]
+  SymbolIndex ix;      // sorted / seg_start / seg_sym / n_seg
+  int* slot_of_label;  // [L]    slot of label i in the symbol-sorted posterior row
+  int* row_start;      // [n_seg+1] first row of every symbol segment
+  int* n_rows;         // total rows R
+};
+
+// named barrier ids (0 is __syncthreads)
+__device__ __forceinline__ int bar_halo(int side) { return 1 + side * 6; }
+__device__ __forceinline__ int bar_total(int side) { return 2 + side * 6; }
+__device__ __forceinline__ int bar_ready(int side, int par) { return 3 + side * 6 + par; }
+__device__ __forceinline__ int bar_free(int side, int par) { return 5 + side * 6 + par; }
+constexpr int kBarMidpoint = 13;
+
 // ---------------------------------------------------------------------------------------------
-// per-lane state
+// per-lane state of a lattice warp
 // ---------------------------------------------------------------------------------------------
 struct LaneConst {
-  int idx0, idx1, idx2, idx3;  // index of each state's symbol in the staged emission row (zero slot if invalid)
-  float k0, k1, k2, k3;        // 1.0 where the skip transition into the state is allowed, else 0.0
-  int s_lo, s_hi;              // lattice-state range of the group (s_hi = s_lo + 3)
-  bool owned;                  // this lane's group belongs to the warp (not to the halo) and exists
-  int group;                   // global position group (pos0 / 4)
+  int idx[4];       // emission-row index of the four label positions (zero slot if the position is a dummy)
+  int idx_blank;    // emission-row index of the blank
+  f2 K0, K1;        // skip-transition factors (1.0 allowed / 0.0 not) of label pairs (0,2) and (1,3)
+  int pos[4];       // slot of the four label positions in the symbol-sorted posterior row (dump slot if dummy)
+  int s_lo;         // lattice state of the lane's lowest state (s_hi = s_lo + 7)
+  bool owned;       // this lane's group belongs to the warp (not to the halo) and exists
+  int group;        // global position group (pos0 / 8)
 };
 
 struct LaneState {
-  float v0, v1, v2, v3;
+  f2 A[4];
   int e;
 };
 
-// One frame of the recursion for one lane.  Outputs the pre-emission sums (acc*, exponent E) and the
-// new emission-weighted values w* at the same exponent; updates st with the renormalised state.
-__device__ __forceinline__ void lattice_frame(LaneState& st, const LaneConst& lc, const float* __restrict__ row,
-                                              bool lane0, float& acc0, float& acc1, float& acc2, float& acc3,
-                                              float& w0, float& w1, float& w2, float& w3, int& E) {
-  const float n1 = __shfl_up_sync(0xffffffffu, st.v3, 1);
-  const float n2 = __shfl_up_sync(0xffffffffu, st.v2, 1);
+// One frame of the recursion for one lane.  ACC: pre-emission sums at exponent E; W: the new
+// emission-weighted values at the same exponent; st: renormalised state.  Returns max(W).
+template <int SIDE>
+__device__ __forceinline__ float lattice_frame(LaneState& st, const LaneConst& lc, const float* __restrict__ row,
+                                               bool lane0, f2 (&ACC)[4], f2 (&W)[4], int& E) {
+  const float a7 = el_j4<SIDE>(st.A[3]), a6 = el_j4<SIDE>(st.A[2]);
+  const float n1 = __shfl_up_sync(0xffffffffu, a7, 1);
+  const float n2 = __shfl_up_sync(0xffffffffu, a6, 1);
   int ne = __shfl_up_sync(0xffffffffu, st.e, 1);
+  // emissions: one broadcast load for the four blank positions, one gather per label position
+  const float yb = row[lc.idx_blank];
+  const float y0 = row[lc.idx[0]], y1 = row[lc.idx[1]], y2 = row[lc.idx[2]], y3 = row[lc.idx[3]];
   if (lane0) ne = kEZero;                      // nothing below the window: scales n1, n2 to zero
   E = max(st.e, ne);
   const float so = pow2_neg(st.e - E), sn = pow2_neg(ne - E);
-  const float a0 = st.v0 * so, a1 = st.v1 * so, a2 = st.v2 * so, a3 = st.v3 * so;
+  const f2 so2 = f2_pack(so, so);
+  f2 As[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) As[j] = f2_mul(st.A[j], so2);
   const float b1 = n1 * sn, b2 = n2 * sn;
-  acc0 = fmaf(lc.k0, b2, a0 + b1);
-  acc1 = fmaf(lc.k1, b1, a1 + a0);
-  acc2 = fmaf(lc.k2, a0, a2 + a1);
-  acc3 = fmaf(lc.k3, a1, a3 + a2);
-  w0 = acc0 * row[lc.idx0];
-  w1 = acc1 * row[lc.idx1];
-  w2 = acc2 * row[lc.idx2];
-  w3 = acc3 * row[lc.idx3];
-  const float mx = fmaxf(fmaxf(w0, w1), fmaxf(w2, w3));
-  // renormalise: largest mantissa -> [1,2).  mx == 0 (or NaN from garbage): the group is empty.
+  const f2 Q1 = mk<SIDE>(b1, el_j<SIDE>(As[3]));   // elements (-1, 3)
+  ACC[0] = f2_add(As[0], Q1);
+  ACC[1] = f2_add(As[1], As[0]);
+  ACC[2] = f2_add(As[2], As[1]);
+  ACC[3] = f2_add(As[3], As[2]);
+  const f2 YB = f2_pack(yb, yb);
+  const f2 YL0 = mk<SIDE>(y0, y2), YL1 = mk<SIDE>(y1, y3);
+  if (SIDE == 0) {   // labels on the odd elements: pairs 1 = (1,5) and 3 = (3,7)
+    ACC[1] = f2_fma(lc.K0, Q1, ACC[1]);            // two below (1,5) is (-1,3)
+    ACC[3] = f2_fma(lc.K1, As[1], ACC[3]);         // two below (3,7) is (1,5)
+    W[0] = f2_mul(ACC[0], YB);  W[1] = f2_mul(ACC[1], YL0);
+    W[2] = f2_mul(ACC[2], YB);  W[3] = f2_mul(ACC[3], YL1);
+  } else {           // labels on the even elements: pairs 0 = (0,4) and 2 = (2,6)
+    const f2 Q2 = mk<SIDE>(b2, el_j<SIDE>(As[2])); // elements (-2, 2)
+    ACC[0] = f2_fma(lc.K0, Q2, ACC[0]);
+    ACC[2] = f2_fma(lc.K1, As[0], ACC[2]);         // two below (2,6) is (0,4)
+    W[0] = f2_mul(ACC[0], YL0); W[1] = f2_mul(ACC[1], YB);
+    W[2] = f2_mul(ACC[2], YL1); W[3] = f2_mul(ACC[3], YB);
+  }
+  const float m01 = fmax3(f2_lo(W[0]), f2_hi(W[0]), f2_lo(W[1]));
+  const float m23 = fmax3(f2_hi(W[1]), f2_lo(W[2]), f2_hi(W[2]));
+  const float mx = fmaxf(fmax3(m01, f2_lo(W[3]), f2_hi(W[3])), m23);
+  // renormalise: largest mantissa -> [1,2).  mx == 0 (or NaN from garbage): the lane is empty.
   const int eb = __float_as_int(mx) >> 23;                       // biased exponent
   const bool nz = mx > 0.f;
   const float sc = nz ? __int_as_float((254 - eb) << 23) : 0.f;  // 2^(127-eb)
-  st.v0 = w0 * sc; st.v1 = w1 * sc; st.v2 = w2 * sc; st.v3 = w3 * sc;
+  const f2 sc2 = f2_pack(sc, sc);
+#pragma unroll
+  for (int j = 0; j < 4; ++j) st.A[j] = f2_mul(W[j], sc2);
   st.e = nz ? E + eb - 127 : kEZero;
+  return mx;
 }
 
 template <int SIDE>
 struct FastCtx {
   const CallParams* p;
-  int b, T, L, S, J, P, NW, RW, RWS;
-  int w, lane, tid_side, nt_side;
+  int b, T, L, S, J8, P, NW, RW, RWS, PS, RC;
+  int w, lane, tid_side;
   FastSideSmem sm;
-  SymbolIndex ix;
-  float4* scr_m;   // [T][J]   stored pre-emission mantissas, in the READER's group order
-  int* scr_e;      // [T][J]
+  float4* scr_a;   // [T][J8]  stored pre-emission pairs 0,1 in the READER's group order and packing
+  float4* scr_b;   // [T][J8]  ... pairs 2,3
+  int* scr_e;      // [T][J8]
   int row_vec, per_row;                       // emission rows: floats per cp.async, copies per row
-  const float* row_src; long long row_stride; // element (t) at row_src + t*row_stride
+  const float* row_src; long long row_stride; // frame t at row_src + t*row_stride
   __device__ __forceinline__ int frame_of(int n) const { return SIDE ? T - 1 - n : n; }
 };
 
-// Stage the emission rows of the kc frames starting at step n0: one warp per frame.
+// Stage the emission rows of the kc frames starting at step n0 into ring slot `slot`: one warp per frame.
 template <int K, int SIDE>
-__device__ __forceinline__ void stage_rows(const FastCtx<SIDE>& c, int buf, int n0, int kc) {
+__device__ __forceinline__ void stage_rows(const FastCtx<SIDE>& c, int slot, int n0, int kc) {
   for (int j = c.w; j < kc; j += c.NW) {
     const float* src = c.row_src + (long long)c.frame_of(n0 + j) * c.row_stride;
-    float* dst = c.sm.rows + (size_t)(buf * K + j) * c.RWS;
+    float* dst = c.sm.rows + (size_t)(slot * K + j) * c.RWS;
     if (c.row_vec == 4) {
       for (int e = c.lane; e < c.per_row; e += 32) cp_async_16(dst + 4 * e, src + 4 * e);
     } else if (c.row_vec == 2) {
@@ -198,63 +331,19 @@ __device__ __forceinline__ void stage_rows(const FastCtx<SIDE>& c, int buf, int 
   }
 }
 
-// Every thread fetches the opposite side's stored group for ITS OWN group and each frame of the
-// chunk into its private shared-memory slot (no cross-thread visibility needed).
-template <int K, int SIDE>
-__device__ __forceinline__ void stage_other(const FastCtx<SIDE>& c, const LaneConst& lc, int buf, int n0, int kc) {
-  if (!lc.owned) return;
-  const int NT = blockDim.x >> 1;
-  float4* dm = c.sm.oth_m + (size_t)buf * K * NT + c.tid_side;
-  int* de = c.sm.oth_e + (size_t)buf * K * NT + c.tid_side;
-  const long long step = SIDE ? -(long long)c.J : (long long)c.J;
-  long long off = (long long)c.frame_of(n0) * c.J + lc.group;
-#pragma unroll
-  for (int j = 0; j < K; ++j) {
-    if (j < kc) {
-      cp_async_16(dm + j * NT, c.scr_m + off);
-      cp_async_4(de + j * NT, c.scr_e + off);
-      off += step;
-    }
+// Prefetch the opposite side's stored record of this thread's group for step n into its private ring slot.
+template <int SIDE>
+__device__ __forceinline__ void prefetch_other(const FastCtx<SIDE>& c, const LaneConst& lc, int NT, int n) {
+  if (lc.owned && n < c.T) {
+    const int slot = (n & (kOthRing - 1)) * NT + c.tid_side;
+    const long long off = (long long)c.frame_of(n) * c.J8 + lc.group;
+    cp_async_16(c.sm.oth_a + slot, c.scr_a + off);
+    cp_async_16(c.sm.oth_b + slot, c.scr_b + off);
+    cp_async_4(c.sm.oth_e + slot, c.scr_e + off);
   }
 }
 
-// Occupancy update for the frames of one finished phase-2 chunk: one deterministic sum and one RED
-// per (frame, symbol).  Executed by all threads of the side; frames are spread over the warps.
-template <int K, int SIDE>
-__device__ __forceinline__ void reduce_chunk(const FastCtx<SIDE>& c, int pbuf, int n0, int kc) {
-  const CallParams& p = *c.p;
-  const int P = c.P, NW = c.NW;
-  const float* post = c.sm.post + (size_t)pbuf * K * P;
-  const int n_seg = *c.ix.n_seg;
-  // work item = (frame j, slice): slice 0 is the blank (a whole warp), slices 1.. cover 32 symbols each
-  const int n_slices = 1 + (n_seg + 31) / 32;
-  for (int item = c.w; item < kc * n_slices; item += NW) {
-    const int j = item / n_slices, slice = item - j * n_slices;
-    const float* row = post + (size_t)j * P;
-    float* grow = p.grads + ((long long)c.frame_of(n0 + j) * p.B + c.b) * p.V;
-    if (slice == 0) {
-      // blank: lattice states with even index.  forward: even positions; backward: odd positions.
-      const float4* row4 = reinterpret_cast<const float4*>(row);
-      float acc = 0.f;
-      for (int gq = c.lane; gq < c.J; gq += 32) {
-        const float4 q = row4[gq];
-        acc += SIDE ? (q.y + q.w) : (q.x + q.z);
-      }
-      acc = warp_sum(acc);
-      if (c.lane == 0) atomicAdd(grow + p.blank, -acc);
-    } else {
-      const int u = (slice - 1) * 32 + c.lane;
-      if (u < n_seg) {
-        float acc = 0.f;
-        const int k1 = c.ix.seg_start[u + 1];
-        for (int k = c.ix.seg_start[u]; k < k1; ++k) acc += row[c.sm.pos[k]];
-        atomicAdd(grow + c.ix.seg_sym[u], -acc);
-      }
-    }
-  }
-}
-
-// Everything a side's warps carry through the sweep.
+// Everything a lattice warp carries through the sweep.
 struct SweepState {
   LaneState st;
   LaneConst lc;
@@ -263,74 +352,109 @@ struct SweepState {
   bool lost;
 };
 
-// One chunk (kc <= K frames starting at step n0, staged in buffer `buf`).
+// Posterior of one frame for one lane: fresh values W (exponent E) times the stored record of the
+// opposite side, normalised by P.  Scatters the label posteriors and the blank partial sum.
+// Called by every lane of an in-band warp (warp collectives inside); only owned lanes have effects.
+template <int SIDE>
+__device__ __forceinline__ void posterior_frame(const FastCtx<SIDE>& c, SweepState& ss, const f2 (&W)[4], float wmax,
+                                                int E, int NT, int n, int t, float* __restrict__ post, bool write_post) {
+  const LaneConst& lc = ss.lc;
+  const int slot = (n & (kOthRing - 1)) * NT + c.tid_side;
+  const float4 qa = c.sm.oth_a[slot], qb = c.sm.oth_b[slot];
+  const int oe = c.sm.oth_e[slot];
+  f2 O[4] = {f2_pack(qa.x, qa.y), f2_pack(qa.z, qa.w), f2_pack(qb.x, qb.y), f2_pack(qb.z, qb.w)};
+  // States outside the reachable band carry dead (own side) or never-written (other side) values.
+  // Only the warps at the band edges have such lanes.
+  const int hi_t = min(c.S, 2 * (t + 1)), lo_t = max(0, c.S - 2 * (c.T - t));
+  const bool all_in = lc.s_lo >= lo_t && lc.s_lo + 7 < hi_t;
+  if (!__all_sync(0xffffffffu, all_in || !lc.owned)) {
+    // element i of the lane is lattice state s_lo + i (forward) or s_lo + 7 - i (backward)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int sj = SIDE ? lc.s_lo + 7 - j : lc.s_lo + j;
+      const int sj4 = SIDE ? sj - 4 : sj + 4;
+      const float oj = (sj >= lo_t && sj < hi_t) ? el_j<SIDE>(O[j]) : 0.f;
+      const float oj4 = (sj4 >= lo_t && sj4 < hi_t) ? el_j4<SIDE>(O[j]) : 0.f;
+      O[j] = mk<SIDE>(oj, oj4);
+    }
+  }
+  // posterior = w * o * 2^dexp / mP.  Both mantissas may be far below 1 (their lane's maximum is
+  // elsewhere), so dexp can legitimately exceed 127: beyond 2^60 the scale is applied in two halves.
+  const int dexp = E + oe - ss.eP;
+  f2 PO[4];
+  if (dexp <= 60) {
+    const float s = pow2_clamped(dexp) * ss.inv_mP;   // inv_mP in (0.5, 1]
+    const f2 s2 = f2_pack(s, s);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) PO[j] = f2_mul(f2_mul(W[j], O[j]), s2);
+  } else {
+    const int dhalf = dexp >> 1;
+    const float sa = pow2_clamped(min(dhalf, 120)) * ss.inv_mP;
+    const float sb = pow2_clamped(min(dexp - dhalf, 120));
+    const f2 sa2 = f2_pack(sa, sa), sb2 = f2_pack(sb, sb);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) PO[j] = f2_mul(f2_mul(W[j], sa2), f2_mul(O[j], sb2));
+  }
+  // Range check.  A state that sits more than 2^-110 below its lane's largest value may have lost
+  // bits (on either side).  Its posterior is bounded by
+  //   2^-110 * max(own lane) * max(other lane) * 2^dexp / mP;
+  // if that bound is not negligible (> 2^-24) the block-exponent result cannot be trusted.  The own
+  // maximum runs over ALL eight states: dead states (too late to finish) share the exponent.
+  // Evaluated on the exponent fields, so it cannot overflow or underflow.
+  const float omax = fmaxf(f2_max(O[0], O[1]), f2_max(O[2], O[3]));
+  const int bound = (__float_as_int(wmax) >> 23) + (__float_as_int(omax) >> 23) - 254 + dexp;
+  ss.lost |= lc.owned && (wmax > 0.f) && (omax > 0.f) && (bound > 110 - 24 - 2);
+  if (write_post && lc.owned) {
+    constexpr int jL0 = SIDE ? 0 : 1, jL1 = SIDE ? 2 : 3, jB0 = SIDE ? 1 : 0, jB1 = SIDE ? 3 : 2;
+    post[lc.pos[0]] = el_j<SIDE>(PO[jL0]);
+    post[lc.pos[1]] = el_j<SIDE>(PO[jL1]);
+    post[lc.pos[2]] = el_j4<SIDE>(PO[jL0]);
+    post[lc.pos[3]] = el_j4<SIDE>(PO[jL1]);
+    const f2 bs = f2_add(PO[jB0], PO[jB1]);
+    post[c.RC + c.tid_side] = f2_lo(bs) + f2_hi(bs);
+  }
+}
+
+// One chunk (kc <= K frames starting at step n0; emission rows in ring slot `rslot`).
 template <int K, bool PH2, int SIDE>
-__device__ __forceinline__ void run_chunk(const FastCtx<SIDE>& c, SweepState& ss, int buf, int n0, int kc,
-                                          bool write_post) {
-  const int T = c.T, S = c.S, J = c.J, P = c.P;
+__device__ __forceinline__ void run_chunk(const FastCtx<SIDE>& c, SweepState& ss, int rslot, int pbuf, int n0, int kc,
+                                          bool write_post, int NT) {
+  const int T = c.T, S = c.S, J8 = c.J8;
   const LaneConst& lc = ss.lc;
   const bool lane0 = c.lane == 0;
-  const int NT = blockDim.x >> 1;
-  const float* rows = c.sm.rows + (size_t)buf * K * c.RWS;
-  const float4* oth_m = c.sm.oth_m + (size_t)buf * K * NT + c.tid_side;
-  const int* oth_e = c.sm.oth_e + (size_t)buf * K * NT + c.tid_side;
-  float* post = c.sm.post + (size_t)buf * K * P + 4 * lc.group;
+  const float* rows = c.sm.rows + (size_t)rslot * K * c.RWS;
+  float* post = c.sm.post + (size_t)pbuf * K * c.PS;
   int t = c.frame_of(n0);
   // scratch slot of this lane's group for the opposite side's reader (mirrored group order)
-  long long scr_off = (long long)t * J + (J - 1 - lc.group);
-  const long long scr_step = SIDE ? -(long long)J : (long long)J;
+  long long scr_off = (long long)t * J8 + (J8 - 1 - lc.group);
+  const long long scr_step = SIDE ? -(long long)J8 : (long long)J8;
 #pragma unroll
   for (int j = 0; j < K; ++j) {
     if (j < kc) {
+      if (PH2) {
+        prefetch_other<SIDE>(c, lc, NT, n0 + j + kOthAhead);
+        cp_async_commit();
+      }
       const int hi_t = min(S, 2 * (t + 1)), lo_t = max(0, S - 2 * (T - t));
       const bool in_band = !(ss.win_s_hi < lo_t || ss.win_s_lo >= hi_t);   // warp-uniform
+      if (PH2) cp_async_wait<kOthAhead>();   // every thread: retires this frame's record and, in time, the staged rows
       if (in_band) {
-        float a0, a1, a2, a3, w0, w1, w2, w3; int E;
-        lattice_frame(ss.st, lc, rows + j * c.RWS, lane0, a0, a1, a2, a3, w0, w1, w2, w3, E);
-        if (lc.owned) {
-          if (!PH2) {
-            // stored reversed at the mirrored group: exactly the slot order of the reader's lane
-            c.scr_m[scr_off] = make_float4(a3, a2, a1, a0);
+        f2 ACC[4], W[4]; int E;
+        const float wmax = lattice_frame<SIDE>(ss.st, lc, rows + j * c.RWS, lane0, ACC, W, E);
+        if (!PH2) {
+          if (lc.owned) {
+            // the reader's pair j is this lane's pair 3-j (mirrored group, mirrored packing)
+            asm volatile("st.global.v2.b64 [%0], {%1, %2};" ::"l"(c.scr_a + scr_off), "l"(ACC[3]), "l"(ACC[2]) : "memory");
+            asm volatile("st.global.v2.b64 [%0], {%1, %2};" ::"l"(c.scr_b + scr_off), "l"(ACC[1]), "l"(ACC[0]) : "memory");
             c.scr_e[scr_off] = E;
-          } else {
-            const float4 om = oth_m[j * NT];
-            const int oe = oth_e[j * NT];
-            // posterior = w * om * 2^dexp / mP.  Both mantissas may be far below 1 (their group's
-            // maximum is elsewhere), so dexp can legitimately exceed 127: apply it in two halves.
-            const int dexp = E + oe - ss.eP;
-            const int dhalf = dexp >> 1;
-            const float sa = pow2_clamped(min(dhalf, 120)) * ss.inv_mP;   // inv_mP in (0.5, 1]
-            const float sb = pow2_clamped(min(dexp - dhalf, 120));
-            float u0 = w0, u1 = w1, u2 = w2, u3 = w3;
-            float o0 = om.x, o1 = om.y, o2 = om.z, o3 = om.w;
-            // States outside the reachable band carry dead (own side) or never-written (other side)
-            // values.  Only the warps at the band edges have such lanes.
-            const bool all_in = lc.s_lo >= lo_t && lc.s_hi < hi_t;
-            if (!__all_sync(__activemask(), all_in)) {
-              const int sA = SIDE ? lc.s_hi : lc.s_lo, d = SIDE ? -1 : 1;   // state of slot 0, direction
-              const bool b0 = (sA >= lo_t && sA < hi_t), b1 = (sA + d >= lo_t && sA + d < hi_t);
-              const bool b2 = (sA + 2 * d >= lo_t && sA + 2 * d < hi_t), b3 = (sA + 3 * d >= lo_t && sA + 3 * d < hi_t);
-              u0 = b0 ? u0 : 0.f; u1 = b1 ? u1 : 0.f; u2 = b2 ? u2 : 0.f; u3 = b3 ? u3 : 0.f;
-              o0 = b0 ? o0 : 0.f; o1 = b1 ? o1 : 0.f; o2 = b2 ? o2 : 0.f; o3 = b3 ? o3 : 0.f;
-            }
-            float4 po;
-            po.x = (u0 * sa) * (o0 * sb); po.y = (u1 * sa) * (o1 * sb);
-            po.z = (u2 * sa) * (o2 * sb); po.w = (u3 * sa) * (o3 * sb);
-            // Range check.  A state that sits more than 2^-110 below its group's largest value may
-            // have lost bits (on either side).  Its posterior is bounded by
-            //   2^-110 * max(own group) * max(other group) * 2^dexp / mP;
-            // if that bound is not negligible (> 2^-24) the block-exponent result cannot be trusted.
-            // The own maximum runs over ALL four states: dead states (too late to finish) share the
-            // exponent.  Evaluated on the exponent fields, so it cannot overflow or underflow.
-            const float umax = fmaxf(fmaxf(w0, w1), fmaxf(w2, w3));
-            const float omax = fmaxf(fmaxf(o0, o1), fmaxf(o2, o3));
-            const int bound = (__float_as_int(umax) >> 23) + (__float_as_int(omax) >> 23) - 254 + dexp;
-            ss.lost |= (umax > 0.f) && (omax > 0.f) && (bound > 110 - 24 - 2);
-            if (write_post) *reinterpret_cast<float4*>(post + j * P) = po;
           }
+        } else {
+          posterior_frame<SIDE>(c, ss, W, wmax, E, NT, n0 + j, t, post + (size_t)j * c.PS, write_post);
         }
       } else if (PH2 && write_post && lc.owned) {
-        *reinterpret_cast<float4*>(post + j * P) = make_float4(0.f, 0.f, 0.f, 0.f);
+        float* pr = post + (size_t)j * c.PS;
+        pr[lc.pos[0]] = 0.f; pr[lc.pos[1]] = 0.f; pr[lc.pos[2]] = 0.f; pr[lc.pos[3]] = 0.f;
+        pr[c.RC + c.tid_side] = 0.f;
       }
       t += SIDE ? -1 : 1;
       scr_off += scr_step;
@@ -338,65 +462,62 @@ __device__ __forceinline__ void run_chunk(const FastCtx<SIDE>& c, SweepState& ss
   }
 }
 
-// Chunk boundary: publish the halo, take the abort snapshot, ONE side barrier, import the halo.
-// Returns true when the side must leave the fast path.
+// Chunk boundary of the lattice warps: publish the halo lane, ONE side barrier, import the halo.
 template <int K, int NWMAX, int SIDE>
-__device__ __forceinline__ bool chunk_boundary(const FastCtx<SIDE>& c, SweepState& ss, int cc, int* abort_flag,
-                                               int* abort_seen) {
-  constexpr int HG = K / 2;
+__device__ __forceinline__ void chunk_boundary(const FastCtx<SIDE>& c, SweepState& ss, int cc, int* abort_flag) {
+  static_assert(K == 4, "one halo lane per warp");
   const int hb = cc & 1, NW = c.NW, w = c.w, lane = c.lane;
-  if (w + 1 < NW && lane >= 32 - HG) {
-    const int slot = (hb * NWMAX + w) * HG + (lane - (32 - HG));
-    c.sm.halo_m[slot] = make_float4(ss.st.v0, ss.st.v1, ss.st.v2, ss.st.v3);
-    c.sm.halo_e[slot] = ss.st.e;
+  LaneState& st = ss.st;
+  if (w + 1 < NW && lane == 31) {
+    const int slot = hb * NWMAX + w;
+    c.sm.halo_a[slot] = make_float4(f2_lo(st.A[0]), f2_hi(st.A[0]), f2_lo(st.A[1]), f2_hi(st.A[1]));
+    c.sm.halo_b[slot] = make_float4(f2_lo(st.A[2]), f2_hi(st.A[2]), f2_lo(st.A[3]), f2_hi(st.A[3]));
+    c.sm.halo_e[slot] = st.e;
   }
-  if (__any_sync(0xffffffffu, ss.lost) && lane == 0) *abort_flag = 1;
-  if (c.tid_side == 0) abort_seen[SIDE * 2 + hb] = *(volatile int*)abort_flag;
-  cp_async_wait_all();
-  named_bar(1 + SIDE, NW * 32);
-  if (w > 0 && lane < HG) {
-    const int slot = (hb * NWMAX + (w - 1)) * HG + lane;
-    const float4 hv = c.sm.halo_m[slot];
-    ss.st.v0 = hv.x; ss.st.v1 = hv.y; ss.st.v2 = hv.z; ss.st.v3 = hv.w;
-    ss.st.e = c.sm.halo_e[slot];
+  if (ss.lost) *abort_flag = 1;
+  named_bar_sync(bar_halo(SIDE), NW * 32);
+  if (w > 0 && lane == 0) {
+    const int slot = hb * NWMAX + (w - 1);
+    const float4 ha = c.sm.halo_a[slot], hv = c.sm.halo_b[slot];
+    st.A[0] = f2_pack(ha.x, ha.y); st.A[1] = f2_pack(ha.z, ha.w);
+    st.A[2] = f2_pack(hv.x, hv.y); st.A[3] = f2_pack(hv.z, hv.w);
+    st.e = c.sm.halo_e[slot];
   }
-  return abort_seen[SIDE * 2 + hb] != 0;
 }
 
-struct FastCommon {
-  int* abort_flag;   // set by any thread: leave the fast path
-  int* abort_seen;   // [side][parity] snapshots, [4] midpoint snapshot
-  int* lab;
-  SymbolIndex ix;
-};
+// Total probability from the per-warp partial sums (every thread of the side, reducer included,
+// evaluates the same expression on the same shared values).  Returns false when the fast path must
+// give up; otherwise mP in [1,2) and eP with P = mP * 2^eP, and log2(P) for the cost.
+__device__ __forceinline__ bool total_probability(const FastSideSmem& sm, int NW, float& inv_mP, int& eP, double& log2P) {
+  int Emax = kEZero;
+  for (int i = 0; i < NW; ++i) Emax = max(Emax, sm.red_e[i]);
+  float tot = 0.f;
+  for (int i = 0; i < NW; ++i) tot += sm.red_m[i] * pow2_neg(sm.red_e[i] - Emax);
+  if (!(tot > 0.f) || !(tot < INFINITY) || Emax <= kEZero / 2) return false;
+  const int eb = (__float_as_int(tot) >> 23) - 127;
+  const float mP = tot * pow2_clamped(-eb);
+  inv_mP = 1.0f / mP;
+  eP = Emax + eb;
+  log2P = (double)Emax + log2((double)tot);
+  return true;
+}
 
-// One side's sweep (all warps w < NW of that side).
 template <int K, int NWMAX, int SIDE>
-__device__ void fast_side_sweep(const CallParams& p, int b, const UttMeta& m, const FastCommon& cm,
-                                unsigned char* side_smem, int w, int lane) {
-  constexpr int H = 2 * K;          // halo positions
-  constexpr int HG = K / 2;         // halo groups (lanes)
-  constexpr int OWN = 128 - H;
-
-  FastCtx<SIDE> c;
+__device__ __forceinline__ void fill_ctx(FastCtx<SIDE>& c, const CallParams& p, int b, const UttMeta& m,
+                                         unsigned char* side_smem, int w, int lane) {
   c.p = &p; c.b = b;
-  const int T = m.T, L = m.L;
-  c.T = T; c.L = L; c.S = 2 * L + 1; c.J = m.J; c.P = 4 * m.J;
-  c.NW = fast_warps_needed<K>(L);
+  c.T = m.T; c.L = m.L; c.S = 2 * m.L + 1; c.J8 = (c.S + 7) / 8; c.P = 8 * c.J8;
+  c.NW = fast_warps_needed<K>(m.L);
   c.RW = p.gathered ? m.W : (p.V + 3) / 4 * 4;
   c.RWS = c.RW + 4;
-  c.w = w; c.lane = lane; c.tid_side = w * 32 + lane; c.nt_side = c.NW * 32;
-  c.ix = cm.ix;
-  const int J = c.J, P = c.P, S = c.S, NW = c.NW;
-  c.sm = carve_fast_side<K, NWMAX>(side_smem, L, c.RW);
-  const int* lab = cm.lab;
-
-  // scratch rows
+  c.PS = post_stride<NWMAX>(m.L, p.V);
+  c.RC = c.PS - NWMAX * 32 - 4;                 // label slots come first, then the blank partials, then the dump slot
+  c.w = w; c.lane = lane; c.tid_side = w * 32 + lane;
+  c.sm = carve_fast_side<K, NWMAX>(side_smem, m.L, c.RW, p.V);
   unsigned char* scr = p.scratch + m.scratch_off * kGroupBytes;
-  c.scr_m = reinterpret_cast<float4*>(scr);
-  c.scr_e = reinterpret_cast<int*>(scr + (size_t)T * J * 16);
-
-  // emission row source
+  c.scr_a = reinterpret_cast<float4*>(scr);
+  c.scr_b = reinterpret_cast<float4*>(scr + (size_t)c.T * c.J8 * 16);
+  c.scr_e = reinterpret_cast<int*>(scr + (size_t)c.T * c.J8 * 32);
   if (p.gathered) {
     c.row_src = p.em + m.em_off; c.row_stride = m.W; c.row_vec = 4; c.per_row = m.W / 4;
   } else {
@@ -405,122 +526,152 @@ __device__ void fast_side_sweep(const CallParams& p, int b, const UttMeta& m, co
     c.row_vec = (p.V % 4 == 0 && a % 16 == 0) ? 4 : ((p.V % 2 == 0 && a % 8 == 0) ? 2 : 1);
     c.per_row = p.V / c.row_vec;
   }
+}
 
-  // ---- side prologue: zero slots of the row buffers, label positions in this side's post rows ----
-  for (int i = c.tid_side; i < 2 * K; i += c.nt_side) c.sm.rows[(size_t)i * c.RWS + c.RW] = 0.f;
-  for (int k = c.tid_side; k < L; k += c.nt_side) {
-    const int s = 2 * cm.ix.sorted[k] + 1;
-    c.sm.pos[k] = SIDE ? (P - 1 - s) : s;
-  }
+struct SidePlan {
+  int M_side, nc1, nc2, n_chunks;
+};
+template <int K, int SIDE>
+__device__ __forceinline__ SidePlan side_plan(int T) {
+  SidePlan s;
+  s.M_side = SIDE ? (T / 2) : (T - T / 2);      // frames this side covers in phase 1
+  s.nc1 = (s.M_side + K - 1) / K;
+  s.nc2 = (T - s.M_side + K - 1) / K;
+  s.n_chunks = s.nc1 + s.nc2;
+  return s;
+}
+
+// ---------------------------------------------------------------------------------------------
+// lattice warps of one side
+// ---------------------------------------------------------------------------------------------
+template <int K, int NWMAX, int SIDE>
+__device__ void fast_side_sweep(const CallParams& p, int b, const UttMeta& m, const FastCommon& cm,
+                                unsigned char* side_smem, int w, int lane) {
+  constexpr int H = 2 * K;          // halo positions (one lane)
+  constexpr int OWN = 256 - H;
+  constexpr int NT = NWMAX * 32;
+
+  FastCtx<SIDE> c;
+  fill_ctx<K, NWMAX, SIDE>(c, p, b, m, side_smem, w, lane);
+  const int T = c.T, L = c.L, S = c.S, J8 = c.J8, P = c.P, NW = c.NW;
+  const int* lab = cm.lab;
 
   // ---- per-lane constants ----
   SweepState ss;
   LaneConst& lc = ss.lc;
   const int base_w = w * OWN;
-  const int pos0 = base_w + 4 * lane;
-  lc.group = pos0 >> 2;
-  lc.owned = ((w == 0) || (lane >= HG)) && (lc.group < J);
-  lc.s_lo = SIDE ? (P - 1 - pos0 - 3) : pos0;
-  lc.s_hi = lc.s_lo + 3;
+  const int pos0 = base_w + 8 * lane;
+  lc.group = pos0 >> 3;
+  lc.owned = ((w == 0) || (lane >= 1)) && (lc.group < J8);
+  lc.s_lo = SIDE ? (P - 1 - pos0 - 7) : pos0;
+  lc.idx_blank = p.gathered ? 0 : p.blank;
   {
-    int idx[4]; float kk[4];
+    float kk[4];
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      const int q = pos0 + i;
+    for (int mslot = 0; mslot < 4; ++mslot) {
+      const int q = pos0 + (SIDE ? 2 * mslot : 2 * mslot + 1);   // label positions of the lane
       const int s = SIDE ? (P - 1 - q) : q;
-      const bool ok = (q < P) && (s >= 0) && (s < S);
-      idx[i] = c.RW;   // zero slot
-      kk[i] = 0.f;
+      const bool ok = (q < P) && (s >= 0) && (s < S);             // s is odd by construction
+      lc.idx[mslot] = c.RW;            // zero slot
+      lc.pos[mslot] = c.PS - 4;        // dump slot
+      kk[mslot] = 0.f;
       if (ok) {
-        const int li = s >> 1;                       // label index of an odd state
-        if (s & 1) {
-          idx[i] = p.gathered ? li + 1 : lab[li];
-          const bool sk = SIDE ? (s + 2 < S && lab[li] != lab[li + 1]) : (s >= 3 && lab[li] != lab[li - 1]);
-          kk[i] = sk ? 1.f : 0.f;
-        } else {
-          idx[i] = p.gathered ? 0 : p.blank;
-        }
+        const int li = s >> 1;
+        lc.idx[mslot] = p.gathered ? li + 1 : lab[li];
+        lc.pos[mslot] = cm.slot_of_label[li];
+        const bool sk = SIDE ? (s + 2 < S && lab[li] != lab[li + 1]) : (s >= 3 && lab[li] != lab[li - 1]);
+        kk[mslot] = sk ? 1.f : 0.f;
       }
     }
-    lc.idx0 = idx[0]; lc.idx1 = idx[1]; lc.idx2 = idx[2]; lc.idx3 = idx[3];
-    lc.k0 = kk[0]; lc.k1 = kk[1]; lc.k2 = kk[2]; lc.k3 = kk[3];
+    lc.K0 = mk<SIDE>(kk[0], kk[2]);
+    lc.K1 = mk<SIDE>(kk[1], kk[3]);
   }
   {
-    const int win_lo_pos = base_w, win_hi_pos = min(base_w + 127, P - 1);
+    const int win_lo_pos = base_w, win_hi_pos = min(base_w + 255, P - 1);
     ss.win_s_lo = SIDE ? (P - 1 - win_hi_pos) : win_lo_pos;
     ss.win_s_hi = SIDE ? (P - 1 - win_lo_pos) : win_hi_pos;
   }
   // ---- initial state: delta on the first lattice state of this side's sweep ----
-  ss.st.v0 = ss.st.v1 = ss.st.v2 = ss.st.v3 = 0.f; ss.st.e = kEZero;
-  ss.lost = false; ss.inv_mP = 0.f; ss.eP = 0;
   {
-    const int q_start = SIDE ? (P - S) : 0;   // backward: 4J - S dummy positions come first
-    if (w == 0 && q_start >= pos0 && q_start < pos0 + 4) {
-      const int i = q_start - pos0;
-      if (i == 0) ss.st.v0 = 1.f; else if (i == 1) ss.st.v1 = 1.f; else if (i == 2) ss.st.v2 = 1.f; else ss.st.v3 = 1.f;
+    float v[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) v[i] = 0.f;
+    ss.st.e = kEZero;
+    const int q_start = SIDE ? (P - S) : 0;   // backward: 8*J8 - S dummy positions come first
+    if (w == 0 && q_start >= pos0 && q_start < pos0 + 8) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) if (q_start - pos0 == i) v[i] = 1.f;
       ss.st.e = 0;
     }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) ss.st.A[j] = mk<SIDE>(v[j], v[j + 4]);
   }
+  ss.lost = false; ss.inv_mP = 0.f; ss.eP = 0;
 
-  const int M_side = SIDE ? (T / 2) : (T - T / 2);      // frames this side covers in phase 1
-  const int nc1 = (M_side + K - 1) / K;
-  const int nc2 = (T - M_side + K - 1) / K;
-  const int n_chunks = nc1 + nc2;
-  const int bar_id = 1 + SIDE;
-  const int n_side_threads = NW * 32;
+  const SidePlan pl = side_plan<K, SIDE>(T);
+  const int M_side = pl.M_side, nc1 = pl.nc1, nc2 = pl.nc2, n_chunks = pl.n_chunks;
   auto chunk_n0 = [&](int cc) { return cc < nc1 ? cc * K : M_side + (cc - nc1) * K; };
   auto chunk_kc = [&](int cc) { return cc < nc1 ? min(K, M_side - cc * K) : min(K, T - (M_side + (cc - nc1) * K)); };
+  auto stage = [&](int cc) {
+    if (cc < n_chunks) stage_rows<K, SIDE>(c, cc % kRowsRing, chunk_n0(cc), chunk_kc(cc));
+    cp_async_commit();
+  };
   int* abort_flag = cm.abort_flag;
-  int* abort_seen = cm.abort_seen;
 
-  // emission rows of the first chunk
-  if (n_chunks > 0) stage_rows<K, SIDE>(c, 0, chunk_n0(0), chunk_kc(0));
-  cp_async_commit();
-  cp_async_wait_all();
-  named_bar(bar_id, n_side_threads);
-
-  bool aborted = false;
+  // zero slots of the row buffers; emission rows of the first two chunks
+  for (int i = c.tid_side; i < kRowsRing * K; i += NW * 32) {
+    float* z = c.sm.rows + (size_t)i * c.RWS + c.RW;
+    z[0] = 0.f; z[1] = 0.f; z[2] = 0.f; z[3] = 0.f;
+  }
+  stage(0);
+  stage(1);
+  cp_async_wait<1>();
+  named_bar_sync(bar_halo(SIDE), NW * 32);
 
   // ================================ phase 1 ================================
-  for (int cc = 0; cc < nc1 && !aborted; ++cc) {
-    if (cc + 1 < n_chunks) stage_rows<K, SIDE>(c, (cc + 1) & 1, chunk_n0(cc + 1), chunk_kc(cc + 1));
-    cp_async_commit();
-    run_chunk<K, false, SIDE>(c, ss, cc & 1, chunk_n0(cc), chunk_kc(cc), false);
-    aborted = chunk_boundary<K, NWMAX, SIDE>(c, ss, cc, abort_flag, abort_seen);
+  for (int cc = 0; cc < nc1; ++cc) {
+    stage(cc + 2);
+    run_chunk<K, false, SIDE>(c, ss, cc % kRowsRing, 0, chunk_n0(cc), chunk_kc(cc), false, NT);
+    cp_async_wait<1>();                                   // rows of chunk cc+1 have landed
+    chunk_boundary<K, NWMAX, SIDE>(c, ss, cc, abort_flag);
   }
 
   // ================================ midpoint ================================
-  // Both sides always meet here exactly once (even when one of them has already given up).
-  if (threadIdx.x == 0) abort_seen[4] = *(volatile int*)abort_flag;
-  named_bar(3, 2 * n_side_threads);
-  if (abort_seen[4]) aborted = true;
-  if (aborted || nc2 == 0) return;
+  // Both sides' lattice warps meet here exactly once: everything phase 1 stored is visible afterwards.
+  named_bar_sync(kBarMidpoint, 2 * NW * 32);
+  if (nc2 == 0) return;
 
-  // the opposite side's groups for the first phase-2 chunk could not be prefetched earlier
-  stage_other<K, SIDE>(c, lc, nc1 & 1, chunk_n0(nc1), chunk_kc(nc1));
-  cp_async_commit();
-  cp_async_wait_all();
+  // the opposite side's records of the first kOthAhead phase-2 frames, one commit group per frame
+#pragma unroll
+  for (int d = 0; d < kOthAhead; ++d) {
+    prefetch_other<SIDE>(c, lc, NT, M_side + d);
+    cp_async_commit();
+  }
+  cp_async_wait<kOthAhead - 1>();
 
   // ---- total probability P = sum_s alpha_t(s) beta'_t(s) at the first phase-2 frame (state copy) ----
   {
-    const int buf = nc1 & 1, n0 = chunk_n0(nc1);
-    const int NT = blockDim.x >> 1;
+    const int rslot = nc1 % kRowsRing, n0 = M_side;
     LaneState tmp = ss.st;
     float part = 0.f; int pe = kEZero;
     const int t = c.frame_of(n0);
     const int hi_t = min(S, 2 * (t + 1)), lo_t = max(0, S - 2 * (T - t));
     if (!(ss.win_s_hi < lo_t || ss.win_s_lo >= hi_t)) {
-      float a0, a1, a2, a3, w0, w1, w2, w3; int E;
-      lattice_frame(tmp, lc, c.sm.rows + (size_t)buf * K * c.RWS, lane == 0, a0, a1, a2, a3, w0, w1, w2, w3, E);
+      f2 ACC[4], W[4]; int E;
+      lattice_frame<SIDE>(tmp, lc, c.sm.rows + (size_t)rslot * K * c.RWS, lane == 0, ACC, W, E);
       if (lc.owned) {
-        const float4 om = c.sm.oth_m[(size_t)buf * K * NT + c.tid_side];
-        const int oe = c.sm.oth_e[(size_t)buf * K * NT + c.tid_side];
-        const int sA = SIDE ? lc.s_hi : lc.s_lo, d = SIDE ? -1 : 1;
+        const int slot = (n0 & (kOthRing - 1)) * NT + c.tid_side;
+        const float4 qa = c.sm.oth_a[slot], qb = c.sm.oth_b[slot];
+        const int oe = c.sm.oth_e[slot];
+        const f2 O[4] = {f2_pack(qa.x, qa.y), f2_pack(qa.z, qa.w), f2_pack(qb.x, qb.y), f2_pack(qb.z, qb.w)};
         float sum = 0.f;
-        if (sA >= lo_t && sA < hi_t) sum += w0 * om.x;
-        if (sA + d >= lo_t && sA + d < hi_t) sum += w1 * om.y;
-        if (sA + 2 * d >= lo_t && sA + 2 * d < hi_t) sum += w2 * om.z;
-        if (sA + 3 * d >= lo_t && sA + 3 * d < hi_t) sum += w3 * om.w;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const int sj = SIDE ? lc.s_lo + 7 - j : lc.s_lo + j;
+          const int sj4 = SIDE ? sj - 4 : sj + 4;
+          if (sj >= lo_t && sj < hi_t) sum += el_j<SIDE>(W[j]) * el_j<SIDE>(O[j]);
+          if (sj4 >= lo_t && sj4 < hi_t) sum += el_j4<SIDE>(W[j]) * el_j4<SIDE>(O[j]);
+        }
         if (sum > 0.f) { part = sum; pe = E + oe; }
       }
     }
@@ -530,38 +681,106 @@ __device__ void fast_side_sweep(const CallParams& p, int b, const UttMeta& m, co
     float scaled = part * pow2_neg(pe - emax);
     scaled = warp_sum(scaled);
     if (lane == 0) { c.sm.red_m[w] = scaled; c.sm.red_e[w] = emax; }
-    named_bar(bar_id, n_side_threads);
-    int Emax = kEZero;
-    for (int i = 0; i < NW; ++i) Emax = max(Emax, c.sm.red_e[i]);
-    float tot = 0.f;
-    for (int i = 0; i < NW; ++i) tot += c.sm.red_m[i] * pow2_neg(c.sm.red_e[i] - Emax);
-    if (!(tot > 0.f) || !(tot < INFINITY) || Emax <= kEZero / 2) {
+    named_bar_sync(bar_total(SIDE), (NW + 1) * 32);     // lattice warps + the side's reducer
+    double log2P;
+    if (!total_probability(c.sm, NW, ss.inv_mP, ss.eP, log2P)) {
       // zero / underflowed / garbage total probability: the safe lattice decides
       if (c.tid_side == 0) *abort_flag = 1;
-      aborted = true;                          // every thread of the side computed the same `tot`
-    } else {
-      // normalise P = tot * 2^Emax to a mantissa in [1,2)
-      const int eb = (__float_as_int(tot) >> 23) - 127;
-      const float mP = tot * pow2_clamped(-eb);
-      ss.inv_mP = 1.0f / mP; ss.eP = Emax + eb;
-      if (SIDE == 1 && c.tid_side == 0)
-        p.costs[b] = (float)(-((double)Emax + log2((double)tot)) * 0.69314718055994530942);
+      return;                                            // every thread of the side computed the same value
     }
+    if (SIDE == 1 && c.tid_side == 0) p.costs[b] = (float)(-log2P * 0.69314718055994530942);
   }
-  if (aborted) return;
   // cost-only calls still walk phase 2 (for the range check) but neither store posteriors nor update rows
   const bool write_post = p.grads != nullptr;
 
   // ================================ phase 2 ================================
-  for (int cc = nc1; cc < n_chunks && !aborted; ++cc) {
-    if (cc + 1 < n_chunks) {
-      stage_rows<K, SIDE>(c, (cc + 1) & 1, chunk_n0(cc + 1), chunk_kc(cc + 1));
-      stage_other<K, SIDE>(c, lc, (cc + 1) & 1, chunk_n0(cc + 1), chunk_kc(cc + 1));
+  for (int cc = nc1; cc < n_chunks; ++cc) {
+    const int k2 = cc - nc1, par = k2 & 1;
+    if (write_post && k2 >= 2) named_bar_sync(bar_free(SIDE, par), (NW + 1) * 32);   // reducer done with post[par]
+    stage(cc + 2);
+    run_chunk<K, true, SIDE>(c, ss, cc % kRowsRing, par, chunk_n0(cc), chunk_kc(cc), write_post, NT);
+    // rows of chunk cc+1 were committed more than kOthAhead groups ago: the per-frame waits retired them
+    chunk_boundary<K, NWMAX, SIDE>(c, ss, cc, abort_flag);
+    if (write_post) named_bar_arrive(bar_ready(SIDE, par), (NW + 1) * 32);            // post[par] of chunk cc is complete
+  }
+  if (ss.lost) *abort_flag = 1;
+  cp_async_wait<0>();
+}
+
+// ---------------------------------------------------------------------------------------------
+// reducer warp of one side: per-symbol occupancy of every phase-2 frame, gradient rows
+// ---------------------------------------------------------------------------------------------
+template <int K, int NWMAX, int SIDE>
+__device__ void fast_side_reduce(const CallParams& p, int b, const UttMeta& m, const FastCommon& cm,
+                                 unsigned char* side_smem, int lane) {
+  FastCtx<SIDE> c;
+  fill_ctx<K, NWMAX, SIDE>(c, p, b, m, side_smem, NWMAX, lane);
+  const int T = c.T, NW = c.NW, V = p.V;
+  const SidePlan pl = side_plan<K, SIDE>(T);
+  if (pl.nc2 == 0) return;
+  named_bar_sync(bar_total(SIDE), (NW + 1) * 32);
+  {
+    float inv_mP; int eP; double log2P;
+    if (!total_probability(c.sm, NW, inv_mP, eP, log2P)) return;
+  }
+  if (p.grads == nullptr) return;
+
+  const int C4 = post_row_width(c.L, V) / 4;          // 16-byte chunks per row
+  const int R = *cm.n_rows, n_seg = *cm.ix.n_seg;
+  const int NTa = NW * 32;
+  const bool gathered = p.gathered != 0;
+  for (int cc = pl.nc1; cc < pl.n_chunks; ++cc) {
+    const int k2 = cc - pl.nc1, par = k2 & 1;
+    const int n0 = pl.M_side + k2 * K, kc = min(K, T - n0);
+    named_bar_sync(bar_ready(SIDE, par), (NW + 1) * 32);
+    for (int j = 0; j < kc; ++j) {
+      const float* post = c.sm.post + (size_t)(par * K + j) * c.PS;
+      const int t = c.frame_of(n0 + j);
+      float* grow = p.grads + ((long long)t * p.B + b) * V;
+      // 1. row sums: one lane per row of C slots
+      for (int r0 = 0; r0 < R; r0 += 32) {
+        const int r = r0 + lane;
+        if (r < R) {
+          const float4* row4 = reinterpret_cast<const float4*>(post) + (size_t)r * C4;
+          float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+          for (int q = 0; q < C4; ++q) {
+            const float4 v = row4[q];
+            a0 += v.x; a1 += v.y; a2 += v.z; a3 += v.w;
+          }
+          c.sm.rowsum[r] = (a0 + a1) + (a2 + a3);
+        }
+      }
+      // 2. blank: partial sums of the lattice threads
+      float accb = 0.f;
+      for (int i = lane; i < NTa; i += 32) accb += post[c.RC + i];
+      accb = warp_sum(accb);
+      __syncwarp();
+      // 3. per symbol: its rows are adjacent
+      if (!gathered) {
+        const float* yrow = c.sm.rows + (size_t)((cc % kRowsRing) * K + j) * c.RWS;
+        for (int u = lane; u < n_seg; u += 32) {
+          float tot = 0.f;
+          for (int r = cm.row_start[u]; r < cm.row_start[u + 1]; ++r) tot += c.sm.rowsum[r];
+          c.sm.occ_row[cm.ix.seg_sym[u]] = tot;
+        }
+        if (lane == 0) c.sm.occ_row[p.blank] = accb;
+        __syncwarp();
+        for (int v = lane; v < V; v += 32) grow[v] = yrow[v] - c.sm.occ_row[v];   // one coalesced row
+        __syncwarp();
+        for (int u = lane; u < n_seg; u += 32) c.sm.occ_row[cm.ix.seg_sym[u]] = 0.f;
+        if (lane == 0) c.sm.occ_row[p.blank] = 0.f;
+        __syncwarp();
+      } else {
+        for (int u = lane; u < n_seg; u += 32) {
+          float tot = 0.f;
+          for (int r = cm.row_start[u]; r < cm.row_start[u + 1]; ++r) tot += c.sm.rowsum[r];
+          atomicAdd(grow + cm.ix.seg_sym[u], -tot);
+        }
+        if (lane == 0) atomicAdd(grow + p.blank, -accb);
+        __syncwarp();
+      }
     }
-    cp_async_commit();
-    run_chunk<K, true, SIDE>(c, ss, cc & 1, chunk_n0(cc), chunk_kc(cc), write_post);
-    aborted = chunk_boundary<K, NWMAX, SIDE>(c, ss, cc, abort_flag, abort_seen);
-    if (!aborted && write_post) reduce_chunk<K, SIDE>(c, cc & 1, chunk_n0(cc), chunk_kc(cc));
+    if (cc + 2 < pl.n_chunks) named_bar_arrive(bar_free(SIDE, par), (NW + 1) * 32);
   }
 }
 
@@ -570,39 +789,80 @@ __device__ void fast_side_sweep(const CallParams& p, int b, const UttMeta& m, co
 // caller reads it after a __syncthreads()).
 template <int K, int NWMAX>
 __device__ void lattice_fast_utterance(const CallParams& p, int b, unsigned char* smem, int** smem_abort) {
-  static_assert(K % 2 == 0 && K >= 2 && K <= 16, "K must be even");
   const UttMeta m = p.meta[b];
   const int L = m.L;
   const int NW = fast_warps_needed<K>(L);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int side = warp / NWMAX;
-  const int w = warp - side * NWMAX;
+  const int side = warp / (NWMAX + 1);
+  const int w = warp - side * (NWMAX + 1);
 
   // ---- shared memory: common part, then one block per side ----
   FastCommon cm;
   int* ip = reinterpret_cast<int*>(smem);
-  cm.abort_flag = ip;            ip += 1;
-  cm.abort_seen = ip;            ip += 7;
+  cm.abort_flag = ip;            ip += 8;
+  cm.ix.n_seg = ip;              ip += 4;
+  cm.n_rows = ip;                ip += 4;
   cm.lab = ip;                   ip += L;
   cm.ix.sorted = ip;             ip += L;
   cm.ix.seg_start = ip;          ip += L + 1;
   cm.ix.seg_sym = ip;            ip += L + 1;
-  cm.ix.n_seg = ip;              ip += 1;
+  cm.slot_of_label = ip;         ip += L;
+  cm.row_start = ip;             ip += L + 2;
   size_t common = (size_t)(reinterpret_cast<unsigned char*>(ip) - smem);
   common = (common + 15) / 16 * 16;
   const int RW = p.gathered ? m.W : (p.V + 3) / 4 * 4;
-  const size_t side_bytes = fast_side_bytes<K, NWMAX>(L, RW);
+  const size_t side_bytes = fast_side_bytes<K, NWMAX>(L, RW, p.V);
   *smem_abort = cm.abort_flag;
 
   // ---- prologue (all threads of the CTA) ----
   for (int i = threadIdx.x; i < L; i += blockDim.x) cm.lab[i] = p.labels[m.lab_off + i];
-  if (threadIdx.x < 8) cm.abort_flag[threadIdx.x] = 0;  // abort_flag + abort_seen[0..6]
+  if (threadIdx.x < 8) cm.abort_flag[threadIdx.x] = 0;
+  // posterior buffers start all-zero: padding slots and the blank partials of idle threads are never written
+  {
+    const int PS = post_stride<NWMAX>(L, p.V);
+    for (int sd = 0; sd < 2; ++sd) {
+      FastSideSmem s = carve_fast_side<K, NWMAX>(smem + common + sd * side_bytes, L, RW, p.V);
+      for (int i = threadIdx.x; i < 2 * K * PS; i += blockDim.x) s.post[i] = 0.f;
+      for (int i = threadIdx.x; i < (p.V + 3) / 4 * 4 + 4; i += blockDim.x) s.occ_row[i] = 0.f;
+    }
+  }
   __syncthreads();
   build_symbol_index(cm.lab, L, cm.ix);
-  if (w >= NW) return;   // idle warps wait at the caller's __syncthreads()
-
-  if (side == 0) fast_side_sweep<K, NWMAX, 0>(p, b, m, cm, smem + common, w, lane);
-  else           fast_side_sweep<K, NWMAX, 1>(p, b, m, cm, smem + common + side_bytes, w, lane);
+  // rows of the symbol-sorted posterior layout: segment u owns ceil(count_u / C) rows of C slots
+  {
+    const int C = post_row_width(L, p.V);
+    const int n_seg = *cm.ix.n_seg;
+    if (warp == 0) {
+      int base = 0;
+      for (int u0 = 0; u0 < n_seg; u0 += 32) {
+        const int u = u0 + lane;
+        const int rows = (u < n_seg) ? (cm.ix.seg_start[u + 1] - cm.ix.seg_start[u] + C - 1) / C : 0;
+        int incl = rows;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+          const int v = __shfl_up_sync(0xffffffffu, incl, o);
+          if (lane >= o) incl += v;
+        }
+        if (u < n_seg) cm.row_start[u] = base + incl - rows;
+        base += __shfl_sync(0xffffffffu, incl, 31);
+      }
+      if (lane == 0) { cm.row_start[n_seg] = base; *cm.n_rows = base; }
+    }
+    __syncthreads();
+    for (int u = threadIdx.x; u < n_seg; u += blockDim.x) {
+      const int k0 = cm.ix.seg_start[u], k1 = cm.ix.seg_start[u + 1], s0 = cm.row_start[u] * C;
+      for (int k = k0; k < k1; ++k) cm.slot_of_label[cm.ix.sorted[k]] = s0 + (k - k0);
+    }
+    __syncthreads();
+  }
+  if (w < NW) {
+    if (side == 0) fast_side_sweep<K, NWMAX, 0>(p, b, m, cm, smem + common, w, lane);
+    else           fast_side_sweep<K, NWMAX, 1>(p, b, m, cm, smem + common + side_bytes, w, lane);
+  } else if (w == NWMAX) {
+    if (side == 0) fast_side_reduce<K, NWMAX, 0>(p, b, m, cm, smem + common, lane);
+    else           fast_side_reduce<K, NWMAX, 1>(p, b, m, cm, smem + common + side_bytes, lane);
+  }
+  // idle warps wait at the caller's __syncthreads()
 }
 
 }  // namespace b200ctc
