@@ -10,12 +10,12 @@ namespace {
 
 constexpr int kChunk = 4;  // frames between halo exchanges (K)
 
-// One CTA per utterance, longest lattice first (p.order): per side NWMAX lattice warps and one reducer
-// warp (lattice_fast.cuh).  The block-exponent fast path runs unless
+// One CTA per utterance, longest lattice first (p.order): per side NWMAX lattice warps and kReducers
+// reducer warps (lattice_fast.cuh).  The block-exponent fast path runs unless
 // the utterance was flagged by K1 or is too long for the lattice window; when the fast path gives
 // up (range lost, zero probability) the same CTA redoes the utterance with the fp64 safe path.
 template <int K, int NWMAX>
-__global__ void __launch_bounds__(2 * (NWMAX + 1) * 32, 1) lattice_kernel(CallParams p) {
+__global__ void __launch_bounds__(2 * (NWMAX + kReducers) * 32, 1) lattice_kernel(CallParams p) {
   extern __shared__ __align__(16) unsigned char smem[];
   const int b = p.order[blockIdx.x];
   const UttMeta m = p.meta[b];
@@ -78,7 +78,7 @@ cudaError_t launch_lattice_t(const CallParams& p, int max_L, cudaStream_t stream
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
   }
-  lattice_kernel<K, NWMAX><<<p.B, 2 * (NWMAX + 1) * 32, smem, stream>>>(p);
+  lattice_kernel<K, NWMAX><<<p.B, 2 * (NWMAX + kReducers) * 32, smem, stream>>>(p);
   return cudaGetLastError();
 }
 

@@ -20,15 +20,16 @@
 // so one FADD2/FFMA2/FMUL2 (sm_100 packed fp32) advances two lattice states, and the mirrored pairing
 // of the two sides makes the stored values of one side load as ready-made pairs on the other.
 //
-// Schedule.  One CTA per utterance, 2*(NWMAX+1) warps.  Per side: NW lattice warps (forward: alpha,
-// t = 0,1,..; backward: beta on the reversed label sequence, t = T-1,T-2,..) and one reducer warp.
+// Schedule.  One CTA per utterance, 2*(NWMAX+K) warps.  Per side: NW lattice warps (forward: alpha,
+// t = 0,1,..; backward: beta on the reversed label sequence, t = T-1,T-2,..) and K reducer warps.
 // Phase 1: each side covers half of the frames and stores its pre-emission values to the scratch.
 // Phase 2 (after one CTA barrier): each side continues through the other half, multiplies its fresh
 // values with the stored ones of the opposite side -- posterior(t,s) = alpha_t(s) * beta'_t(s) / P --
-// and scatters the label posteriors into a symbol-sorted shared-memory row.  The reducer warp of the
-// side sums that row per symbol one chunk behind the lattice warps (named-barrier hand-off, double
-// buffered) and writes  grad[t,b,:] = y - occupancy  as ONE coalesced V-wide row per frame (small
-// vocabularies), or one RED per (frame, symbol) into the softmax rows K1 left (gathered mode).
+// and scatters the label posteriors into a symbol-sorted shared-memory row.  The reducer warps of the
+// side (one frame of the chunk each) sum that row per symbol one chunk behind the lattice warps
+// (named-barrier hand-off, double buffered) and turn the softmax row K1 left in the gradient buffer
+// into  grad[t,b,:] = y - occupancy  with one store per warp (small vocabularies: every touched
+// symbol of the frame lies in the same 128-byte row), or one RED per (frame, symbol) (gathered mode).
 // Sequential depth is T frames instead of 2T, only half of alpha and beta ever goes through HBM, and
 // nothing but the recursion itself is on the critical path.
 //
@@ -50,6 +51,7 @@ constexpr int kEZero = -(1 << 28);  // exponent of an all-zero lane
 constexpr int kRowsRing = 4;        // emission-row chunks in flight (staged two chunks ahead + reducer lag)
 constexpr int kOthRing = 8;         // per-thread ring of the opposite side's records (frames)
 constexpr int kOthAhead = 7;        // prefetch distance in frames (must be <= 2K so that row groups retire in time)
+constexpr int kReducers = 4;        // reducer warps per side: warp j takes frame j of every phase-2 chunk (== K)
 
 // ---------------------------------------------------------------------------------------------
 // PTX helpers
@@ -161,8 +163,7 @@ struct FastSideSmem {
   int* halo_e;      // [2][NWMAX]
   float* red_m;     // [NWMAX]
   int* red_e;       // [NWMAX]
-  float* rowsum;    // [Rmax]               reducer scratch
-  float* occ_row;   // [Vpad]               reducer scratch (small vocabularies)
+  float* rowsum;    // [kReducers][Rmax+4]  reducer scratch (symbols spanning several rows)
 };
 
 template <int NWMAX>
@@ -181,8 +182,7 @@ __host__ __device__ inline size_t fast_side_bytes(int L, int RW, int V) {
   b += (size_t)kOthRing * NT * 4;                            // oth_e
   b += 2 * NWMAX * 4;                                        // halo_e
   b += NWMAX * 8;                                            // red
-  b += (size_t)(post_rows_max(L, V) + 4) * 4;                // rowsum
-  b += (size_t)((V + 3) / 4 * 4 + 4) * 4;                    // occ_row
+  b += (size_t)kReducers * (post_rows_max(L, V) + 4) * 4;    // rowsum (one per reducer warp)
   return (b + 15) / 16 * 16;
 }
 template <int K, int NWMAX>
@@ -208,8 +208,7 @@ __device__ __forceinline__ FastSideSmem carve_fast_side(unsigned char* base, int
   s.halo_e = reinterpret_cast<int*>(p);    p += 2 * NWMAX * 4;
   s.red_m = reinterpret_cast<float*>(p);   p += NWMAX * 4;
   s.red_e = reinterpret_cast<int*>(p);     p += NWMAX * 4;
-  s.rowsum = reinterpret_cast<float*>(p);  p += (size_t)(post_rows_max(L, V) + 4) * 4;
-  s.occ_row = reinterpret_cast<float*>(p);
+  s.rowsum = reinterpret_cast<float*>(p);
   return s;
 }
 
@@ -318,14 +317,18 @@ struct FastCtx {
 // Stage the emission rows of the kc frames starting at step n0 into ring slot `slot`: one warp per frame.
 template <int K, int SIDE>
 __device__ __forceinline__ void stage_rows(const FastCtx<SIDE>& c, int slot, int n0, int kc) {
+#pragma unroll 1
   for (int j = c.w; j < kc; j += c.NW) {
     const float* src = c.row_src + (long long)c.frame_of(n0 + j) * c.row_stride;
     float* dst = c.sm.rows + (size_t)(slot * K + j) * c.RWS;
     if (c.row_vec == 4) {
+#pragma unroll 1
       for (int e = c.lane; e < c.per_row; e += 32) cp_async_16(dst + 4 * e, src + 4 * e);
     } else if (c.row_vec == 2) {
+#pragma unroll 1
       for (int e = c.lane; e < c.per_row; e += 32) cp_async_8(dst + 2 * e, src + 2 * e);
     } else {
+#pragma unroll 1
       for (int e = c.lane; e < c.per_row; e += 32) cp_async_4(dst + e, src + e);
     }
   }
@@ -428,9 +431,9 @@ __device__ __forceinline__ void run_chunk(const FastCtx<SIDE>& c, SweepState& ss
   // scratch slot of this lane's group for the opposite side's reader (mirrored group order)
   long long scr_off = (long long)t * J8 + (J8 - 1 - lc.group);
   const long long scr_step = SIDE ? -(long long)J8 : (long long)J8;
-#pragma unroll
-  for (int j = 0; j < K; ++j) {
-    if (j < kc) {
+#pragma unroll 1
+  for (int j = 0; j < kc; ++j) {
+    {
       if (PH2) {
         prefetch_other<SIDE>(c, lc, NT, n0 + j + kOthAhead);
         cp_async_commit();
@@ -681,7 +684,7 @@ __device__ void fast_side_sweep(const CallParams& p, int b, const UttMeta& m, co
     float scaled = part * pow2_neg(pe - emax);
     scaled = warp_sum(scaled);
     if (lane == 0) { c.sm.red_m[w] = scaled; c.sm.red_e[w] = emax; }
-    named_bar_sync(bar_total(SIDE), (NW + 1) * 32);     // lattice warps + the side's reducer
+    named_bar_sync(bar_total(SIDE), (NW + kReducers) * 32);   // lattice warps + the side's reducers
     double log2P;
     if (!total_probability(c.sm, NW, ss.inv_mP, ss.eP, log2P)) {
       // zero / underflowed / garbage total probability: the safe lattice decides
@@ -696,29 +699,50 @@ __device__ void fast_side_sweep(const CallParams& p, int b, const UttMeta& m, co
   // ================================ phase 2 ================================
   for (int cc = nc1; cc < n_chunks; ++cc) {
     const int k2 = cc - nc1, par = k2 & 1;
-    if (write_post && k2 >= 2) named_bar_sync(bar_free(SIDE, par), (NW + 1) * 32);   // reducer done with post[par]
+    if (write_post && k2 >= 2) named_bar_sync(bar_free(SIDE, par), (NW + kReducers) * 32);   // reducers done with post[par]
     stage(cc + 2);
     run_chunk<K, true, SIDE>(c, ss, cc % kRowsRing, par, chunk_n0(cc), chunk_kc(cc), write_post, NT);
     // rows of chunk cc+1 were committed more than kOthAhead groups ago: the per-frame waits retired them
     chunk_boundary<K, NWMAX, SIDE>(c, ss, cc, abort_flag);
-    if (write_post) named_bar_arrive(bar_ready(SIDE, par), (NW + 1) * 32);            // post[par] of chunk cc is complete
+    if (write_post) named_bar_arrive(bar_ready(SIDE, par), (NW + kReducers) * 32);    // post[par] of chunk cc is complete
   }
   if (ss.lost) *abort_flag = 1;
   cp_async_wait<0>();
 }
 
 // ---------------------------------------------------------------------------------------------
-// reducer warp of one side: per-symbol occupancy of every phase-2 frame, gradient rows
+// reducer warps of one side: per-symbol occupancy of every phase-2 frame, gradient rows
 // ---------------------------------------------------------------------------------------------
+template <int C4>
+__device__ __forceinline__ float post_row_sum(const float4* __restrict__ row4) {
+  float4 v[C4];
+#pragma unroll
+  for (int q = 0; q < C4; ++q) v[q] = row4[q];        // all loads in flight before the first add
+  float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+#pragma unroll
+  for (int q = 0; q < C4; ++q) { a0 += v[q].x; a1 += v[q].y; a2 += v[q].z; a3 += v[q].w; }
+  return (a0 + a1) + (a2 + a3);
+}
+__device__ __forceinline__ float post_row_sum_c4(const float4* __restrict__ row4, int C4) {   // C4 is warp-uniform
+  switch (C4) {
+    case 1: return post_row_sum<1>(row4);
+    case 3: return post_row_sum<3>(row4);
+    case 5: return post_row_sum<5>(row4);
+    default: return post_row_sum<7>(row4);
+  }
+}
+
+// Reducer warp rj of the side handles frame rj of every phase-2 chunk.
 template <int K, int NWMAX, int SIDE>
 __device__ void fast_side_reduce(const CallParams& p, int b, const UttMeta& m, const FastCommon& cm,
-                                 unsigned char* side_smem, int lane) {
+                                 unsigned char* side_smem, int rj, int lane) {
+  static_assert(kReducers == K, "one reducer warp per frame of a chunk");
   FastCtx<SIDE> c;
-  fill_ctx<K, NWMAX, SIDE>(c, p, b, m, side_smem, NWMAX, lane);
+  fill_ctx<K, NWMAX, SIDE>(c, p, b, m, side_smem, NWMAX + rj, lane);
   const int T = c.T, NW = c.NW, V = p.V;
   const SidePlan pl = side_plan<K, SIDE>(T);
   if (pl.nc2 == 0) return;
-  named_bar_sync(bar_total(SIDE), (NW + 1) * 32);
+  named_bar_sync(bar_total(SIDE), (NW + kReducers) * 32);
   {
     float inv_mP; int eP; double log2P;
     if (!total_probability(c.sm, NW, inv_mP, eP, log2P)) return;
@@ -727,60 +751,56 @@ __device__ void fast_side_reduce(const CallParams& p, int b, const UttMeta& m, c
 
   const int C4 = post_row_width(c.L, V) / 4;          // 16-byte chunks per row
   const int R = *cm.n_rows, n_seg = *cm.ix.n_seg;
-  const int NTa = NW * 32;
   const bool gathered = p.gathered != 0;
+  const bool one_row = (R == n_seg);                  // every symbol fits one row: row index == segment index
+  const int sym_first = lane < n_seg ? cm.ix.seg_sym[lane] : 0;
+  float* rowsum = c.sm.rowsum + (size_t)rj * (post_rows_max(c.L, V) + 4);
   for (int cc = pl.nc1; cc < pl.n_chunks; ++cc) {
     const int k2 = cc - pl.nc1, par = k2 & 1;
     const int n0 = pl.M_side + k2 * K, kc = min(K, T - n0);
-    named_bar_sync(bar_ready(SIDE, par), (NW + 1) * 32);
-    for (int j = 0; j < kc; ++j) {
-      const float* post = c.sm.post + (size_t)(par * K + j) * c.PS;
-      const int t = c.frame_of(n0 + j);
-      float* grow = p.grads + ((long long)t * p.B + b) * V;
-      // 1. row sums: one lane per row of C slots
-      for (int r0 = 0; r0 < R; r0 += 32) {
-        const int r = r0 + lane;
-        if (r < R) {
-          const float4* row4 = reinterpret_cast<const float4*>(post) + (size_t)r * C4;
-          float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
-          for (int q = 0; q < C4; ++q) {
-            const float4 v = row4[q];
-            a0 += v.x; a1 += v.y; a2 += v.z; a3 += v.w;
-          }
-          c.sm.rowsum[r] = (a0 + a1) + (a2 + a3);
-        }
-      }
-      // 2. blank: partial sums of the lattice threads
+    named_bar_sync(bar_ready(SIDE, par), (NW + kReducers) * 32);
+    if (rj < kc) {
+      const float* post = c.sm.post + (size_t)(par * K + rj) * c.PS;
+      const float4* post4 = reinterpret_cast<const float4*>(post);
+      const float* yrow = c.sm.rows + (size_t)((cc % kRowsRing) * K + rj) * c.RWS;
+      float* grow = p.grads + ((long long)c.frame_of(n0 + rj) * p.B + b) * V;
+      // blank: partial sums of the lattice threads
       float accb = 0.f;
-      for (int i = lane; i < NTa; i += 32) accb += post[c.RC + i];
-      accb = warp_sum(accb);
-      __syncwarp();
-      // 3. per symbol: its rows are adjacent
-      if (!gathered) {
-        const float* yrow = c.sm.rows + (size_t)((cc % kRowsRing) * K + j) * c.RWS;
-        for (int u = lane; u < n_seg; u += 32) {
-          float tot = 0.f;
-          for (int r = cm.row_start[u]; r < cm.row_start[u + 1]; ++r) tot += c.sm.rowsum[r];
-          c.sm.occ_row[cm.ix.seg_sym[u]] = tot;
+#pragma unroll
+      for (int i = 0; i < NWMAX; ++i)
+        if (i < NW) accb += post[c.RC + i * 32 + lane];
+      if (one_row) {
+        for (int u0 = 0; u0 < n_seg; u0 += 32) {
+          const int u = u0 + lane;
+          if (u < n_seg) {
+            const float tot = post_row_sum_c4(post4 + (size_t)u * C4, C4);
+            const int sym = u0 == 0 ? sym_first : cm.ix.seg_sym[u];
+            if (!gathered) grow[sym] = yrow[sym] - tot;      // the touched symbols of a frame share one 128-byte row
+            else atomicAdd(grow + sym, -tot);
+          }
         }
-        if (lane == 0) c.sm.occ_row[p.blank] = accb;
-        __syncwarp();
-        for (int v = lane; v < V; v += 32) grow[v] = yrow[v] - c.sm.occ_row[v];   // one coalesced row
-        __syncwarp();
-        for (int u = lane; u < n_seg; u += 32) c.sm.occ_row[cm.ix.seg_sym[u]] = 0.f;
-        if (lane == 0) c.sm.occ_row[p.blank] = 0.f;
-        __syncwarp();
       } else {
+        for (int r0 = 0; r0 < R; r0 += 32) {
+          const int r = r0 + lane;
+          if (r < R) rowsum[r] = post_row_sum_c4(post4 + (size_t)r * C4, C4);
+        }
+        __syncwarp();
         for (int u = lane; u < n_seg; u += 32) {
           float tot = 0.f;
-          for (int r = cm.row_start[u]; r < cm.row_start[u + 1]; ++r) tot += c.sm.rowsum[r];
-          atomicAdd(grow + cm.ix.seg_sym[u], -tot);
+          for (int r = cm.row_start[u]; r < cm.row_start[u + 1]; ++r) tot += rowsum[r];
+          const int sym = cm.ix.seg_sym[u];
+          if (!gathered) grow[sym] = yrow[sym] - tot;
+          else atomicAdd(grow + sym, -tot);
         }
-        if (lane == 0) atomicAdd(grow + p.blank, -accb);
         __syncwarp();
+      }
+      accb = warp_sum(accb);
+      if (lane == 0) {
+        if (!gathered) grow[p.blank] = yrow[p.blank] - accb;
+        else atomicAdd(grow + p.blank, -accb);
       }
     }
-    if (cc + 2 < pl.n_chunks) named_bar_arrive(bar_free(SIDE, par), (NW + 1) * 32);
+    if (cc + 2 < pl.n_chunks) named_bar_arrive(bar_free(SIDE, par), (NW + kReducers) * 32);
   }
 }
 
@@ -793,8 +813,8 @@ __device__ void lattice_fast_utterance(const CallParams& p, int b, unsigned char
   const int L = m.L;
   const int NW = fast_warps_needed<K>(L);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int side = warp / (NWMAX + 1);
-  const int w = warp - side * (NWMAX + 1);
+  const int side = warp / (NWMAX + kReducers);
+  const int w = warp - side * (NWMAX + kReducers);
 
   // ---- shared memory: common part, then one block per side ----
   FastCommon cm;
@@ -823,7 +843,6 @@ __device__ void lattice_fast_utterance(const CallParams& p, int b, unsigned char
     for (int sd = 0; sd < 2; ++sd) {
       FastSideSmem s = carve_fast_side<K, NWMAX>(smem + common + sd * side_bytes, L, RW, p.V);
       for (int i = threadIdx.x; i < 2 * K * PS; i += blockDim.x) s.post[i] = 0.f;
-      for (int i = threadIdx.x; i < (p.V + 3) / 4 * 4 + 4; i += blockDim.x) s.occ_row[i] = 0.f;
     }
   }
   __syncthreads();
@@ -858,9 +877,9 @@ __device__ void lattice_fast_utterance(const CallParams& p, int b, unsigned char
   if (w < NW) {
     if (side == 0) fast_side_sweep<K, NWMAX, 0>(p, b, m, cm, smem + common, w, lane);
     else           fast_side_sweep<K, NWMAX, 1>(p, b, m, cm, smem + common + side_bytes, w, lane);
-  } else if (w == NWMAX) {
-    if (side == 0) fast_side_reduce<K, NWMAX, 0>(p, b, m, cm, smem + common, lane);
-    else           fast_side_reduce<K, NWMAX, 1>(p, b, m, cm, smem + common + side_bytes, lane);
+  } else if (w >= NWMAX) {
+    if (side == 0) fast_side_reduce<K, NWMAX, 0>(p, b, m, cm, smem + common, w - NWMAX, lane);
+    else           fast_side_reduce<K, NWMAX, 1>(p, b, m, cm, smem + common + side_bytes, w - NWMAX, lane);
   }
   // idle warps wait at the caller's __syncthreads()
 }
