@@ -38,8 +38,8 @@
 // point downwards (s-1, s-2), so a warp can run K frames without talking to its neighbour while the
 // garbage creeping up from its window bottom stays inside the halo; every K frames ("chunk") the
 // lattice warps of a side exchange halos through shared memory -- ONE named barrier per K frames.
-// Neighbour states inside a warp travel by __shfl_up.  Emission rows are staged two chunks ahead and
-// the opposite side's stored records seven frames ahead with cp.async.
+// Neighbour states inside a warp travel by __shfl_up.  The emission rows and the opposite side's
+// stored records of chunk c+1 are fetched with cp.async while chunk c computes.
 #pragma once
 
 #include "lattice_common.cuh"
@@ -48,9 +48,8 @@
 namespace b200ctc {
 
 constexpr int kEZero = -(1 << 28);  // exponent of an all-zero lane
-constexpr int kRowsRing = 4;        // emission-row chunks in flight (staged two chunks ahead + reducer lag)
-constexpr int kOthRing = 8;         // per-thread ring of the opposite side's records (frames)
-constexpr int kOthAhead = 7;        // prefetch distance in frames (must be <= 2K so that row groups retire in time)
+constexpr int kRowsRing = 3;        // emission-row chunks in flight (this chunk, the next one, the reducers' one)
+constexpr int kOthRing = 8;         // per-thread ring of the opposite side's records: two chunks of K = 4 frames
 constexpr int kReducers = 4;        // reducer warps per side: warp j takes frame j of every phase-2 chunk (== K)
 
 // ---------------------------------------------------------------------------------------------
@@ -154,8 +153,7 @@ __host__ __device__ inline int post_rows_max(int L, int V) {
 
 struct FastSideSmem {
   float* rows;      // [kRowsRing][K][RWS]  staged emission rows (+ a zero slot at index RW)
-  float4* oth_a;    // [kOthRing][NT]       opposite side's stored pairs 0,1 of this thread's group
-  float4* oth_b;    // [kOthRing][NT]       ... pairs 2,3
+  float4* oth_a;    // [2][kOthRing][NT]    opposite side's stored pairs 0,1 ([0]) and 2,3 ([1]) of this thread's group
   int* oth_e;       // [kOthRing][NT]       ... exponent
   float* post;      // [2][K][PS]           symbol-sorted label posteriors + blank partials + dump slot
   float4* halo_a;   // [2][NWMAX]           halo lanes (one per warp for K = 4)
@@ -198,8 +196,7 @@ __device__ __forceinline__ FastSideSmem carve_fast_side(unsigned char* base, int
   const size_t NT = NWMAX * 32;
   FastSideSmem s;
   unsigned char* p = base;
-  s.oth_a = reinterpret_cast<float4*>(p);  p += (size_t)kOthRing * NT * 16;
-  s.oth_b = reinterpret_cast<float4*>(p);  p += (size_t)kOthRing * NT * 16;
+  s.oth_a = reinterpret_cast<float4*>(p);  p += (size_t)2 * kOthRing * NT * 16;
   s.halo_a = reinterpret_cast<float4*>(p); p += 2 * NWMAX * 16;
   s.halo_b = reinterpret_cast<float4*>(p); p += 2 * NWMAX * 16;
   s.rows = reinterpret_cast<float*>(p);    p += (size_t)kRowsRing * K * (size_t)(RW + 4) * 4;
@@ -233,11 +230,11 @@ constexpr int kBarMidpoint = 13;
 // per-lane state of a lattice warp
 // ---------------------------------------------------------------------------------------------
 struct LaneConst {
-  int idx[4];       // emission-row index of the four label positions (zero slot if the position is a dummy)
-  int idx_blank;    // emission-row index of the blank
+  int idxB[4];      // byte offset in the emission row of the four label positions (zero slot if the position is a dummy)
+  int idxB_blank;   // byte offset of the blank
   f2 K0, K1;        // skip-transition factors (1.0 allowed / 0.0 not) of label pairs (0,2) and (1,3)
-  int pos[4];       // slot of the four label positions in the symbol-sorted posterior row (dump slot if dummy)
-  int s_lo;         // lattice state of the lane's lowest state (s_hi = s_lo + 7)
+  int posB[4];      // byte offset of the four label positions in the symbol-sorted posterior row (dump slot if dummy)
+  int blankB;       // byte offset of this thread's blank partial sum in the posterior row
   bool owned;       // this lane's group belongs to the warp (not to the halo) and exists
   int group;        // global position group (pos0 / 8)
 };
@@ -247,18 +244,26 @@ struct LaneState {
   int e;
 };
 
-// One frame of the recursion for one lane.  ACC: pre-emission sums at exponent E; W: the new
-// emission-weighted values at the same exponent; st: renormalised state.  Returns max(W).
+__device__ __forceinline__ float lds_f32(const void* base, int byte_off) {
+  return *reinterpret_cast<const float*>(reinterpret_cast<const char*>(base) + byte_off);
+}
+__device__ __forceinline__ void sts_f32(void* base, int byte_off, float v) {
+  *reinterpret_cast<float*>(reinterpret_cast<char*>(base) + byte_off) = v;
+}
+
+// One frame of the recursion for one lane.  ACC: pre-emission sums at exponent E; st: the new
+// emission-weighted state, renormalised.
 template <int SIDE>
-__device__ __forceinline__ float lattice_frame(LaneState& st, const LaneConst& lc, const float* __restrict__ row,
-                                               bool lane0, f2 (&ACC)[4], f2 (&W)[4], int& E) {
+__device__ __forceinline__ void lattice_frame(LaneState& st, const LaneConst& lc, const float* __restrict__ row,
+                                              bool lane0, f2 (&ACC)[4], int& E) {
   const float a7 = el_j4<SIDE>(st.A[3]), a6 = el_j4<SIDE>(st.A[2]);
   const float n1 = __shfl_up_sync(0xffffffffu, a7, 1);
   const float n2 = __shfl_up_sync(0xffffffffu, a6, 1);
   int ne = __shfl_up_sync(0xffffffffu, st.e, 1);
   // emissions: one broadcast load for the four blank positions, one gather per label position
-  const float yb = row[lc.idx_blank];
-  const float y0 = row[lc.idx[0]], y1 = row[lc.idx[1]], y2 = row[lc.idx[2]], y3 = row[lc.idx[3]];
+  const float yb = lds_f32(row, lc.idxB_blank);
+  const float y0 = lds_f32(row, lc.idxB[0]), y1 = lds_f32(row, lc.idxB[1]);
+  const float y2 = lds_f32(row, lc.idxB[2]), y3 = lds_f32(row, lc.idxB[3]);
   if (lane0) ne = kEZero;                      // nothing below the window: scales n1, n2 to zero
   E = max(st.e, ne);
   const float so = pow2_neg(st.e - E), sn = pow2_neg(ne - E);
@@ -274,6 +279,7 @@ __device__ __forceinline__ float lattice_frame(LaneState& st, const LaneConst& l
   ACC[3] = f2_add(As[3], As[2]);
   const f2 YB = f2_pack(yb, yb);
   const f2 YL0 = mk<SIDE>(y0, y2), YL1 = mk<SIDE>(y1, y3);
+  f2 W[4];
   if (SIDE == 0) {   // labels on the odd elements: pairs 1 = (1,5) and 3 = (3,7)
     ACC[1] = f2_fma(lc.K0, Q1, ACC[1]);            // two below (1,5) is (-1,3)
     ACC[3] = f2_fma(lc.K1, As[1], ACC[3]);         // two below (3,7) is (1,5)
@@ -297,7 +303,6 @@ __device__ __forceinline__ float lattice_frame(LaneState& st, const LaneConst& l
 #pragma unroll
   for (int j = 0; j < 4; ++j) st.A[j] = f2_mul(W[j], sc2);
   st.e = nz ? E + eb - 127 : kEZero;
-  return mx;
 }
 
 template <int SIDE>
@@ -334,138 +339,163 @@ __device__ __forceinline__ void stage_rows(const FastCtx<SIDE>& c, int slot, int
   }
 }
 
-// Prefetch the opposite side's stored record of this thread's group for step n into its private ring slot.
-template <int SIDE>
-__device__ __forceinline__ void prefetch_other(const FastCtx<SIDE>& c, const LaneConst& lc, int NT, int n) {
-  if (lc.owned && n < c.T) {
-    const int slot = (n & (kOthRing - 1)) * NT + c.tid_side;
-    const long long off = (long long)c.frame_of(n) * c.J8 + lc.group;
-    cp_async_16(c.sm.oth_a + slot, c.scr_a + off);
-    cp_async_16(c.sm.oth_b + slot, c.scr_b + off);
-    cp_async_4(c.sm.oth_e + slot, c.scr_e + off);
-  }
+// Frames [t0, t1] in which the lattice-state window [ws_lo, ws_hi] intersects the reachable band
+// lo_t = max(0, S - 2(T-t)) <= s < hi_t = min(S, 2(t+1)); empty (t0 > t1) when it never does.
+__device__ __forceinline__ void band_frames(int ws_lo, int ws_hi, int S, int T, int& t0, int& t1) {
+  ws_hi = min(ws_hi, S - 1);
+  t0 = ws_lo >> 1;
+  t1 = T - ((S - ws_hi + 1) >> 1);
+  if (ws_lo > ws_hi) { t0 = 1; t1 = 0; }
 }
 
 // Everything a lattice warp carries through the sweep.
 struct SweepState {
   LaneState st;
   LaneConst lc;
-  int win_s_lo, win_s_hi;   // lattice-state range of the warp window (band skip)
+  int act_lo, act_hi;       // steps in which the warp window intersects the reachable band (chunks outside are skipped)
+  int rd_hi, wr_len;        // the other side stored this lane's record of step n iff (unsigned)(rd_hi - n) < wr_len
   float inv_mP; int eP;     // total probability P = mP * 2^eP (phase 2)
-  bool lost;
+  int maxbound;             // running maximum of the range-check bound (phase 2), as a power-of-two exponent
 };
+constexpr int kLostBound = 127 + 110 - 24 - 2;   // maxbound above this: FLAG_PRECISION_LOST
 
-// Posterior of one frame for one lane: fresh values W (exponent E) times the stored record of the
-// opposite side, normalised by P.  Scatters the label posteriors and the blank partial sum.
-// Called by every lane of an in-band warp (warp collectives inside); only owned lanes have effects.
-template <int SIDE>
-__device__ __forceinline__ void posterior_frame(const FastCtx<SIDE>& c, SweepState& ss, const f2 (&W)[4], float wmax,
-                                                int E, int NT, int n, int t, float* __restrict__ post, bool write_post) {
+// Prefetch the opposite side's stored records of this thread's group for the kc frames starting at
+// step n0 into buffer `obuf` of its private ring; records the other side never wrote (its warp
+// skipped that chunk: out of the band) read as zero.
+template <int K, int SIDE, int NT>
+__device__ __forceinline__ void prefetch_other(const FastCtx<SIDE>& c, const SweepState& ss, int obuf, int n0, int kc) {
   const LaneConst& lc = ss.lc;
-  const int slot = (n & (kOthRing - 1)) * NT + c.tid_side;
-  const float4 qa = c.sm.oth_a[slot], qb = c.sm.oth_b[slot];
-  const int oe = c.sm.oth_e[slot];
-  f2 O[4] = {f2_pack(qa.x, qa.y), f2_pack(qa.z, qa.w), f2_pack(qb.x, qb.y), f2_pack(qb.z, qb.w)};
-  // States outside the reachable band carry dead (own side) or never-written (other side) values.
-  // Only the warps at the band edges have such lanes.
-  const int hi_t = min(c.S, 2 * (t + 1)), lo_t = max(0, c.S - 2 * (c.T - t));
-  const bool all_in = lc.s_lo >= lo_t && lc.s_lo + 7 < hi_t;
-  if (!__all_sync(0xffffffffu, all_in || !lc.owned)) {
-    // element i of the lane is lattice state s_lo + i (forward) or s_lo + 7 - i (backward)
+  if (!lc.owned) return;
+  float4* da = c.sm.oth_a + obuf * K * NT + c.tid_side;
+  int* de = c.sm.oth_e + obuf * K * NT + c.tid_side;
+  int off = c.frame_of(n0) * c.J8 + lc.group;
+  const int step = SIDE ? -c.J8 : c.J8;
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const int sj = SIDE ? lc.s_lo + 7 - j : lc.s_lo + j;
-      const int sj4 = SIDE ? sj - 4 : sj + 4;
-      const float oj = (sj >= lo_t && sj < hi_t) ? el_j<SIDE>(O[j]) : 0.f;
-      const float oj4 = (sj4 >= lo_t && sj4 < hi_t) ? el_j4<SIDE>(O[j]) : 0.f;
-      O[j] = mk<SIDE>(oj, oj4);
+  for (int j = 0; j < K; ++j) {
+    if (j < kc) {
+      if ((unsigned)(ss.rd_hi - (n0 + j)) < (unsigned)ss.wr_len) {
+        cp_async_16(da + j * NT, c.scr_a + off);
+        cp_async_16(da + (2 * K + j) * NT, c.scr_b + off);
+        cp_async_4(de + j * NT, c.scr_e + off);
+      } else {
+        da[j * NT] = make_float4(0.f, 0.f, 0.f, 0.f);
+        da[(2 * K + j) * NT] = make_float4(0.f, 0.f, 0.f, 0.f);
+        de[j * NT] = kEZero;
+      }
+      off += step;
     }
   }
-  // posterior = w * o * 2^dexp / mP.  Both mantissas may be far below 1 (their lane's maximum is
-  // elsewhere), so dexp can legitimately exceed 127: beyond 2^60 the scale is applied in two halves.
-  const int dexp = E + oe - ss.eP;
+}
+
+// Posterior of one frame for one lane: the fresh renormalised state times the stored record of the
+// opposite side, normalised by P:  post = a * o * 2^(e + oe - eP) / mP.  Scatters the label
+// posteriors and the blank partial sum.  Every lane of the warp runs it; only owned lanes store.
+// No band masks: for every state outside the reachable band at least one factor is exactly zero
+// (unreachable from this side's start: a == 0; unreachable from the other side's start: the stored
+// value is 0, or the record was never written and reads as zero -- prefetch_other).
+// The fresh state is normalised to [1,2) per lane, so the one scale factor cannot push a product
+// that matters out of the fp32 range.
+template <int SIDE>
+__device__ __forceinline__ void posterior_frame(SweepState& ss, const float4* __restrict__ oth_a, int b_off,
+                                                const int* __restrict__ oth_e, void* __restrict__ post, bool store) {
+  const LaneConst& lc = ss.lc;
+  const LaneState& st = ss.st;
+  const float4 qa = oth_a[0], qb = oth_a[b_off];
+  const int oe = oth_e[0];
+  const f2 O[4] = {f2_pack(qa.x, qa.y), f2_pack(qa.z, qa.w), f2_pack(qb.x, qb.y), f2_pack(qb.z, qb.w)};
+  const int dexp = st.e + oe - ss.eP;
+  const float s = pow2_clamped(dexp) * ss.inv_mP;   // inv_mP in (0.5, 1]
+  const f2 s2 = f2_pack(s, s);
   f2 PO[4];
-  if (dexp <= 60) {
-    const float s = pow2_clamped(dexp) * ss.inv_mP;   // inv_mP in (0.5, 1]
-    const f2 s2 = f2_pack(s, s);
 #pragma unroll
-    for (int j = 0; j < 4; ++j) PO[j] = f2_mul(f2_mul(W[j], O[j]), s2);
-  } else {
-    const int dhalf = dexp >> 1;
-    const float sa = pow2_clamped(min(dhalf, 120)) * ss.inv_mP;
-    const float sb = pow2_clamped(min(dexp - dhalf, 120));
-    const f2 sa2 = f2_pack(sa, sa), sb2 = f2_pack(sb, sb);
-#pragma unroll
-    for (int j = 0; j < 4; ++j) PO[j] = f2_mul(f2_mul(W[j], sa2), f2_mul(O[j], sb2));
-  }
+  for (int j = 0; j < 4; ++j) PO[j] = f2_mul(f2_mul(st.A[j], O[j]), s2);
   // Range check.  A state that sits more than 2^-110 below its lane's largest value may have lost
   // bits (on either side).  Its posterior is bounded by
-  //   2^-110 * max(own lane) * max(other lane) * 2^dexp / mP;
+  //   2^-110 * max(own lane) * max(other lane) * 2^dexp / mP,   max(own lane) in [1,2);
   // if that bound is not negligible (> 2^-24) the block-exponent result cannot be trusted.  The own
   // maximum runs over ALL eight states: dead states (too late to finish) share the exponent.
-  // Evaluated on the exponent fields, so it cannot overflow or underflow.
-  const float omax = fmaxf(f2_max(O[0], O[1]), f2_max(O[2], O[3]));
-  const int bound = (__float_as_int(wmax) >> 23) + (__float_as_int(omax) >> 23) - 254 + dexp;
-  ss.lost |= lc.owned && (wmax > 0.f) && (omax > 0.f) && (bound > 110 - 24 - 2);
-  if (write_post && lc.owned) {
+  // Evaluated on the exponent fields (a zero maximum has field 0 and can only lower the bound), so
+  // it cannot overflow or underflow; the running maximum is tested at the chunk boundary.
+  const float omax = fmaxf(fmax3(f2_lo(O[0]), f2_hi(O[0]), f2_lo(O[1])),
+                           fmax3(fmax3(f2_hi(O[1]), f2_lo(O[2]), f2_hi(O[2])), f2_lo(O[3]), f2_hi(O[3])));
+  ss.maxbound = max(ss.maxbound, (__float_as_int(omax) >> 23) + dexp);
+  if (store) {
     constexpr int jL0 = SIDE ? 0 : 1, jL1 = SIDE ? 2 : 3, jB0 = SIDE ? 1 : 0, jB1 = SIDE ? 3 : 2;
-    post[lc.pos[0]] = el_j<SIDE>(PO[jL0]);
-    post[lc.pos[1]] = el_j<SIDE>(PO[jL1]);
-    post[lc.pos[2]] = el_j4<SIDE>(PO[jL0]);
-    post[lc.pos[3]] = el_j4<SIDE>(PO[jL1]);
+    sts_f32(post, lc.posB[0], el_j<SIDE>(PO[jL0]));
+    sts_f32(post, lc.posB[1], el_j<SIDE>(PO[jL1]));
+    sts_f32(post, lc.posB[2], el_j4<SIDE>(PO[jL0]));
+    sts_f32(post, lc.posB[3], el_j4<SIDE>(PO[jL1]));
     const f2 bs = f2_add(PO[jB0], PO[jB1]);
-    post[c.RC + c.tid_side] = f2_lo(bs) + f2_hi(bs);
+    sts_f32(post, lc.blankB, f2_lo(bs) + f2_hi(bs));
   }
 }
 
-// One chunk (kc <= K frames starting at step n0; emission rows in ring slot `rslot`).
-template <int K, bool PH2, int SIDE>
-__device__ __forceinline__ void run_chunk(const FastCtx<SIDE>& c, SweepState& ss, int rslot, int pbuf, int n0, int kc,
-                                          bool write_post, int NT) {
-  const int T = c.T, S = c.S, J8 = c.J8;
+// One chunk (kc <= K frames starting at step n0; emission rows in ring slot `rslot`).  A warp whose
+// window misses the reachable band in all frames of the chunk skips it (warp-uniform).
+template <int K, bool PH2, int SIDE, int NT>
+__device__ __forceinline__ void run_chunk(const FastCtx<SIDE>& c, SweepState& ss, int rslot, int pbuf, int obuf,
+                                          int n0, int kc, bool write_post) {
   const LaneConst& lc = ss.lc;
   const bool lane0 = c.lane == 0;
-  const float* rows = c.sm.rows + (size_t)rslot * K * c.RWS;
-  float* post = c.sm.post + (size_t)pbuf * K * c.PS;
-  int t = c.frame_of(n0);
-  // scratch slot of this lane's group for the opposite side's reader (mirrored group order)
-  long long scr_off = (long long)t * J8 + (J8 - 1 - lc.group);
-  const long long scr_step = SIDE ? -(long long)J8 : (long long)J8;
+  const char* rows = reinterpret_cast<const char*>(c.sm.rows + (size_t)rslot * K * c.RWS);
+  const int row_bytes = c.RWS * 4;
+  const bool active = n0 <= ss.act_hi && n0 + kc - 1 >= ss.act_lo;
+  if (!PH2) {
+    if (!active) return;
+    // scratch slot of this lane's group for the opposite side's reader (mirrored group order)
+    const int off0 = c.frame_of(n0) * c.J8 + (c.J8 - 1 - lc.group);
+    const int step = SIDE ? -c.J8 : c.J8;
+    auto frame = [&](int j) {
+      f2 ACC[4]; int E;
+      lattice_frame<SIDE>(ss.st, lc, reinterpret_cast<const float*>(rows + j * row_bytes), lane0, ACC, E);
+      if (lc.owned) {
+        const int off = off0 + j * step;
+        // the reader's pair j is this lane's pair 3-j (mirrored group, mirrored packing)
+        asm volatile("st.global.v2.b64 [%0], {%1, %2};" ::"l"(c.scr_a + off), "l"(ACC[3]), "l"(ACC[2]) : "memory");
+        asm volatile("st.global.v2.b64 [%0], {%1, %2};" ::"l"(c.scr_b + off), "l"(ACC[1]), "l"(ACC[0]) : "memory");
+        c.scr_e[off] = E;
+      }
+    };
+    if (kc == K) {
+#pragma unroll
+      for (int j = 0; j < K; ++j) frame(j);
+    } else {
 #pragma unroll 1
-  for (int j = 0; j < kc; ++j) {
-    {
-      if (PH2) {
-        prefetch_other<SIDE>(c, lc, NT, n0 + j + kOthAhead);
-        cp_async_commit();
+      for (int j = 0; j < kc; ++j) frame(j);
+    }
+  } else {
+    char* post = reinterpret_cast<char*>(c.sm.post + (size_t)pbuf * K * c.PS);
+    const int post_bytes = c.PS * 4;
+    const bool store = write_post && lc.owned;
+    if (active) {
+      const float4* oa = c.sm.oth_a + obuf * K * NT + c.tid_side;
+      const int* oe = c.sm.oth_e + obuf * K * NT + c.tid_side;
+      auto frame = [&](int j) {
+        f2 ACC[4]; int E;
+        lattice_frame<SIDE>(ss.st, lc, reinterpret_cast<const float*>(rows + j * row_bytes), lane0, ACC, E);
+        posterior_frame<SIDE>(ss, oa + j * NT, 2 * K * NT, oe + j * NT, post + j * post_bytes, store);
+      };
+      if (kc == K) {
+#pragma unroll
+        for (int j = 0; j < K; ++j) frame(j);
+      } else {
+#pragma unroll 1
+        for (int j = 0; j < kc; ++j) frame(j);
       }
-      const int hi_t = min(S, 2 * (t + 1)), lo_t = max(0, S - 2 * (T - t));
-      const bool in_band = !(ss.win_s_hi < lo_t || ss.win_s_lo >= hi_t);   // warp-uniform
-      if (PH2) cp_async_wait<kOthAhead>();   // every thread: retires this frame's record and, in time, the staged rows
-      if (in_band) {
-        f2 ACC[4], W[4]; int E;
-        const float wmax = lattice_frame<SIDE>(ss.st, lc, rows + j * c.RWS, lane0, ACC, W, E);
-        if (!PH2) {
-          if (lc.owned) {
-            // the reader's pair j is this lane's pair 3-j (mirrored group, mirrored packing)
-            asm volatile("st.global.v2.b64 [%0], {%1, %2};" ::"l"(c.scr_a + scr_off), "l"(ACC[3]), "l"(ACC[2]) : "memory");
-            asm volatile("st.global.v2.b64 [%0], {%1, %2};" ::"l"(c.scr_b + scr_off), "l"(ACC[1]), "l"(ACC[0]) : "memory");
-            c.scr_e[scr_off] = E;
-          }
-        } else {
-          posterior_frame<SIDE>(c, ss, W, wmax, E, NT, n0 + j, t, post + (size_t)j * c.PS, write_post);
-        }
-      } else if (PH2 && write_post && lc.owned) {
-        float* pr = post + (size_t)j * c.PS;
-        pr[lc.pos[0]] = 0.f; pr[lc.pos[1]] = 0.f; pr[lc.pos[2]] = 0.f; pr[lc.pos[3]] = 0.f;
-        pr[c.RC + c.tid_side] = 0.f;
+    } else if (store) {
+#pragma unroll 1
+      for (int j = 0; j < kc; ++j) {
+        char* pr = post + j * post_bytes;
+        sts_f32(pr, lc.posB[0], 0.f); sts_f32(pr, lc.posB[1], 0.f);
+        sts_f32(pr, lc.posB[2], 0.f); sts_f32(pr, lc.posB[3], 0.f);
+        sts_f32(pr, lc.blankB, 0.f);
       }
-      t += SIDE ? -1 : 1;
-      scr_off += scr_step;
     }
   }
 }
 
-// Chunk boundary of the lattice warps: publish the halo lane, ONE side barrier, import the halo.
+// Chunk boundary of the lattice warps: everything this thread prefetched at the start of the chunk
+// has landed, publish the halo lane, ONE side barrier, import the halo.
 template <int K, int NWMAX, int SIDE>
 __device__ __forceinline__ void chunk_boundary(const FastCtx<SIDE>& c, SweepState& ss, int cc, int* abort_flag) {
   static_assert(K == 4, "one halo lane per warp");
@@ -477,7 +507,8 @@ __device__ __forceinline__ void chunk_boundary(const FastCtx<SIDE>& c, SweepStat
     c.sm.halo_b[slot] = make_float4(f2_lo(st.A[2]), f2_hi(st.A[2]), f2_lo(st.A[3]), f2_hi(st.A[3]));
     c.sm.halo_e[slot] = st.e;
   }
-  if (ss.lost) *abort_flag = 1;
+  if (ss.lc.owned && ss.maxbound > kLostBound) *abort_flag = 1;
+  cp_async_wait<0>();
   named_bar_sync(bar_halo(SIDE), NW * 32);
   if (w > 0 && lane == 0) {
     const int slot = hb * NWMAX + (w - 1);
@@ -488,7 +519,7 @@ __device__ __forceinline__ void chunk_boundary(const FastCtx<SIDE>& c, SweepStat
   }
 }
 
-// Total probability from the per-warp partial sums (every thread of the side, reducer included,
+// Total probability from the per-warp partial sums (every thread of the side, reducers included,
 // evaluates the same expression on the same shared values).  Returns false when the fast path must
 // give up; otherwise mP in [1,2) and eP with P = mP * 2^eP, and log2(P) for the cost.
 __device__ __forceinline__ bool total_probability(const FastSideSmem& sm, int NW, float& inv_mP, int& eP, double& log2P) {
@@ -556,7 +587,7 @@ __device__ void fast_side_sweep(const CallParams& p, int b, const UttMeta& m, co
 
   FastCtx<SIDE> c;
   fill_ctx<K, NWMAX, SIDE>(c, p, b, m, side_smem, w, lane);
-  const int T = c.T, L = c.L, S = c.S, J8 = c.J8, P = c.P, NW = c.NW;
+  const int T = c.T, S = c.S, J8 = c.J8, P = c.P, NW = c.NW;
   const int* lab = cm.lab;
 
   // ---- per-lane constants ----
@@ -566,8 +597,8 @@ __device__ void fast_side_sweep(const CallParams& p, int b, const UttMeta& m, co
   const int pos0 = base_w + 8 * lane;
   lc.group = pos0 >> 3;
   lc.owned = ((w == 0) || (lane >= 1)) && (lc.group < J8);
-  lc.s_lo = SIDE ? (P - 1 - pos0 - 7) : pos0;
-  lc.idx_blank = p.gathered ? 0 : p.blank;
+  lc.idxB_blank = 4 * (p.gathered ? 0 : p.blank);
+  lc.blankB = 4 * (c.RC + c.tid_side);
   {
     float kk[4];
 #pragma unroll
@@ -575,13 +606,13 @@ __device__ void fast_side_sweep(const CallParams& p, int b, const UttMeta& m, co
       const int q = pos0 + (SIDE ? 2 * mslot : 2 * mslot + 1);   // label positions of the lane
       const int s = SIDE ? (P - 1 - q) : q;
       const bool ok = (q < P) && (s >= 0) && (s < S);             // s is odd by construction
-      lc.idx[mslot] = c.RW;            // zero slot
-      lc.pos[mslot] = c.PS - 4;        // dump slot
+      lc.idxB[mslot] = 4 * c.RW;            // zero slot
+      lc.posB[mslot] = 4 * (c.PS - 4);      // dump slot
       kk[mslot] = 0.f;
       if (ok) {
         const int li = s >> 1;
-        lc.idx[mslot] = p.gathered ? li + 1 : lab[li];
-        lc.pos[mslot] = cm.slot_of_label[li];
+        lc.idxB[mslot] = 4 * (p.gathered ? li + 1 : lab[li]);
+        lc.posB[mslot] = 4 * cm.slot_of_label[li];
         const bool sk = SIDE ? (s + 2 < S && lab[li] != lab[li + 1]) : (s >= 3 && lab[li] != lab[li - 1]);
         kk[mslot] = sk ? 1.f : 0.f;
       }
@@ -590,9 +621,35 @@ __device__ void fast_side_sweep(const CallParams& p, int b, const UttMeta& m, co
     lc.K1 = mk<SIDE>(kk[1], kk[3]);
   }
   {
+    // steps in which this warp's window intersects the reachable band (the same for every lane:
+    // broadcast from lane 0 so that the compiler can see the chunk-skip branch is warp-uniform)
     const int win_lo_pos = base_w, win_hi_pos = min(base_w + 255, P - 1);
-    ss.win_s_lo = SIDE ? (P - 1 - win_hi_pos) : win_lo_pos;
-    ss.win_s_hi = SIDE ? (P - 1 - win_lo_pos) : win_hi_pos;
+    const int ws_lo = SIDE ? (P - 1 - win_hi_pos) : win_lo_pos;
+    const int ws_hi = SIDE ? (P - 1 - win_lo_pos) : win_hi_pos;
+    int t0, t1;
+    band_frames(ws_lo, ws_hi, S, T, t0, t1);
+    int a_lo = SIDE ? T - 1 - t1 : t0, a_hi = SIDE ? T - 1 - t0 : t1;
+    if (t0 > t1) { a_lo = 1 << 30; a_hi = -1; }
+    ss.act_lo = __shfl_sync(0xffffffffu, a_lo, 0);
+    ss.act_hi = __shfl_sync(0xffffffffu, a_hi, 0);
+    // which phase-1 records of this lane's group the OTHER side wrote: its warp that owns the mirrored
+    // group was active in the chunk (K steps aligned at its step 0) that holds the frame
+    const int G = J8 - 1 - lc.group;                       // the writer's group index
+    const int wo = G <= 31 ? 0 : (G - 1) / 31;             // its owner warp (lane 0 of warps > 0 is halo)
+    const int o_lo_pos = wo * OWN, o_hi_pos = min(wo * OWN + 255, P - 1);
+    const int os_lo = SIDE ? o_lo_pos : (P - 1 - o_hi_pos);   // the writer is the opposite side
+    const int os_hi = SIDE ? o_hi_pos : (P - 1 - o_lo_pos);
+    band_frames(os_lo, os_hi, S, T, t0, t1);
+    const int M_other = SIDE ? (T - T / 2) : (T / 2);       // frames the other side covers in phase 1
+    int na = SIDE ? t0 : T - 1 - t1;                        // in the writer's steps
+    int nb = min(SIDE ? t1 : T - 1 - t0, M_other - 1);
+    ss.rd_hi = 0; ss.wr_len = 0;
+    if (t0 <= t1 && na <= nb && lc.group < J8) {
+      na = na / K * K;
+      nb = nb / K * K + K - 1;
+      ss.rd_hi = T - 1 - na;                                // writer step n' = T-1-n for a reader at step n
+      ss.wr_len = nb - na + 1;
+    }
   }
   // ---- initial state: delta on the first lattice state of this side's sweep ----
   {
@@ -609,7 +666,7 @@ __device__ void fast_side_sweep(const CallParams& p, int b, const UttMeta& m, co
 #pragma unroll
     for (int j = 0; j < 4; ++j) ss.st.A[j] = mk<SIDE>(v[j], v[j + 4]);
   }
-  ss.lost = false; ss.inv_mP = 0.f; ss.eP = 0;
+  ss.maxbound = -(1 << 30); ss.inv_mP = 0.f; ss.eP = 0;
 
   const SidePlan pl = side_plan<K, SIDE>(T);
   const int M_side = pl.M_side, nc1 = pl.nc1, nc2 = pl.nc2, n_chunks = pl.n_chunks;
@@ -617,25 +674,24 @@ __device__ void fast_side_sweep(const CallParams& p, int b, const UttMeta& m, co
   auto chunk_kc = [&](int cc) { return cc < nc1 ? min(K, M_side - cc * K) : min(K, T - (M_side + (cc - nc1) * K)); };
   auto stage = [&](int cc) {
     if (cc < n_chunks) stage_rows<K, SIDE>(c, cc % kRowsRing, chunk_n0(cc), chunk_kc(cc));
-    cp_async_commit();
   };
   int* abort_flag = cm.abort_flag;
 
-  // zero slots of the row buffers; emission rows of the first two chunks
+  // zero slots of the row buffers; emission rows of the first chunk
   for (int i = c.tid_side; i < kRowsRing * K; i += NW * 32) {
     float* z = c.sm.rows + (size_t)i * c.RWS + c.RW;
     z[0] = 0.f; z[1] = 0.f; z[2] = 0.f; z[3] = 0.f;
   }
   stage(0);
-  stage(1);
-  cp_async_wait<1>();
+  cp_async_commit();
+  cp_async_wait<0>();
   named_bar_sync(bar_halo(SIDE), NW * 32);
 
   // ================================ phase 1 ================================
   for (int cc = 0; cc < nc1; ++cc) {
-    stage(cc + 2);
-    run_chunk<K, false, SIDE>(c, ss, cc % kRowsRing, 0, chunk_n0(cc), chunk_kc(cc), false, NT);
-    cp_async_wait<1>();                                   // rows of chunk cc+1 have landed
+    stage(cc + 1);                                        // lands during this chunk (chunk_boundary waits)
+    cp_async_commit();
+    run_chunk<K, false, SIDE, NT>(c, ss, cc % kRowsRing, 0, 0, chunk_n0(cc), chunk_kc(cc), false);
     chunk_boundary<K, NWMAX, SIDE>(c, ss, cc, abort_flag);
   }
 
@@ -644,38 +700,31 @@ __device__ void fast_side_sweep(const CallParams& p, int b, const UttMeta& m, co
   named_bar_sync(kBarMidpoint, 2 * NW * 32);
   if (nc2 == 0) return;
 
-  // the opposite side's records of the first kOthAhead phase-2 frames, one commit group per frame
-#pragma unroll
-  for (int d = 0; d < kOthAhead; ++d) {
-    prefetch_other<SIDE>(c, lc, NT, M_side + d);
-    cp_async_commit();
-  }
-  cp_async_wait<kOthAhead - 1>();
+  // the opposite side's records of the first phase-2 chunk
+  prefetch_other<K, SIDE, NT>(c, ss, 0, M_side, chunk_kc(nc1));
+  cp_async_commit();
+  cp_async_wait<0>();
 
   // ---- total probability P = sum_s alpha_t(s) beta'_t(s) at the first phase-2 frame (state copy) ----
   {
     const int rslot = nc1 % kRowsRing, n0 = M_side;
     LaneState tmp = ss.st;
     float part = 0.f; int pe = kEZero;
-    const int t = c.frame_of(n0);
-    const int hi_t = min(S, 2 * (t + 1)), lo_t = max(0, S - 2 * (T - t));
-    if (!(ss.win_s_hi < lo_t || ss.win_s_lo >= hi_t)) {
-      f2 ACC[4], W[4]; int E;
-      lattice_frame<SIDE>(tmp, lc, c.sm.rows + (size_t)rslot * K * c.RWS, lane == 0, ACC, W, E);
+    if (n0 <= ss.act_hi && n0 + chunk_kc(nc1) - 1 >= ss.act_lo) {   // same rule as run_chunk: the warp runs this chunk
+      f2 ACC[4]; int E;
+      lattice_frame<SIDE>(tmp, lc, c.sm.rows + (size_t)rslot * K * c.RWS, lane == 0, ACC, E);
       if (lc.owned) {
-        const int slot = (n0 & (kOthRing - 1)) * NT + c.tid_side;
-        const float4 qa = c.sm.oth_a[slot], qb = c.sm.oth_b[slot];
-        const int oe = c.sm.oth_e[slot];
+        const float4 qa = c.sm.oth_a[c.tid_side], qb = c.sm.oth_a[2 * K * NT + c.tid_side];
+        const int oe = c.sm.oth_e[c.tid_side];
         const f2 O[4] = {f2_pack(qa.x, qa.y), f2_pack(qa.z, qa.w), f2_pack(qb.x, qb.y), f2_pack(qb.z, qb.w)};
+        // no band masks: outside the band one of the two factors is exactly zero (posterior_frame)
         float sum = 0.f;
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-          const int sj = SIDE ? lc.s_lo + 7 - j : lc.s_lo + j;
-          const int sj4 = SIDE ? sj - 4 : sj + 4;
-          if (sj >= lo_t && sj < hi_t) sum += el_j<SIDE>(W[j]) * el_j<SIDE>(O[j]);
-          if (sj4 >= lo_t && sj4 < hi_t) sum += el_j4<SIDE>(W[j]) * el_j4<SIDE>(O[j]);
+          const f2 pr = f2_mul(tmp.A[j], O[j]);
+          sum += f2_lo(pr) + f2_hi(pr);
         }
-        if (sum > 0.f) { part = sum; pe = E + oe; }
+        if (sum > 0.f) { part = sum; pe = tmp.e + oe; }
       }
     }
     int emax = pe;
@@ -700,14 +749,13 @@ __device__ void fast_side_sweep(const CallParams& p, int b, const UttMeta& m, co
   for (int cc = nc1; cc < n_chunks; ++cc) {
     const int k2 = cc - nc1, par = k2 & 1;
     if (write_post && k2 >= 2) named_bar_sync(bar_free(SIDE, par), (NW + kReducers) * 32);   // reducers done with post[par]
-    stage(cc + 2);
-    run_chunk<K, true, SIDE>(c, ss, cc % kRowsRing, par, chunk_n0(cc), chunk_kc(cc), write_post, NT);
-    // rows of chunk cc+1 were committed more than kOthAhead groups ago: the per-frame waits retired them
+    stage(cc + 1);
+    if (cc + 1 < n_chunks) prefetch_other<K, SIDE, NT>(c, ss, par ^ 1, chunk_n0(cc + 1), chunk_kc(cc + 1));
+    cp_async_commit();
+    run_chunk<K, true, SIDE, NT>(c, ss, cc % kRowsRing, par, par, chunk_n0(cc), chunk_kc(cc), write_post);
     chunk_boundary<K, NWMAX, SIDE>(c, ss, cc, abort_flag);
     if (write_post) named_bar_arrive(bar_ready(SIDE, par), (NW + kReducers) * 32);    // post[par] of chunk cc is complete
   }
-  if (ss.lost) *abort_flag = 1;
-  cp_async_wait<0>();
 }
 
 // ---------------------------------------------------------------------------------------------
