@@ -167,6 +167,7 @@ int b200ctc_loss_and_grad(b200ctc_handle* h, const float* acts, int64_t acts_str
   if (st != B200CTC_STATUS_SUCCESS) return st;
   if (tot.sum_labels > 0 && !flat_labels) return B200CTC_STATUS_INVALID_VALUE;
   if (tot.sum_labels > 0x7fffffffLL) return B200CTC_STATUS_UNSUPPORTED;
+  if ((long long)B * V * 4 > 0x7fffffffLL) return B200CTC_STATUS_UNSUPPORTED;   // frame stride of the gradient rows in bytes (int32 in the lattice)
   const WorkspaceLayout lay = make_layout(tot, T, B);
   unsigned char* ws = reinterpret_cast<unsigned char*>(
       (reinterpret_cast<uintptr_t>(workspace) + kAlign - 1) / kAlign * kAlign);

@@ -314,27 +314,28 @@ struct FastCtx {
   float4* scr_a;   // [T][J8]  stored pre-emission pairs 0,1 in the READER's group order and packing
   float4* scr_b;   // [T][J8]  ... pairs 2,3
   int* scr_e;      // [T][J8]
-  int row_vec, per_row;                       // emission rows: floats per cp.async, copies per row
-  const float* row_src; long long row_stride; // frame t at row_src + t*row_stride
+  int per_row;                                // emission rows: cp.async copies per row
+  const char* st_src; int st_stride;          // this lane's element of frame t at st_src + t*st_stride (bytes)
+  unsigned st_dst; int st_vecB;               // shared address of this lane's element in row 0 of the ring; bytes per copy
+  unsigned oth_dst, oth_dst_e;                // shared addresses of this thread's slot 0 of the record ring
   __device__ __forceinline__ int frame_of(int n) const { return SIDE ? T - 1 - n : n; }
 };
 
-// Stage the emission rows of the kc frames starting at step n0 into ring slot `slot`: one warp per frame.
+// Stage the emission rows of the kc frames starting at step n0 into ring slot `slot`: one warp per frame,
+// one cp.async per lane and 32 row elements (st_src / st_dst already point at this lane's element).
 template <int K, int SIDE>
 __device__ __forceinline__ void stage_rows(const FastCtx<SIDE>& c, int slot, int n0, int kc) {
 #pragma unroll 1
   for (int j = c.w; j < kc; j += c.NW) {
-    const float* src = c.row_src + (long long)c.frame_of(n0 + j) * c.row_stride;
-    float* dst = c.sm.rows + (size_t)(slot * K + j) * c.RWS;
-    if (c.row_vec == 4) {
+    const char* src = c.st_src + (long long)c.frame_of(n0 + j) * c.st_stride;
+    const unsigned dst = c.st_dst + (unsigned)((slot * K + j) * c.RWS * 4);
 #pragma unroll 1
-      for (int e = c.lane; e < c.per_row; e += 32) cp_async_16(dst + 4 * e, src + 4 * e);
-    } else if (c.row_vec == 2) {
-#pragma unroll 1
-      for (int e = c.lane; e < c.per_row; e += 32) cp_async_8(dst + 2 * e, src + 2 * e);
-    } else {
-#pragma unroll 1
-      for (int e = c.lane; e < c.per_row; e += 32) cp_async_4(dst + e, src + e);
+    for (int e = c.lane; e < c.per_row; e += 32) {
+      const unsigned d = dst + (unsigned)(e - c.lane) * (unsigned)c.st_vecB;
+      const char* g = src + (e - c.lane) * c.st_vecB;
+      if (c.st_vecB == 16) asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(g) : "memory");
+      else if (c.st_vecB == 8) asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(d), "l"(g) : "memory");
+      else asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(d), "l"(g) : "memory");
     }
   }
 }
@@ -366,21 +367,33 @@ template <int K, int SIDE, int NT>
 __device__ __forceinline__ void prefetch_other(const FastCtx<SIDE>& c, const SweepState& ss, int obuf, int n0, int kc) {
   const LaneConst& lc = ss.lc;
   if (!lc.owned) return;
-  float4* da = c.sm.oth_a + obuf * K * NT + c.tid_side;
-  int* de = c.sm.oth_e + obuf * K * NT + c.tid_side;
+  const unsigned da = c.oth_dst + (unsigned)(obuf * K * NT * 16);
+  const unsigned de = c.oth_dst_e + (unsigned)(obuf * K * NT * 4);
   int off = c.frame_of(n0) * c.J8 + lc.group;
   const int step = SIDE ? -c.J8 : c.J8;
+  const bool first = (unsigned)(ss.rd_hi - n0) < (unsigned)ss.wr_len;
+  const bool last = (unsigned)(ss.rd_hi - (n0 + K - 1)) < (unsigned)ss.wr_len;
+  if (kc == K && first && last) {   // the written steps are one interval: both ends inside means all inside
 #pragma unroll
-  for (int j = 0; j < K; ++j) {
-    if (j < kc) {
+    for (int j = 0; j < K; ++j) {
+      asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(da + j * NT * 16), "l"(c.scr_a + off) : "memory");
+      asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(da + (2 * K + j) * NT * 16), "l"(c.scr_b + off) : "memory");
+      asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(de + j * NT * 4), "l"(c.scr_e + off) : "memory");
+      off += step;
+    }
+  } else {
+    float4* sa = c.sm.oth_a + obuf * K * NT + c.tid_side;
+    int* se = c.sm.oth_e + obuf * K * NT + c.tid_side;
+#pragma unroll 1
+    for (int j = 0; j < kc; ++j) {
       if ((unsigned)(ss.rd_hi - (n0 + j)) < (unsigned)ss.wr_len) {
-        cp_async_16(da + j * NT, c.scr_a + off);
-        cp_async_16(da + (2 * K + j) * NT, c.scr_b + off);
-        cp_async_4(de + j * NT, c.scr_e + off);
+        cp_async_16(sa + j * NT, c.scr_a + off);
+        cp_async_16(sa + (2 * K + j) * NT, c.scr_b + off);
+        cp_async_4(se + j * NT, c.scr_e + off);
       } else {
-        da[j * NT] = make_float4(0.f, 0.f, 0.f, 0.f);
-        da[(2 * K + j) * NT] = make_float4(0.f, 0.f, 0.f, 0.f);
-        de[j * NT] = kEZero;
+        sa[j * NT] = make_float4(0.f, 0.f, 0.f, 0.f);
+        sa[(2 * K + j) * NT] = make_float4(0.f, 0.f, 0.f, 0.f);
+        se[j * NT] = kEZero;
       }
       off += step;
     }
@@ -552,14 +565,21 @@ __device__ __forceinline__ void fill_ctx(FastCtx<SIDE>& c, const CallParams& p, 
   c.scr_a = reinterpret_cast<float4*>(scr);
   c.scr_b = reinterpret_cast<float4*>(scr + (size_t)c.T * c.J8 * 16);
   c.scr_e = reinterpret_cast<int*>(scr + (size_t)c.T * c.J8 * 32);
+  const float* row_src; long long row_stride; int row_vec;
   if (p.gathered) {
-    c.row_src = p.em + m.em_off; c.row_stride = m.W; c.row_vec = 4; c.per_row = m.W / 4;
+    row_src = p.em + m.em_off; row_stride = m.W; row_vec = 4; c.per_row = m.W / 4;
   } else {
-    c.row_src = p.grads + (long long)b * p.V; c.row_stride = (long long)p.B * p.V;
+    row_src = p.grads + (long long)b * p.V; row_stride = (long long)p.B * p.V;
     const uintptr_t a = reinterpret_cast<uintptr_t>(p.grads);
-    c.row_vec = (p.V % 4 == 0 && a % 16 == 0) ? 4 : ((p.V % 2 == 0 && a % 8 == 0) ? 2 : 1);
-    c.per_row = p.V / c.row_vec;
+    row_vec = (p.V % 4 == 0 && a % 16 == 0) ? 4 : ((p.V % 2 == 0 && a % 8 == 0) ? 2 : 1);
+    c.per_row = p.V / row_vec;
   }
+  c.st_vecB = row_vec * 4;
+  c.st_src = reinterpret_cast<const char*>(row_src) + lane * c.st_vecB;
+  c.st_stride = (int)(row_stride * 4);          // api.cu rejects mini-batches whose frame stride exceeds 2^31 bytes
+  c.st_dst = (unsigned)__cvta_generic_to_shared(c.sm.rows) + (unsigned)(lane * c.st_vecB);
+  c.oth_dst = (unsigned)__cvta_generic_to_shared(c.sm.oth_a + c.tid_side);
+  c.oth_dst_e = (unsigned)__cvta_generic_to_shared(c.sm.oth_e + c.tid_side);
 }
 
 struct SidePlan {
@@ -669,12 +689,7 @@ __device__ void fast_side_sweep(const CallParams& p, int b, const UttMeta& m, co
   ss.maxbound = -(1 << 30); ss.inv_mP = 0.f; ss.eP = 0;
 
   const SidePlan pl = side_plan<K, SIDE>(T);
-  const int M_side = pl.M_side, nc1 = pl.nc1, nc2 = pl.nc2, n_chunks = pl.n_chunks;
-  auto chunk_n0 = [&](int cc) { return cc < nc1 ? cc * K : M_side + (cc - nc1) * K; };
-  auto chunk_kc = [&](int cc) { return cc < nc1 ? min(K, M_side - cc * K) : min(K, T - (M_side + (cc - nc1) * K)); };
-  auto stage = [&](int cc) {
-    if (cc < n_chunks) stage_rows<K, SIDE>(c, cc % kRowsRing, chunk_n0(cc), chunk_kc(cc));
-  };
+  const int M_side = pl.M_side, nc1 = pl.nc1, nc2 = pl.nc2;
   int* abort_flag = cm.abort_flag;
 
   // zero slots of the row buffers; emission rows of the first chunk
@@ -682,17 +697,25 @@ __device__ void fast_side_sweep(const CallParams& p, int b, const UttMeta& m, co
     float* z = c.sm.rows + (size_t)i * c.RWS + c.RW;
     z[0] = 0.f; z[1] = 0.f; z[2] = 0.f; z[3] = 0.f;
   }
-  stage(0);
+  // Step ranges: phase 1 = [0, M_side), phase 2 = [M_side, T); chunks of K steps from the start of each.
+  // `rs` is the row-ring slot of the current chunk; the rows of the next chunk are staged while it runs.
+  int rs = 0;
+  stage_rows<K, SIDE>(c, 0, 0, min(K, nc1 > 0 ? M_side : T));
   cp_async_commit();
   cp_async_wait<0>();
   named_bar_sync(bar_halo(SIDE), NW * 32);
 
   // ================================ phase 1 ================================
-  for (int cc = 0; cc < nc1; ++cc) {
-    stage(cc + 1);                                        // lands during this chunk (chunk_boundary waits)
+  int cc = 0;
+  for (int n0 = 0; n0 < M_side; n0 += K, ++cc) {
+    const int kc = min(K, M_side - n0);
+    const int rs_next = rs == kRowsRing - 1 ? 0 : rs + 1;
+    const int nn = n0 + kc;                               // first step of the next chunk (phase 1 or 2)
+    if (nn < T) stage_rows<K, SIDE>(c, rs_next, nn, min(K, (nn < M_side ? M_side : T) - nn));   // lands during this chunk
     cp_async_commit();
-    run_chunk<K, false, SIDE, NT>(c, ss, cc % kRowsRing, 0, 0, chunk_n0(cc), chunk_kc(cc), false);
+    run_chunk<K, false, SIDE, NT>(c, ss, rs, 0, 0, n0, kc, false);
     chunk_boundary<K, NWMAX, SIDE>(c, ss, cc, abort_flag);
+    rs = rs_next;
   }
 
   // ================================ midpoint ================================
@@ -701,16 +724,16 @@ __device__ void fast_side_sweep(const CallParams& p, int b, const UttMeta& m, co
   if (nc2 == 0) return;
 
   // the opposite side's records of the first phase-2 chunk
-  prefetch_other<K, SIDE, NT>(c, ss, 0, M_side, chunk_kc(nc1));
+  prefetch_other<K, SIDE, NT>(c, ss, 0, M_side, min(K, T - M_side));
   cp_async_commit();
   cp_async_wait<0>();
 
   // ---- total probability P = sum_s alpha_t(s) beta'_t(s) at the first phase-2 frame (state copy) ----
   {
-    const int rslot = nc1 % kRowsRing, n0 = M_side;
+    const int rslot = rs, n0 = M_side;
     LaneState tmp = ss.st;
     float part = 0.f; int pe = kEZero;
-    if (n0 <= ss.act_hi && n0 + chunk_kc(nc1) - 1 >= ss.act_lo) {   // same rule as run_chunk: the warp runs this chunk
+    if (n0 <= ss.act_hi && n0 + min(K, T - M_side) - 1 >= ss.act_lo) {   // same rule as run_chunk: the warp runs this chunk
       f2 ACC[4]; int E;
       lattice_frame<SIDE>(tmp, lc, c.sm.rows + (size_t)rslot * K * c.RWS, lane == 0, ACC, E);
       if (lc.owned) {
@@ -746,16 +769,22 @@ __device__ void fast_side_sweep(const CallParams& p, int b, const UttMeta& m, co
   const bool write_post = p.grads != nullptr;
 
   // ================================ phase 2 ================================
-  for (int cc = nc1; cc < n_chunks; ++cc) {
-    const int k2 = cc - nc1, par = k2 & 1;
+  int k2 = 0;
+  for (int n0 = M_side; n0 < T; n0 += K, ++k2, ++cc) {
+    const int kc = min(K, T - n0), par = k2 & 1;
+    const int rs_next = rs == kRowsRing - 1 ? 0 : rs + 1;
     if (write_post && k2 >= 2) named_bar_sync(bar_free(SIDE, par), (NW + kReducers) * 32);   // reducers done with post[par]
-    stage(cc + 1);
-    if (cc + 1 < n_chunks) prefetch_other<K, SIDE, NT>(c, ss, par ^ 1, chunk_n0(cc + 1), chunk_kc(cc + 1));
+    if (n0 + K < T) {
+      stage_rows<K, SIDE>(c, rs_next, n0 + K, min(K, T - n0 - K));
+      prefetch_other<K, SIDE, NT>(c, ss, par ^ 1, n0 + K, min(K, T - n0 - K));
+    }
     cp_async_commit();
-    run_chunk<K, true, SIDE, NT>(c, ss, cc % kRowsRing, par, par, chunk_n0(cc), chunk_kc(cc), write_post);
+    run_chunk<K, true, SIDE, NT>(c, ss, rs, par, par, n0, kc, write_post);
     chunk_boundary<K, NWMAX, SIDE>(c, ss, cc, abort_flag);
     if (write_post) named_bar_arrive(bar_ready(SIDE, par), (NW + kReducers) * 32);    // post[par] of chunk cc is complete
+    rs = rs_next;
   }
+  (void)nc2;
 }
 
 // ---------------------------------------------------------------------------------------------

@@ -60,7 +60,7 @@ def main():
             except ValueError:
                 continue
             if samp or inst:
-                rows.append((samp, inst, cur.split("/")[-1], row[0], row[1].strip(), d))
+                rows.append((samp, inst, cur.split("/")[-1], row[0], row[1].strip(), d, cur))
     tot_s = sum(r[0] for r in rows) or 1
     tot_i = sum(r[1] for r in rows) or 1
     print("total warp-instructions %d, stall samples %d" % (tot_i, tot_s))
@@ -73,12 +73,45 @@ def main():
             except ValueError:
                 pass
     print("stall totals:", sorted(((v, k) for k, v in totals.items() if v), reverse=True)[:10])
+    # per-function aggregates: a source line belongs to the last function header above it
+    import os
+    import re
+    fn_of = {}
+    for path in sorted({r[6] for r in rows}):
+        if not os.path.exists(path):
+            continue
+        cur_fn, names = "(file scope)", {}
+        pending = False
+        for i, line in enumerate(open(path, errors="replace"), 1):
+            if re.match(r"^(template\s*<|__device__|__global__|static\s+__device__)", line):
+                pending = True
+            if pending:
+                m = re.search(r"([A-Za-z_][A-Za-z_0-9]*)\s*\(", line)
+                if m and not line.startswith("template"):
+                    cur_fn, pending = m.group(1), False
+            names[i] = cur_fn
+        fn_of[path] = names
+    agg = {}
+    for samp, inst, f, ln, src, d, path in rows:
+        fn = fn_of.get(path, {}).get(int(ln), f)
+        a = agg.setdefault(fn, [0, 0, {}])
+        a[0] += inst
+        a[1] += samp
+        for k in stall_cols:
+            try:
+                a[2][k] = a[2].get(k, 0) + int(d[k] or 0)
+            except ValueError:
+                pass
+    print("--- by function (inlined code is attributed to the function its source line is in)")
+    for fn, (inst, samp, st) in sorted(agg.items(), key=lambda x: -x[1][0]):
+        top = ", ".join("%s %d" % (k[6:], v) for k, v in sorted(st.items(), key=lambda x: -x[1])[:4] if v)
+        print("inst %5.1f%% samp %5.1f%%  %-26s %s" % (100.0 * inst / tot_i, 100.0 * samp / tot_s, fn, top))
     print("--- by samples")
-    for samp, inst, f, ln, src, d in sorted(rows, key=lambda r: -r[0])[:n_lines]:
+    for samp, inst, f, ln, src, d, _ in sorted(rows, key=lambda r: -r[0])[:n_lines]:
         top = sorted(((int(d[k] or 0), k) for k in stall_cols), reverse=True)[:2]
         print("samp %5.1f%% inst %5.1f%%  %s:%s  %s  %s" % (100.0 * samp / tot_s, 100.0 * inst / tot_i, f, ln, src[:90], top))
     print("--- by instructions")
-    for samp, inst, f, ln, src, d in sorted(rows, key=lambda r: -r[1])[:n_lines]:
+    for samp, inst, f, ln, src, d, _ in sorted(rows, key=lambda r: -r[1])[:n_lines]:
         print("inst %5.1f%% samp %5.1f%%  %s:%s  %s" % (100.0 * inst / tot_i, 100.0 * samp / tot_s, f, ln, src[:90]))
 
 
