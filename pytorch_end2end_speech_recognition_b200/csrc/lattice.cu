@@ -1,5 +1,7 @@
 // K2: alpha/beta lattice recursion + posterior occupancy update of the gradient rows.
 // K3: fixed-order sum of the per-utterance costs.
+#include <cstdlib>
+
 #include "common.cuh"
 #include "lattice_fast.cuh"
 #include "lattice_safe.cuh"
@@ -11,10 +13,10 @@ namespace {
 constexpr int kChunk = 4;  // frames between halo exchanges (K)
 
 // One CTA per utterance, longest lattice first (p.order): per side NWMAX lattice warps and kReducers
-// reducer warps (lattice_fast.cuh).  The block-exponent fast path runs unless
+// reducer warps (lattice_fast.cuh); NS lattice states per lane.  The block-exponent fast path runs unless
 // the utterance was flagged by K1 or is too long for the lattice window; when the fast path gives
 // up (range lost, zero probability) the same CTA redoes the utterance with the fp64 safe path.
-template <int K, int NWMAX>
+template <int K, int NWMAX, int NS>
 __global__ void __launch_bounds__(2 * (NWMAX + kReducers) * 32, 1) lattice_kernel(CallParams p) {
   extern __shared__ __align__(16) unsigned char smem[];
   const int b = p.order[blockIdx.x];
@@ -27,17 +29,17 @@ __global__ void __launch_bounds__(2 * (NWMAX + kReducers) * 32, 1) lattice_kerne
     if (threadIdx.x == 0) p.costs[b] = 0.f;
     return;
   }
-  bool use_safe = (p.flags[b] & FLAG_EXTREME_ROW) != 0 || fast_warps_needed<K>(m.L) > NWMAX;
+  bool use_safe = (p.flags[b] & FLAG_EXTREME_ROW) != 0 || fast_warps_needed<K, NS>(m.L) > NWMAX;
   bool dirty = false;
   if (!use_safe) {
     int* abort_word = nullptr;
-    lattice_fast_utterance<K, NWMAX>(p, b, smem, &abort_word);
+    lattice_fast_utterance<K, NWMAX, NS>(p, b, smem, &abort_word);
     __syncthreads();
     use_safe = *abort_word != 0;
     if (use_safe) {
-      dirty = p.grads != nullptr;  // part of the occupancy may already have been subtracted
+      dirty = p.grads != nullptr;  // part of the gradient rows may already have been rewritten
       if (threadIdx.x == 0) atomicOr(p.flags + b, FLAG_PRECISION_LOST);
-      __threadfence();             // order this thread's REDs before the rows are rebuilt
+      __threadfence();             // order this thread's row updates before the rows are rebuilt
       __syncthreads();
     }
   }
@@ -59,26 +61,26 @@ __global__ void __launch_bounds__(256) cost_sum_kernel(const float* __restrict__
   if (threadIdx.x == 0) *loss_sum = (float)part[0];
 }
 
-template <int K, int NWMAX>
+template <int K, int NWMAX, int NS>
 cudaError_t launch_lattice_t(const CallParams& p, int max_L, cudaStream_t stream) {
   // longest label sequence the fast path's lattice window holds with NWMAX warps per side
   int l_cap = max_L;
-  while (l_cap > 0 && fast_warps_needed<K>(l_cap) > NWMAX) --l_cap;
+  while (l_cap > 0 && fast_warps_needed<K, NS>(l_cap) > NWMAX) --l_cap;
   const int rw = p.gathered ? (l_cap + 1 + 3) / 4 * 4 : (p.V + 3) / 4 * 4;
   // the posterior row is not monotonic in L (its slot width steps): size for the worst L <= l_cap
   size_t smem = 0;
   for (int L = 0; L <= l_cap; ++L) {
-    const size_t s = fast_smem_bytes<K, NWMAX>(L, rw, p.V);
+    const size_t s = fast_smem_bytes<K, NWMAX, NS>(L, rw, p.V);
     smem = s > smem ? s : smem;
   }
   smem = smem > safe_smem_bytes(max_L) ? smem : safe_smem_bytes(max_L);
   if (smem > 227 * 1024) return cudaErrorInvalidConfiguration;
   if (smem > 48 * 1024) {
-    cudaError_t e = cudaFuncSetAttribute(lattice_kernel<K, NWMAX>,
+    cudaError_t e = cudaFuncSetAttribute(lattice_kernel<K, NWMAX, NS>,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
   }
-  lattice_kernel<K, NWMAX><<<p.B, 2 * (NWMAX + kReducers) * 32, smem, stream>>>(p);
+  lattice_kernel<K, NWMAX, NS><<<p.B, 2 * (NWMAX + kReducers) * 32, smem, stream>>>(p);
   return cudaGetLastError();
 }
 
@@ -86,10 +88,23 @@ cudaError_t launch_lattice_t(const CallParams& p, int max_L, cudaStream_t stream
 
 cudaError_t launch_lattice(const CallParams& p, int max_L, cudaStream_t stream) {
   if (p.B == 0) return cudaSuccess;
-  const int nw = fast_warps_needed<kChunk>(max_L);
-  if (nw <= 1) return launch_lattice_t<kChunk, 1>(p, max_L, stream);
-  if (nw <= 2) return launch_lattice_t<kChunk, 2>(p, max_L, stream);
-  return launch_lattice_t<kChunk, 4>(p, max_L, stream);   // longer label sequences (L > 499) take the safe lattice
+  // States per lane: four (twice the lattice warps, better latency hiding) while the label sequence
+  // fits eight warps per side, eight beyond.  B200CTC_NS=4|8 overrides the choice (tuning knob).
+  int ns = fast_warps_needed<kChunk, 4>(max_L) <= 8 ? 4 : 8;
+  if (const char* e = std::getenv("B200CTC_NS")) {
+    if (e[0] == '8') ns = 8;
+    if (e[0] == '4' && fast_warps_needed<kChunk, 4>(max_L) <= 8) ns = 4;
+  }
+  if (ns == 4) {
+    const int nw = fast_warps_needed<kChunk, 4>(max_L);
+    if (nw <= 2) return launch_lattice_t<kChunk, 2, 4>(p, max_L, stream);
+    if (nw <= 4) return launch_lattice_t<kChunk, 4, 4>(p, max_L, stream);
+    return launch_lattice_t<kChunk, 8, 4>(p, max_L, stream);
+  }
+  const int nw = fast_warps_needed<kChunk, 8>(max_L);
+  if (nw <= 1) return launch_lattice_t<kChunk, 1, 8>(p, max_L, stream);
+  if (nw <= 2) return launch_lattice_t<kChunk, 2, 8>(p, max_L, stream);
+  return launch_lattice_t<kChunk, 4, 8>(p, max_L, stream);   // longer label sequences (L > 499) take the safe lattice
 }
 
 cudaError_t launch_cost_sum(const CallParams& p, cudaStream_t stream) {

@@ -131,13 +131,13 @@ __device__ __forceinline__ float f2_max(f2 a, f2 b) {  // max over the four floa
 }
 
 // ---------------------------------------------------------------------------------------------
-// geometry shared by host (shared-memory sizing) and device
+// geometry shared by host (shared-memory sizing) and device.  NS = lattice states per lane (4 or 8).
 // ---------------------------------------------------------------------------------------------
-template <int K>
+template <int K, int NS>
 __host__ __device__ inline int fast_warps_needed(int L) {
-  const int P = 8 * ((2 * L + 1 + 7) / 8);
-  const int own = 256 - 2 * K;
-  return P <= 256 ? 1 : 1 + (P - 256 + own - 1) / own;
+  const int P = NS * ((2 * L + 1 + NS - 1) / NS);
+  const int win = 32 * NS, own = win - 2 * K;
+  return P <= win ? 1 : 1 + (P - win + own - 1) / own;
 }
 // Symbol-sorted posterior row: every symbol of the label sequence owns whole rows of C slots.
 __host__ __device__ inline int post_row_width(int L, int V) {
@@ -152,16 +152,15 @@ __host__ __device__ inline int post_rows_max(int L, int V) {
 }
 
 struct FastSideSmem {
-  float* rows;      // [kRowsRing][K][RWS]  staged emission rows (+ a zero slot at index RW)
-  float4* oth_a;    // [2][kOthRing][NT]    opposite side's stored pairs 0,1 ([0]) and 2,3 ([1]) of this thread's group
-  int* oth_e;       // [kOthRing][NT]       ... exponent
-  float* post;      // [2][K][PS]           symbol-sorted label posteriors + blank partials + dump slot
-  float4* halo_a;   // [2][NWMAX]           halo lanes (one per warp for K = 4)
-  float4* halo_b;   // [2][NWMAX]
-  int* halo_e;      // [2][NWMAX]
+  float* rows;      // [kRowsRing][K][RWS]     staged emission rows (+ a zero slot at index RW)
+  float4* oth_m;    // [2][K][NS/4][NT]        opposite side's stored pairs of this thread's group, two chunks
+  int* oth_e;       // [2][K][NT]              ... exponent
+  float* post;      // [2][K][PS]              symbol-sorted label posteriors + blank partials + dump slot
+  float4* halo_m;   // [2][NWMAX][HL][NS/4]    halo lanes
+  int* halo_e;      // [2][NWMAX][HL]
   float* red_m;     // [NWMAX]
   int* red_e;       // [NWMAX]
-  float* rowsum;    // [kReducers][Rmax+4]  reducer scratch (symbols spanning several rows)
+  float* rowsum;    // [kReducers][Rmax+4]     reducer scratch (symbols spanning several rows)
 };
 
 template <int NWMAX>
@@ -169,40 +168,41 @@ __host__ __device__ inline int post_stride(int L, int V) {  // floats per frame 
   return post_row_width(L, V) * post_rows_max(L, V) + NWMAX * 32 + 4;
 }
 
-template <int K, int NWMAX>
+template <int K, int NWMAX, int NS>
 __host__ __device__ inline size_t fast_side_bytes(int L, int RW, int V) {
   const size_t NT = NWMAX * 32;
+  constexpr int HL = 2 * K / NS;
   size_t b = 0;
-  b += (size_t)kOthRing * NT * 16 * 2;                       // oth_a, oth_b
-  b += 2 * NWMAX * 16 * 2;                                   // halo_a, halo_b
+  b += (size_t)2 * K * (NS / 4) * NT * 16;                   // oth_m
+  b += (size_t)2 * NWMAX * HL * (NS / 4) * 16;               // halo_m
   b += (size_t)kRowsRing * K * (size_t)(RW + 4) * 4;         // rows
   b += 2 * (size_t)K * post_stride<NWMAX>(L, V) * 4;         // post
-  b += (size_t)kOthRing * NT * 4;                            // oth_e
-  b += 2 * NWMAX * 4;                                        // halo_e
+  b += (size_t)2 * K * NT * 4;                               // oth_e
+  b += (size_t)2 * NWMAX * HL * 4;                           // halo_e
   b += NWMAX * 8;                                            // red
   b += (size_t)kReducers * (post_rows_max(L, V) + 4) * 4;    // rowsum (one per reducer warp)
   return (b + 15) / 16 * 16;
 }
-template <int K, int NWMAX>
+template <int K, int NWMAX, int NS>
 __host__ __device__ inline size_t fast_smem_bytes(int L, int RW, int V) {
   // control words, lab, sorted, seg_start, seg_sym, slot_of_label, row_start
   size_t common = (size_t)(16 + 6 * L + 16) * 4;
   common = (common + 15) / 16 * 16;
-  return common + 2 * fast_side_bytes<K, NWMAX>(L, RW, V) + 16;
+  return common + 2 * fast_side_bytes<K, NWMAX, NS>(L, RW, V) + 16;
 }
 
-template <int K, int NWMAX>
+template <int K, int NWMAX, int NS>
 __device__ __forceinline__ FastSideSmem carve_fast_side(unsigned char* base, int L, int RW, int V) {
   const size_t NT = NWMAX * 32;
+  constexpr int HL = 2 * K / NS;
   FastSideSmem s;
   unsigned char* p = base;
-  s.oth_a = reinterpret_cast<float4*>(p);  p += (size_t)2 * kOthRing * NT * 16;
-  s.halo_a = reinterpret_cast<float4*>(p); p += 2 * NWMAX * 16;
-  s.halo_b = reinterpret_cast<float4*>(p); p += 2 * NWMAX * 16;
+  s.oth_m = reinterpret_cast<float4*>(p);  p += (size_t)2 * K * (NS / 4) * NT * 16;
+  s.halo_m = reinterpret_cast<float4*>(p); p += (size_t)2 * NWMAX * HL * (NS / 4) * 16;
   s.rows = reinterpret_cast<float*>(p);    p += (size_t)kRowsRing * K * (size_t)(RW + 4) * 4;
   s.post = reinterpret_cast<float*>(p);    p += 2 * (size_t)K * post_stride<NWMAX>(L, V) * 4;
-  s.oth_e = reinterpret_cast<int*>(p);     p += (size_t)kOthRing * NT * 4;
-  s.halo_e = reinterpret_cast<int*>(p);    p += 2 * NWMAX * 4;
+  s.oth_e = reinterpret_cast<int*>(p);     p += (size_t)2 * K * NT * 4;
+  s.halo_e = reinterpret_cast<int*>(p);    p += (size_t)2 * NWMAX * HL * 4;
   s.red_m = reinterpret_cast<float*>(p);   p += NWMAX * 4;
   s.red_e = reinterpret_cast<int*>(p);     p += NWMAX * 4;
   s.rowsum = reinterpret_cast<float*>(p);
@@ -227,20 +227,24 @@ __device__ __forceinline__ int bar_free(int side, int par) { return 5 + side * 6
 constexpr int kBarMidpoint = 13;
 
 // ---------------------------------------------------------------------------------------------
-// per-lane state of a lattice warp
+// per-lane state of a lattice warp.  NP = NS/2 packed pairs; pair j holds elements (j, j+NP).
+// Label positions are the odd elements (forward) / even elements (backward); label slot m is element
+// 2m+1 / 2m; label pair u (pair index 2u+1 / 2u) holds label slots (u, u + NP/2).
 // ---------------------------------------------------------------------------------------------
+template <int NS>
 struct LaneConst {
-  int idxB[4];      // byte offset in the emission row of the four label positions (zero slot if the position is a dummy)
+  int idxB[NS / 2]; // byte offset in the emission row of the label positions (zero slot if the position is a dummy)
   int idxB_blank;   // byte offset of the blank
-  f2 K0, K1;        // skip-transition factors (1.0 allowed / 0.0 not) of label pairs (0,2) and (1,3)
-  int posB[4];      // byte offset of the four label positions in the symbol-sorted posterior row (dump slot if dummy)
+  f2 Kf[NS / 4];    // skip-transition factors (1.0 allowed / 0.0 not) of the label pairs
+  int posB[NS / 2]; // byte offset of the label positions in the symbol-sorted posterior row (dump slot if dummy)
   int blankB;       // byte offset of this thread's blank partial sum in the posterior row
   bool owned;       // this lane's group belongs to the warp (not to the halo) and exists
-  int group;        // global position group (pos0 / 8)
+  int group;        // global position group (pos0 / NS)
 };
 
+template <int NS>
 struct LaneState {
-  f2 A[4];
+  f2 A[NS / 2];
   int e;
 };
 
@@ -250,70 +254,75 @@ __device__ __forceinline__ float lds_f32(const void* base, int byte_off) {
 __device__ __forceinline__ void sts_f32(void* base, int byte_off, float v) {
   *reinterpret_cast<float*>(reinterpret_cast<char*>(base) + byte_off) = v;
 }
+template <int N>
+__device__ __forceinline__ float f2_max_all(const f2 (&v)[N]) {   // max over the 2N floats
+  float m = fmax3(f2_lo(v[0]), f2_hi(v[0]), f2_lo(v[1]));
+  m = fmaxf(m, f2_hi(v[1]));
+  if (N == 4) m = fmaxf(fmax3(m, f2_lo(v[2]), f2_hi(v[2])), fmaxf(f2_lo(v[N - 1]), f2_hi(v[N - 1])));
+  return m;
+}
 
 // One frame of the recursion for one lane.  ACC: pre-emission sums at exponent E; st: the new
 // emission-weighted state, renormalised.
-template <int SIDE>
-__device__ __forceinline__ void lattice_frame(LaneState& st, const LaneConst& lc, const float* __restrict__ row,
-                                              bool lane0, f2 (&ACC)[4], int& E) {
-  const float a7 = el_j4<SIDE>(st.A[3]), a6 = el_j4<SIDE>(st.A[2]);
-  const float n1 = __shfl_up_sync(0xffffffffu, a7, 1);
-  const float n2 = __shfl_up_sync(0xffffffffu, a6, 1);
+template <int SIDE, int NS>
+__device__ __forceinline__ void lattice_frame(LaneState<NS>& st, const LaneConst<NS>& lc, const void* __restrict__ row,
+                                              bool lane0, f2 (&ACC)[NS / 2], int& E) {
+  constexpr int NP = NS / 2;
+  const float a_top = el_j4<SIDE>(st.A[NP - 1]), a_top2 = el_j4<SIDE>(st.A[NP - 2]);
+  const float n1 = __shfl_up_sync(0xffffffffu, a_top, 1);
+  const float n2 = __shfl_up_sync(0xffffffffu, a_top2, 1);
   int ne = __shfl_up_sync(0xffffffffu, st.e, 1);
-  // emissions: one broadcast load for the four blank positions, one gather per label position
+  // emissions: one broadcast load for the blank positions, one gather per label position
   const float yb = lds_f32(row, lc.idxB_blank);
-  const float y0 = lds_f32(row, lc.idxB[0]), y1 = lds_f32(row, lc.idxB[1]);
-  const float y2 = lds_f32(row, lc.idxB[2]), y3 = lds_f32(row, lc.idxB[3]);
+  float y[NP];
+#pragma unroll
+  for (int m = 0; m < NP; ++m) y[m] = lds_f32(row, lc.idxB[m]);
   if (lane0) ne = kEZero;                      // nothing below the window: scales n1, n2 to zero
   E = max(st.e, ne);
   const float so = pow2_neg(st.e - E), sn = pow2_neg(ne - E);
   const f2 so2 = f2_pack(so, so);
-  f2 As[4];
+  f2 As[NP];
 #pragma unroll
-  for (int j = 0; j < 4; ++j) As[j] = f2_mul(st.A[j], so2);
+  for (int j = 0; j < NP; ++j) As[j] = f2_mul(st.A[j], so2);
   const float b1 = n1 * sn, b2 = n2 * sn;
-  const f2 Q1 = mk<SIDE>(b1, el_j<SIDE>(As[3]));   // elements (-1, 3)
+  const f2 Q1 = mk<SIDE>(b1, el_j<SIDE>(As[NP - 1]));   // elements (-1, NP-1)
+  const f2 Q2 = mk<SIDE>(b2, el_j<SIDE>(As[NP - 2]));   // elements (-2, NP-2)
   ACC[0] = f2_add(As[0], Q1);
-  ACC[1] = f2_add(As[1], As[0]);
-  ACC[2] = f2_add(As[2], As[1]);
-  ACC[3] = f2_add(As[3], As[2]);
+#pragma unroll
+  for (int j = 1; j < NP; ++j) ACC[j] = f2_add(As[j], As[j - 1]);
   const f2 YB = f2_pack(yb, yb);
-  const f2 YL0 = mk<SIDE>(y0, y2), YL1 = mk<SIDE>(y1, y3);
-  f2 W[4];
-  if (SIDE == 0) {   // labels on the odd elements: pairs 1 = (1,5) and 3 = (3,7)
-    ACC[1] = f2_fma(lc.K0, Q1, ACC[1]);            // two below (1,5) is (-1,3)
-    ACC[3] = f2_fma(lc.K1, As[1], ACC[3]);         // two below (3,7) is (1,5)
-    W[0] = f2_mul(ACC[0], YB);  W[1] = f2_mul(ACC[1], YL0);
-    W[2] = f2_mul(ACC[2], YB);  W[3] = f2_mul(ACC[3], YL1);
-  } else {           // labels on the even elements: pairs 0 = (0,4) and 2 = (2,6)
-    const f2 Q2 = mk<SIDE>(b2, el_j<SIDE>(As[2])); // elements (-2, 2)
-    ACC[0] = f2_fma(lc.K0, Q2, ACC[0]);
-    ACC[2] = f2_fma(lc.K1, As[0], ACC[2]);         // two below (2,6) is (0,4)
-    W[0] = f2_mul(ACC[0], YL0); W[1] = f2_mul(ACC[1], YB);
-    W[2] = f2_mul(ACC[2], YL1); W[3] = f2_mul(ACC[3], YB);
+  f2 W[NP];
+#pragma unroll
+  for (int j = 0; j < NP; ++j) {
+    const bool is_label = SIDE ? (j % 2 == 0) : (j % 2 == 1);
+    if (is_label) {
+      const int u = j / 2;                                  // label pair u: label slots (u, u + NP/2)
+      const f2 below2 = j >= 2 ? As[j - 2] : (j == 1 ? Q1 : Q2);
+      ACC[j] = f2_fma(lc.Kf[u], below2, ACC[j]);
+      W[j] = f2_mul(ACC[j], mk<SIDE>(y[u], y[u + NP / 2]));
+    } else {
+      W[j] = f2_mul(ACC[j], YB);
+    }
   }
-  const float m01 = fmax3(f2_lo(W[0]), f2_hi(W[0]), f2_lo(W[1]));
-  const float m23 = fmax3(f2_hi(W[1]), f2_lo(W[2]), f2_hi(W[2]));
-  const float mx = fmaxf(fmax3(m01, f2_lo(W[3]), f2_hi(W[3])), m23);
+  const float mx = f2_max_all<NP>(W);
   // renormalise: largest mantissa -> [1,2).  mx == 0 (or NaN from garbage): the lane is empty.
   const int eb = __float_as_int(mx) >> 23;                       // biased exponent
   const bool nz = mx > 0.f;
   const float sc = nz ? __int_as_float((254 - eb) << 23) : 0.f;  // 2^(127-eb)
   const f2 sc2 = f2_pack(sc, sc);
 #pragma unroll
-  for (int j = 0; j < 4; ++j) st.A[j] = f2_mul(W[j], sc2);
+  for (int j = 0; j < NP; ++j) st.A[j] = f2_mul(W[j], sc2);
   st.e = nz ? E + eb - 127 : kEZero;
 }
 
 template <int SIDE>
 struct FastCtx {
   const CallParams* p;
-  int b, T, L, S, J8, P, NW, RW, RWS, PS, RC;
+  int b, T, L, S, JG, P, NW, RW, RWS, PS, RC;
   int w, lane, tid_side;
   FastSideSmem sm;
-  float4* scr_a;   // [T][J8]  stored pre-emission pairs 0,1 in the READER's group order and packing
-  float4* scr_b;   // [T][J8]  ... pairs 2,3
-  int* scr_e;      // [T][J8]
+  float4* scr_m;   // [NS/4][T][JG]  stored pre-emission pairs in the READER's group order and packing
+  int* scr_e;      // [T][JG]
   int per_row;                                // emission rows: cp.async copies per row
   const char* st_src; int st_stride;          // this lane's element of frame t at st_src + t*st_stride (bytes)
   unsigned st_dst; int st_vecB;               // shared address of this lane's element in row 0 of the ring; bytes per copy
@@ -350,9 +359,10 @@ __device__ __forceinline__ void band_frames(int ws_lo, int ws_hi, int S, int T, 
 }
 
 // Everything a lattice warp carries through the sweep.
+template <int NS>
 struct SweepState {
-  LaneState st;
-  LaneConst lc;
+  LaneState<NS> st;
+  LaneConst<NS> lc;
   int act_lo, act_hi;       // steps in which the warp window intersects the reachable band (chunks outside are skipped)
   int rd_hi, wr_len;        // the other side stored this lane's record of step n iff (unsigned)(rd_hi - n) < wr_len
   float inv_mP; int eP;     // total probability P = mP * 2^eP (phase 2)
@@ -363,38 +373,41 @@ constexpr int kLostBound = 127 + 110 - 24 - 2;   // maxbound above this: FLAG_PR
 // Prefetch the opposite side's stored records of this thread's group for the kc frames starting at
 // step n0 into buffer `obuf` of its private ring; records the other side never wrote (its warp
 // skipped that chunk: out of the band) read as zero.
-template <int K, int SIDE, int NT>
-__device__ __forceinline__ void prefetch_other(const FastCtx<SIDE>& c, const SweepState& ss, int obuf, int n0, int kc) {
-  const LaneConst& lc = ss.lc;
+template <int K, int SIDE, int NT, int NS>
+__device__ __forceinline__ void prefetch_other(const FastCtx<SIDE>& c, const SweepState<NS>& ss, int obuf, int n0, int kc) {
+  constexpr int NH = NS / 4;                  // 16-byte halves of a record
+  const LaneConst<NS>& lc = ss.lc;
   if (!lc.owned) return;
-  const unsigned da = c.oth_dst + (unsigned)(obuf * K * NT * 16);
+  const unsigned da = c.oth_dst + (unsigned)(obuf * K * NH * NT * 16);
   const unsigned de = c.oth_dst_e + (unsigned)(obuf * K * NT * 4);
-  int off = c.frame_of(n0) * c.J8 + lc.group;
-  const int step = SIDE ? -c.J8 : c.J8;
+  int off = c.frame_of(n0) * c.JG + lc.group;
+  const int step = SIDE ? -c.JG : c.JG;
+  const int half_stride = c.T * c.JG;         // float4 elements between the halves of a record in the scratch
   const bool first = (unsigned)(ss.rd_hi - n0) < (unsigned)ss.wr_len;
   const bool last = (unsigned)(ss.rd_hi - (n0 + K - 1)) < (unsigned)ss.wr_len;
   if (kc == K && first && last) {   // the written steps are one interval: both ends inside means all inside
 #pragma unroll
     for (int j = 0; j < K; ++j) {
-      asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(da + j * NT * 16), "l"(c.scr_a + off) : "memory");
-      asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(da + (2 * K + j) * NT * 16), "l"(c.scr_b + off) : "memory");
+#pragma unroll
+      for (int h = 0; h < NH; ++h)
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(da + (j * NH + h) * NT * 16),
+                     "l"(c.scr_m + h * half_stride + off) : "memory");
       asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(de + j * NT * 4), "l"(c.scr_e + off) : "memory");
       off += step;
     }
   } else {
-    float4* sa = c.sm.oth_a + obuf * K * NT + c.tid_side;
+    float4* sa = c.sm.oth_m + obuf * K * NH * NT + c.tid_side;
     int* se = c.sm.oth_e + obuf * K * NT + c.tid_side;
 #pragma unroll 1
     for (int j = 0; j < kc; ++j) {
-      if ((unsigned)(ss.rd_hi - (n0 + j)) < (unsigned)ss.wr_len) {
-        cp_async_16(sa + j * NT, c.scr_a + off);
-        cp_async_16(sa + (2 * K + j) * NT, c.scr_b + off);
-        cp_async_4(se + j * NT, c.scr_e + off);
-      } else {
-        sa[j * NT] = make_float4(0.f, 0.f, 0.f, 0.f);
-        sa[(2 * K + j) * NT] = make_float4(0.f, 0.f, 0.f, 0.f);
-        se[j * NT] = kEZero;
+      const bool wr = (unsigned)(ss.rd_hi - (n0 + j)) < (unsigned)ss.wr_len;
+#pragma unroll
+      for (int h = 0; h < NH; ++h) {
+        if (wr) cp_async_16(sa + (j * NH + h) * NT, c.scr_m + h * half_stride + off);
+        else sa[(j * NH + h) * NT] = make_float4(0.f, 0.f, 0.f, 0.f);
       }
+      if (wr) cp_async_4(se + j * NT, c.scr_e + off);
+      else se[j * NT] = kEZero;
       off += step;
     }
   }
@@ -408,126 +421,139 @@ __device__ __forceinline__ void prefetch_other(const FastCtx<SIDE>& c, const Swe
 // value is 0, or the record was never written and reads as zero -- prefetch_other).
 // The fresh state is normalised to [1,2) per lane, so the one scale factor cannot push a product
 // that matters out of the fp32 range.
-template <int SIDE>
-__device__ __forceinline__ void posterior_frame(SweepState& ss, const float4* __restrict__ oth_a, int b_off,
+template <int SIDE, int NT, int NS>
+__device__ __forceinline__ void posterior_frame(SweepState<NS>& ss, const float4* __restrict__ oth_m,
                                                 const int* __restrict__ oth_e, void* __restrict__ post, bool store) {
-  const LaneConst& lc = ss.lc;
-  const LaneState& st = ss.st;
-  const float4 qa = oth_a[0], qb = oth_a[b_off];
+  constexpr int NP = NS / 2, NH = NS / 4;
+  const LaneConst<NS>& lc = ss.lc;
+  const LaneState<NS>& st = ss.st;
+  f2 O[NP];
+#pragma unroll
+  for (int h = 0; h < NH; ++h) {
+    const float4 q = oth_m[h * NT];
+    O[2 * h] = f2_pack(q.x, q.y);
+    O[2 * h + 1] = f2_pack(q.z, q.w);
+  }
   const int oe = oth_e[0];
-  const f2 O[4] = {f2_pack(qa.x, qa.y), f2_pack(qa.z, qa.w), f2_pack(qb.x, qb.y), f2_pack(qb.z, qb.w)};
   const int dexp = st.e + oe - ss.eP;
   const float s = pow2_clamped(dexp) * ss.inv_mP;   // inv_mP in (0.5, 1]
   const f2 s2 = f2_pack(s, s);
-  f2 PO[4];
+  f2 PO[NP];
 #pragma unroll
-  for (int j = 0; j < 4; ++j) PO[j] = f2_mul(f2_mul(st.A[j], O[j]), s2);
+  for (int j = 0; j < NP; ++j) PO[j] = f2_mul(f2_mul(st.A[j], O[j]), s2);
   // Range check.  A state that sits more than 2^-110 below its lane's largest value may have lost
   // bits (on either side).  Its posterior is bounded by
   //   2^-110 * max(own lane) * max(other lane) * 2^dexp / mP,   max(own lane) in [1,2);
   // if that bound is not negligible (> 2^-24) the block-exponent result cannot be trusted.  The own
-  // maximum runs over ALL eight states: dead states (too late to finish) share the exponent.
+  // maximum runs over ALL states of the lane: dead states (too late to finish) share the exponent.
   // Evaluated on the exponent fields (a zero maximum has field 0 and can only lower the bound), so
   // it cannot overflow or underflow; the running maximum is tested at the chunk boundary.
-  const float omax = fmaxf(fmax3(f2_lo(O[0]), f2_hi(O[0]), f2_lo(O[1])),
-                           fmax3(fmax3(f2_hi(O[1]), f2_lo(O[2]), f2_hi(O[2])), f2_lo(O[3]), f2_hi(O[3])));
+  const float omax = f2_max_all<NP>(O);
   ss.maxbound = max(ss.maxbound, (__float_as_int(omax) >> 23) + dexp);
   if (store) {
-    constexpr int jL0 = SIDE ? 0 : 1, jL1 = SIDE ? 2 : 3, jB0 = SIDE ? 1 : 0, jB1 = SIDE ? 3 : 2;
-    sts_f32(post, lc.posB[0], el_j<SIDE>(PO[jL0]));
-    sts_f32(post, lc.posB[1], el_j<SIDE>(PO[jL1]));
-    sts_f32(post, lc.posB[2], el_j4<SIDE>(PO[jL0]));
-    sts_f32(post, lc.posB[3], el_j4<SIDE>(PO[jL1]));
-    const f2 bs = f2_add(PO[jB0], PO[jB1]);
-    sts_f32(post, lc.blankB, f2_lo(bs) + f2_hi(bs));
+    float bsum = 0.f;
+#pragma unroll
+    for (int j = 0; j < NP; ++j) {
+      const bool is_label = SIDE ? (j % 2 == 0) : (j % 2 == 1);
+      if (is_label) {
+        const int u = j / 2;
+        sts_f32(post, lc.posB[u], el_j<SIDE>(PO[j]));
+        sts_f32(post, lc.posB[u + NP / 2], el_j4<SIDE>(PO[j]));
+      } else {
+        bsum += f2_lo(PO[j]) + f2_hi(PO[j]);
+      }
+    }
+    sts_f32(post, lc.blankB, bsum);
   }
 }
 
 // One chunk (kc <= K frames starting at step n0; emission rows in ring slot `rslot`).  A warp whose
 // window misses the reachable band in all frames of the chunk skips it (warp-uniform).
-template <int K, bool PH2, int SIDE, int NT>
-__device__ __forceinline__ void run_chunk(const FastCtx<SIDE>& c, SweepState& ss, int rslot, int pbuf, int obuf,
+template <int K, bool PH2, int SIDE, int NT, int NS>
+__device__ __forceinline__ void run_chunk(const FastCtx<SIDE>& c, SweepState<NS>& ss, int rslot, int pbuf, int obuf,
                                           int n0, int kc, bool write_post) {
-  const LaneConst& lc = ss.lc;
+  constexpr int NP = NS / 2, NH = NS / 4;
+  const LaneConst<NS>& lc = ss.lc;
   const bool lane0 = c.lane == 0;
-  const char* rows = reinterpret_cast<const char*>(c.sm.rows + (size_t)rslot * K * c.RWS);
+  const char* row = reinterpret_cast<const char*>(c.sm.rows + (size_t)rslot * K * c.RWS);
   const int row_bytes = c.RWS * 4;
   const bool active = n0 <= ss.act_hi && n0 + kc - 1 >= ss.act_lo;
   if (!PH2) {
     if (!active) return;
     // scratch slot of this lane's group for the opposite side's reader (mirrored group order)
-    const int off0 = c.frame_of(n0) * c.J8 + (c.J8 - 1 - lc.group);
-    const int step = SIDE ? -c.J8 : c.J8;
-    auto frame = [&](int j) {
-      f2 ACC[4]; int E;
-      lattice_frame<SIDE>(ss.st, lc, reinterpret_cast<const float*>(rows + j * row_bytes), lane0, ACC, E);
+    int off = c.frame_of(n0) * c.JG + (c.JG - 1 - lc.group);
+    const int step = SIDE ? -c.JG : c.JG;
+    const int half_stride = c.T * c.JG;
+#pragma unroll 1
+    for (int j = 0; j < kc; ++j) {
+      f2 ACC[NP]; int E;
+      lattice_frame<SIDE, NS>(ss.st, lc, row, lane0, ACC, E);
       if (lc.owned) {
-        const int off = off0 + j * step;
-        // the reader's pair j is this lane's pair 3-j (mirrored group, mirrored packing)
-        asm volatile("st.global.v2.b64 [%0], {%1, %2};" ::"l"(c.scr_a + off), "l"(ACC[3]), "l"(ACC[2]) : "memory");
-        asm volatile("st.global.v2.b64 [%0], {%1, %2};" ::"l"(c.scr_b + off), "l"(ACC[1]), "l"(ACC[0]) : "memory");
+        // the reader's pair j is this lane's pair NP-1-j (mirrored group, mirrored packing)
+#pragma unroll
+        for (int h = 0; h < NH; ++h)
+          asm volatile("st.global.v2.b64 [%0], {%1, %2};" ::"l"(c.scr_m + h * half_stride + off),
+                       "l"(ACC[NP - 1 - 2 * h]), "l"(ACC[NP - 2 - 2 * h]) : "memory");
         c.scr_e[off] = E;
       }
-    };
-    if (kc == K) {
-#pragma unroll
-      for (int j = 0; j < K; ++j) frame(j);
-    } else {
-#pragma unroll 1
-      for (int j = 0; j < kc; ++j) frame(j);
+      row += row_bytes;
+      off += step;
     }
   } else {
     char* post = reinterpret_cast<char*>(c.sm.post + (size_t)pbuf * K * c.PS);
     const int post_bytes = c.PS * 4;
     const bool store = write_post && lc.owned;
     if (active) {
-      const float4* oa = c.sm.oth_a + obuf * K * NT + c.tid_side;
+      const float4* om = c.sm.oth_m + obuf * K * NH * NT + c.tid_side;
       const int* oe = c.sm.oth_e + obuf * K * NT + c.tid_side;
-      auto frame = [&](int j) {
-        f2 ACC[4]; int E;
-        lattice_frame<SIDE>(ss.st, lc, reinterpret_cast<const float*>(rows + j * row_bytes), lane0, ACC, E);
-        posterior_frame<SIDE>(ss, oa + j * NT, 2 * K * NT, oe + j * NT, post + j * post_bytes, store);
-      };
-      if (kc == K) {
-#pragma unroll
-        for (int j = 0; j < K; ++j) frame(j);
-      } else {
 #pragma unroll 1
-        for (int j = 0; j < kc; ++j) frame(j);
+      for (int j = 0; j < kc; ++j) {
+        f2 ACC[NP]; int E;
+        lattice_frame<SIDE, NS>(ss.st, lc, row, lane0, ACC, E);
+        posterior_frame<SIDE, NT, NS>(ss, om, oe, post, store);
+        row += row_bytes;
+        post += post_bytes;
+        om += NH * NT;
+        oe += NT;
       }
     } else if (store) {
 #pragma unroll 1
       for (int j = 0; j < kc; ++j) {
-        char* pr = post + j * post_bytes;
-        sts_f32(pr, lc.posB[0], 0.f); sts_f32(pr, lc.posB[1], 0.f);
-        sts_f32(pr, lc.posB[2], 0.f); sts_f32(pr, lc.posB[3], 0.f);
-        sts_f32(pr, lc.blankB, 0.f);
+#pragma unroll
+        for (int m = 0; m < NP; ++m) sts_f32(post, lc.posB[m], 0.f);
+        sts_f32(post, lc.blankB, 0.f);
+        post += post_bytes;
       }
     }
   }
 }
 
 // Chunk boundary of the lattice warps: everything this thread prefetched at the start of the chunk
-// has landed, publish the halo lane, ONE side barrier, import the halo.
-template <int K, int NWMAX, int SIDE>
-__device__ __forceinline__ void chunk_boundary(const FastCtx<SIDE>& c, SweepState& ss, int cc, int* abort_flag) {
-  static_assert(K == 4, "one halo lane per warp");
+// has landed, publish the halo lanes, ONE side barrier, import the halo.
+template <int K, int NWMAX, int SIDE, int NS>
+__device__ __forceinline__ void chunk_boundary(const FastCtx<SIDE>& c, SweepState<NS>& ss, int cc, int* abort_flag) {
+  constexpr int NH = NS / 4, HL = 2 * K / NS;
+  static_assert(HL * NS == 2 * K && HL >= 1, "the halo must be whole lanes");
   const int hb = cc & 1, NW = c.NW, w = c.w, lane = c.lane;
-  LaneState& st = ss.st;
-  if (w + 1 < NW && lane == 31) {
-    const int slot = hb * NWMAX + w;
-    c.sm.halo_a[slot] = make_float4(f2_lo(st.A[0]), f2_hi(st.A[0]), f2_lo(st.A[1]), f2_hi(st.A[1]));
-    c.sm.halo_b[slot] = make_float4(f2_lo(st.A[2]), f2_hi(st.A[2]), f2_lo(st.A[3]), f2_hi(st.A[3]));
+  LaneState<NS>& st = ss.st;
+  if (w + 1 < NW && lane >= 32 - HL) {
+    const int slot = (hb * NWMAX + w) * HL + (lane - (32 - HL));
+#pragma unroll
+    for (int h = 0; h < NH; ++h)
+      c.sm.halo_m[slot * NH + h] = make_float4(f2_lo(st.A[2 * h]), f2_hi(st.A[2 * h]), f2_lo(st.A[2 * h + 1]), f2_hi(st.A[2 * h + 1]));
     c.sm.halo_e[slot] = st.e;
   }
   if (ss.lc.owned && ss.maxbound > kLostBound) *abort_flag = 1;
   cp_async_wait<0>();
   named_bar_sync(bar_halo(SIDE), NW * 32);
-  if (w > 0 && lane == 0) {
-    const int slot = hb * NWMAX + (w - 1);
-    const float4 ha = c.sm.halo_a[slot], hv = c.sm.halo_b[slot];
-    st.A[0] = f2_pack(ha.x, ha.y); st.A[1] = f2_pack(ha.z, ha.w);
-    st.A[2] = f2_pack(hv.x, hv.y); st.A[3] = f2_pack(hv.z, hv.w);
+  if (w > 0 && lane < HL) {
+    const int slot = (hb * NWMAX + (w - 1)) * HL + lane;
+#pragma unroll
+    for (int h = 0; h < NH; ++h) {
+      const float4 hv = c.sm.halo_m[slot * NH + h];
+      st.A[2 * h] = f2_pack(hv.x, hv.y);
+      st.A[2 * h + 1] = f2_pack(hv.z, hv.w);
+    }
     st.e = c.sm.halo_e[slot];
   }
 }
@@ -549,22 +575,21 @@ __device__ __forceinline__ bool total_probability(const FastSideSmem& sm, int NW
   return true;
 }
 
-template <int K, int NWMAX, int SIDE>
+template <int K, int NWMAX, int SIDE, int NS>
 __device__ __forceinline__ void fill_ctx(FastCtx<SIDE>& c, const CallParams& p, int b, const UttMeta& m,
                                          unsigned char* side_smem, int w, int lane) {
   c.p = &p; c.b = b;
-  c.T = m.T; c.L = m.L; c.S = 2 * m.L + 1; c.J8 = (c.S + 7) / 8; c.P = 8 * c.J8;
-  c.NW = fast_warps_needed<K>(m.L);
+  c.T = m.T; c.L = m.L; c.S = 2 * m.L + 1; c.JG = (c.S + NS - 1) / NS; c.P = NS * c.JG;
+  c.NW = fast_warps_needed<K, NS>(m.L);
   c.RW = p.gathered ? m.W : (p.V + 3) / 4 * 4;
   c.RWS = c.RW + 4;
   c.PS = post_stride<NWMAX>(m.L, p.V);
   c.RC = c.PS - NWMAX * 32 - 4;                 // label slots come first, then the blank partials, then the dump slot
   c.w = w; c.lane = lane; c.tid_side = w * 32 + lane;
-  c.sm = carve_fast_side<K, NWMAX>(side_smem, m.L, c.RW, p.V);
+  c.sm = carve_fast_side<K, NWMAX, NS>(side_smem, m.L, c.RW, p.V);
   unsigned char* scr = p.scratch + m.scratch_off * kGroupBytes;
-  c.scr_a = reinterpret_cast<float4*>(scr);
-  c.scr_b = reinterpret_cast<float4*>(scr + (size_t)c.T * c.J8 * 16);
-  c.scr_e = reinterpret_cast<int*>(scr + (size_t)c.T * c.J8 * 32);
+  c.scr_m = reinterpret_cast<float4*>(scr);
+  c.scr_e = reinterpret_cast<int*>(scr + (size_t)c.T * c.JG * (NS * 4));
   const float* row_src; long long row_stride; int row_vec;
   if (p.gathered) {
     row_src = p.em + m.em_off; row_stride = m.W; row_vec = 4; c.per_row = m.W / 4;
@@ -578,7 +603,7 @@ __device__ __forceinline__ void fill_ctx(FastCtx<SIDE>& c, const CallParams& p, 
   c.st_src = reinterpret_cast<const char*>(row_src) + lane * c.st_vecB;
   c.st_stride = (int)(row_stride * 4);          // api.cu rejects mini-batches whose frame stride exceeds 2^31 bytes
   c.st_dst = (unsigned)__cvta_generic_to_shared(c.sm.rows) + (unsigned)(lane * c.st_vecB);
-  c.oth_dst = (unsigned)__cvta_generic_to_shared(c.sm.oth_a + c.tid_side);
+  c.oth_dst = (unsigned)__cvta_generic_to_shared(c.sm.oth_m + c.tid_side);
   c.oth_dst_e = (unsigned)__cvta_generic_to_shared(c.sm.oth_e + c.tid_side);
 }
 
@@ -598,31 +623,35 @@ __device__ __forceinline__ SidePlan side_plan(int T) {
 // ---------------------------------------------------------------------------------------------
 // lattice warps of one side
 // ---------------------------------------------------------------------------------------------
-template <int K, int NWMAX, int SIDE>
+template <int K, int NWMAX, int SIDE, int NS>
 __device__ void fast_side_sweep(const CallParams& p, int b, const UttMeta& m, const FastCommon& cm,
                                 unsigned char* side_smem, int w, int lane) {
-  constexpr int H = 2 * K;          // halo positions (one lane)
-  constexpr int OWN = 256 - H;
+  constexpr int NP = NS / 2, NH = NS / 4;
+  constexpr int H = 2 * K;          // halo positions
+  constexpr int HL = H / NS;        // halo lanes
+  constexpr int WIN = 32 * NS;      // positions per warp window
+  constexpr int OWN = WIN - H;
+  constexpr int OWNG = OWN / NS;    // owned groups per warp
   constexpr int NT = NWMAX * 32;
 
   FastCtx<SIDE> c;
-  fill_ctx<K, NWMAX, SIDE>(c, p, b, m, side_smem, w, lane);
-  const int T = c.T, S = c.S, J8 = c.J8, P = c.P, NW = c.NW;
+  fill_ctx<K, NWMAX, SIDE, NS>(c, p, b, m, side_smem, w, lane);
+  const int T = c.T, S = c.S, JG = c.JG, P = c.P, NW = c.NW;
   const int* lab = cm.lab;
 
   // ---- per-lane constants ----
-  SweepState ss;
-  LaneConst& lc = ss.lc;
+  SweepState<NS> ss;
+  LaneConst<NS>& lc = ss.lc;
   const int base_w = w * OWN;
-  const int pos0 = base_w + 8 * lane;
-  lc.group = pos0 >> 3;
-  lc.owned = ((w == 0) || (lane >= 1)) && (lc.group < J8);
+  const int pos0 = base_w + NS * lane;
+  lc.group = pos0 / NS;
+  lc.owned = ((w == 0) || (lane >= HL)) && (lc.group < JG);
   lc.idxB_blank = 4 * (p.gathered ? 0 : p.blank);
   lc.blankB = 4 * (c.RC + c.tid_side);
   {
-    float kk[4];
+    float kk[NP];
 #pragma unroll
-    for (int mslot = 0; mslot < 4; ++mslot) {
+    for (int mslot = 0; mslot < NP; ++mslot) {
       const int q = pos0 + (SIDE ? 2 * mslot : 2 * mslot + 1);   // label positions of the lane
       const int s = SIDE ? (P - 1 - q) : q;
       const bool ok = (q < P) && (s >= 0) && (s < S);             // s is odd by construction
@@ -637,13 +666,13 @@ __device__ void fast_side_sweep(const CallParams& p, int b, const UttMeta& m, co
         kk[mslot] = sk ? 1.f : 0.f;
       }
     }
-    lc.K0 = mk<SIDE>(kk[0], kk[2]);
-    lc.K1 = mk<SIDE>(kk[1], kk[3]);
+#pragma unroll
+    for (int u = 0; u < NP / 2; ++u) lc.Kf[u] = mk<SIDE>(kk[u], kk[u + NP / 2]);
   }
   {
     // steps in which this warp's window intersects the reachable band (the same for every lane:
     // broadcast from lane 0 so that the compiler can see the chunk-skip branch is warp-uniform)
-    const int win_lo_pos = base_w, win_hi_pos = min(base_w + 255, P - 1);
+    const int win_lo_pos = base_w, win_hi_pos = min(base_w + WIN - 1, P - 1);
     const int ws_lo = SIDE ? (P - 1 - win_hi_pos) : win_lo_pos;
     const int ws_hi = SIDE ? (P - 1 - win_lo_pos) : win_hi_pos;
     int t0, t1;
@@ -654,37 +683,37 @@ __device__ void fast_side_sweep(const CallParams& p, int b, const UttMeta& m, co
     ss.act_hi = __shfl_sync(0xffffffffu, a_hi, 0);
     // which phase-1 records of this lane's group the OTHER side wrote: its warp that owns the mirrored
     // group was active in the chunk (K steps aligned at its step 0) that holds the frame
-    const int G = J8 - 1 - lc.group;                       // the writer's group index
-    const int wo = G <= 31 ? 0 : (G - 1) / 31;             // its owner warp (lane 0 of warps > 0 is halo)
-    const int o_lo_pos = wo * OWN, o_hi_pos = min(wo * OWN + 255, P - 1);
+    const int G = JG - 1 - lc.group;                          // the writer's group index
+    const int wo = G < 32 ? 0 : (G - HL) / OWNG;              // its owner warp (the first HL lanes of warps > 0 are halo)
+    const int o_lo_pos = wo * OWN, o_hi_pos = min(wo * OWN + WIN - 1, P - 1);
     const int os_lo = SIDE ? o_lo_pos : (P - 1 - o_hi_pos);   // the writer is the opposite side
     const int os_hi = SIDE ? o_hi_pos : (P - 1 - o_lo_pos);
     band_frames(os_lo, os_hi, S, T, t0, t1);
-    const int M_other = SIDE ? (T - T / 2) : (T / 2);       // frames the other side covers in phase 1
-    int na = SIDE ? t0 : T - 1 - t1;                        // in the writer's steps
+    const int M_other = SIDE ? (T - T / 2) : (T / 2);         // frames the other side covers in phase 1
+    int na = SIDE ? t0 : T - 1 - t1;                          // in the writer's steps
     int nb = min(SIDE ? t1 : T - 1 - t0, M_other - 1);
     ss.rd_hi = 0; ss.wr_len = 0;
-    if (t0 <= t1 && na <= nb && lc.group < J8) {
+    if (t0 <= t1 && na <= nb && lc.group < JG) {
       na = na / K * K;
       nb = nb / K * K + K - 1;
-      ss.rd_hi = T - 1 - na;                                // writer step n' = T-1-n for a reader at step n
+      ss.rd_hi = T - 1 - na;                                  // writer step n' = T-1-n for a reader at step n
       ss.wr_len = nb - na + 1;
     }
   }
   // ---- initial state: delta on the first lattice state of this side's sweep ----
   {
-    float v[8];
+    float v[NS];
 #pragma unroll
-    for (int i = 0; i < 8; ++i) v[i] = 0.f;
+    for (int i = 0; i < NS; ++i) v[i] = 0.f;
     ss.st.e = kEZero;
-    const int q_start = SIDE ? (P - S) : 0;   // backward: 8*J8 - S dummy positions come first
-    if (w == 0 && q_start >= pos0 && q_start < pos0 + 8) {
+    const int q_start = SIDE ? (P - S) : 0;   // backward: NS*JG - S dummy positions come first
+    if (w == 0 && q_start >= pos0 && q_start < pos0 + NS) {
 #pragma unroll
-      for (int i = 0; i < 8; ++i) if (q_start - pos0 == i) v[i] = 1.f;
+      for (int i = 0; i < NS; ++i) if (q_start - pos0 == i) v[i] = 1.f;
       ss.st.e = 0;
     }
 #pragma unroll
-    for (int j = 0; j < 4; ++j) ss.st.A[j] = mk<SIDE>(v[j], v[j + 4]);
+    for (int j = 0; j < NP; ++j) ss.st.A[j] = mk<SIDE>(v[j], v[j + NP]);
   }
   ss.maxbound = -(1 << 30); ss.inv_mP = 0.f; ss.eP = 0;
 
@@ -713,8 +742,8 @@ __device__ void fast_side_sweep(const CallParams& p, int b, const UttMeta& m, co
     const int nn = n0 + kc;                               // first step of the next chunk (phase 1 or 2)
     if (nn < T) stage_rows<K, SIDE>(c, rs_next, nn, min(K, (nn < M_side ? M_side : T) - nn));   // lands during this chunk
     cp_async_commit();
-    run_chunk<K, false, SIDE, NT>(c, ss, rs, 0, 0, n0, kc, false);
-    chunk_boundary<K, NWMAX, SIDE>(c, ss, cc, abort_flag);
+    run_chunk<K, false, SIDE, NT, NS>(c, ss, rs, 0, 0, n0, kc, false);
+    chunk_boundary<K, NWMAX, SIDE, NS>(c, ss, cc, abort_flag);
     rs = rs_next;
   }
 
@@ -724,30 +753,28 @@ __device__ void fast_side_sweep(const CallParams& p, int b, const UttMeta& m, co
   if (nc2 == 0) return;
 
   // the opposite side's records of the first phase-2 chunk
-  prefetch_other<K, SIDE, NT>(c, ss, 0, M_side, min(K, T - M_side));
+  prefetch_other<K, SIDE, NT, NS>(c, ss, 0, M_side, min(K, T - M_side));
   cp_async_commit();
   cp_async_wait<0>();
 
   // ---- total probability P = sum_s alpha_t(s) beta'_t(s) at the first phase-2 frame (state copy) ----
   {
-    const int rslot = rs, n0 = M_side;
-    LaneState tmp = ss.st;
+    const int n0 = M_side;
+    LaneState<NS> tmp = ss.st;
     float part = 0.f; int pe = kEZero;
     if (n0 <= ss.act_hi && n0 + min(K, T - M_side) - 1 >= ss.act_lo) {   // same rule as run_chunk: the warp runs this chunk
-      f2 ACC[4]; int E;
-      lattice_frame<SIDE>(tmp, lc, c.sm.rows + (size_t)rslot * K * c.RWS, lane == 0, ACC, E);
+      f2 ACC[NP]; int E;
+      lattice_frame<SIDE, NS>(tmp, lc, c.sm.rows + (size_t)rs * K * c.RWS, lane == 0, ACC, E);
       if (lc.owned) {
-        const float4 qa = c.sm.oth_a[c.tid_side], qb = c.sm.oth_a[2 * K * NT + c.tid_side];
-        const int oe = c.sm.oth_e[c.tid_side];
-        const f2 O[4] = {f2_pack(qa.x, qa.y), f2_pack(qa.z, qa.w), f2_pack(qb.x, qb.y), f2_pack(qb.z, qb.w)};
         // no band masks: outside the band one of the two factors is exactly zero (posterior_frame)
         float sum = 0.f;
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          const f2 pr = f2_mul(tmp.A[j], O[j]);
-          sum += f2_lo(pr) + f2_hi(pr);
+        for (int h = 0; h < NH; ++h) {
+          const float4 q = c.sm.oth_m[h * NT + c.tid_side];
+          const f2 p0 = f2_mul(tmp.A[2 * h], f2_pack(q.x, q.y)), p1 = f2_mul(tmp.A[2 * h + 1], f2_pack(q.z, q.w));
+          sum += (f2_lo(p0) + f2_hi(p0)) + (f2_lo(p1) + f2_hi(p1));
         }
-        if (sum > 0.f) { part = sum; pe = tmp.e + oe; }
+        if (sum > 0.f) { part = sum; pe = tmp.e + c.sm.oth_e[c.tid_side]; }
       }
     }
     int emax = pe;
@@ -776,15 +803,14 @@ __device__ void fast_side_sweep(const CallParams& p, int b, const UttMeta& m, co
     if (write_post && k2 >= 2) named_bar_sync(bar_free(SIDE, par), (NW + kReducers) * 32);   // reducers done with post[par]
     if (n0 + K < T) {
       stage_rows<K, SIDE>(c, rs_next, n0 + K, min(K, T - n0 - K));
-      prefetch_other<K, SIDE, NT>(c, ss, par ^ 1, n0 + K, min(K, T - n0 - K));
+      prefetch_other<K, SIDE, NT, NS>(c, ss, par ^ 1, n0 + K, min(K, T - n0 - K));
     }
     cp_async_commit();
-    run_chunk<K, true, SIDE, NT>(c, ss, rs, par, par, n0, kc, write_post);
-    chunk_boundary<K, NWMAX, SIDE>(c, ss, cc, abort_flag);
+    run_chunk<K, true, SIDE, NT, NS>(c, ss, rs, par, par, n0, kc, write_post);
+    chunk_boundary<K, NWMAX, SIDE, NS>(c, ss, cc, abort_flag);
     if (write_post) named_bar_arrive(bar_ready(SIDE, par), (NW + kReducers) * 32);    // post[par] of chunk cc is complete
     rs = rs_next;
   }
-  (void)nc2;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -810,12 +836,12 @@ __device__ __forceinline__ float post_row_sum_c4(const float4* __restrict__ row4
 }
 
 // Reducer warp rj of the side handles frame rj of every phase-2 chunk.
-template <int K, int NWMAX, int SIDE>
+template <int K, int NWMAX, int SIDE, int NS>
 __device__ void fast_side_reduce(const CallParams& p, int b, const UttMeta& m, const FastCommon& cm,
                                  unsigned char* side_smem, int rj, int lane) {
   static_assert(kReducers == K, "one reducer warp per frame of a chunk");
   FastCtx<SIDE> c;
-  fill_ctx<K, NWMAX, SIDE>(c, p, b, m, side_smem, NWMAX + rj, lane);
+  fill_ctx<K, NWMAX, SIDE, NS>(c, p, b, m, side_smem, NWMAX + rj, lane);
   const int T = c.T, NW = c.NW, V = p.V;
   const SidePlan pl = side_plan<K, SIDE>(T);
   if (pl.nc2 == 0) return;
@@ -884,11 +910,11 @@ __device__ void fast_side_reduce(const CallParams& p, int b, const UttMeta& m, c
 // The whole fast path for one utterance; every thread of the CTA calls it.  On return the shared
 // word (*smem_abort)[0] is non-zero when the utterance must be redone by the safe lattice (the
 // caller reads it after a __syncthreads()).
-template <int K, int NWMAX>
+template <int K, int NWMAX, int NS>
 __device__ void lattice_fast_utterance(const CallParams& p, int b, unsigned char* smem, int** smem_abort) {
   const UttMeta m = p.meta[b];
   const int L = m.L;
-  const int NW = fast_warps_needed<K>(L);
+  const int NW = fast_warps_needed<K, NS>(L);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int side = warp / (NWMAX + kReducers);
   const int w = warp - side * (NWMAX + kReducers);
@@ -908,7 +934,7 @@ __device__ void lattice_fast_utterance(const CallParams& p, int b, unsigned char
   size_t common = (size_t)(reinterpret_cast<unsigned char*>(ip) - smem);
   common = (common + 15) / 16 * 16;
   const int RW = p.gathered ? m.W : (p.V + 3) / 4 * 4;
-  const size_t side_bytes = fast_side_bytes<K, NWMAX>(L, RW, p.V);
+  const size_t side_bytes = fast_side_bytes<K, NWMAX, NS>(L, RW, p.V);
   *smem_abort = cm.abort_flag;
 
   // ---- prologue (all threads of the CTA) ----
@@ -918,7 +944,7 @@ __device__ void lattice_fast_utterance(const CallParams& p, int b, unsigned char
   {
     const int PS = post_stride<NWMAX>(L, p.V);
     for (int sd = 0; sd < 2; ++sd) {
-      FastSideSmem s = carve_fast_side<K, NWMAX>(smem + common + sd * side_bytes, L, RW, p.V);
+      FastSideSmem s = carve_fast_side<K, NWMAX, NS>(smem + common + sd * side_bytes, L, RW, p.V);
       for (int i = threadIdx.x; i < 2 * K * PS; i += blockDim.x) s.post[i] = 0.f;
     }
   }
@@ -952,11 +978,11 @@ __device__ void lattice_fast_utterance(const CallParams& p, int b, unsigned char
     __syncthreads();
   }
   if (w < NW) {
-    if (side == 0) fast_side_sweep<K, NWMAX, 0>(p, b, m, cm, smem + common, w, lane);
-    else           fast_side_sweep<K, NWMAX, 1>(p, b, m, cm, smem + common + side_bytes, w, lane);
+    if (side == 0) fast_side_sweep<K, NWMAX, 0, NS>(p, b, m, cm, smem + common, w, lane);
+    else           fast_side_sweep<K, NWMAX, 1, NS>(p, b, m, cm, smem + common + side_bytes, w, lane);
   } else if (w >= NWMAX) {
-    if (side == 0) fast_side_reduce<K, NWMAX, 0>(p, b, m, cm, smem + common, w - NWMAX, lane);
-    else           fast_side_reduce<K, NWMAX, 1>(p, b, m, cm, smem + common + side_bytes, w - NWMAX, lane);
+    if (side == 0) fast_side_reduce<K, NWMAX, 0, NS>(p, b, m, cm, smem + common, w - NWMAX, lane);
+    else           fast_side_reduce<K, NWMAX, 1, NS>(p, b, m, cm, smem + common + side_bytes, w - NWMAX, lane);
   }
   // idle warps wait at the caller's __syncthreads()
 }
