@@ -41,9 +41,12 @@ def _stale(target, deps):
     return any(os.path.getmtime(d) > t for d in deps)
 
 
-def build_library(force=False, verbose=False):
-    """Compile csrc/*.cu into lib/libb200ctc.so (no-op when up to date)."""
+def build_library(force=False, verbose=False, extra_flags=(), lib_path=None):
+    """Compile csrc/*.cu into lib/libb200ctc.so (no-op when up to date).  ``extra_flags`` /
+    ``lib_path`` build a developer variant next to it (tools/trace_lattice.py: -DB200CTC_TRACE)."""
     os.makedirs(LIB_DIR, exist_ok=True)
+    if lib_path is not None:
+        return _build_variant(list(extra_flags), lib_path, verbose)
     deps = [os.path.join(CSRC, f) for f in os.listdir(CSRC)] + [os.path.join(REPO_DIR, "include", "b200ctc.h")]
     if not force and not _stale(LIB_PATH, deps):
         return LIB_PATH
@@ -60,6 +63,21 @@ def build_library(force=False, verbose=False):
     cmd = [_nvcc(), "-shared", "-o", LIB_PATH] + objs + ["-Xcompiler", "-fPIC"]
     subprocess.run(cmd, check=True)
     return LIB_PATH
+
+
+def _build_variant(extra_flags, lib_path, verbose):
+    objs = []
+    tag = os.path.basename(lib_path).replace(".so", "")
+    for src in SOURCES:
+        obj = os.path.join(LIB_DIR, "%s_%s" % (tag, src.replace(".cu", ".o")))
+        cmd = [_nvcc()] + NVCC_FLAGS + extra_flags + ["-I", os.path.join(REPO_DIR, "include"), "-I", CSRC,
+                                                      "-c", os.path.join(CSRC, src), "-o", obj]
+        if verbose:
+            print(" ".join(cmd), file=sys.stderr)
+        subprocess.run(cmd, check=True)
+        objs.append(obj)
+    subprocess.run([_nvcc(), "-shared", "-o", lib_path] + objs + ["-Xcompiler", "-fPIC"], check=True)
+    return lib_path
 
 
 if __name__ == "__main__":

@@ -107,6 +107,18 @@ cudaError_t launch_lattice(const CallParams& p, int max_L, cudaStream_t stream) 
   return launch_lattice_t<kChunk, 4, 8>(p, max_L, stream);   // longer label sequences (L > 499) take the safe lattice
 }
 
+#ifdef B200CTC_TRACE
+// developer hook: copies the timeline of CTA 0 of the last lattice launch and clears it
+extern "C" __attribute__((visibility("default"))) int b200ctc_debug_read_trace(long long* host, int* counts) {
+  if (cudaDeviceSynchronize() != cudaSuccess) return 2;
+  if (cudaMemcpyFromSymbol(host, g_trace, sizeof(long long) * 64 * kTraceCap) != cudaSuccess) return 2;
+  if (cudaMemcpyFromSymbol(counts, g_trace_cnt, sizeof(int) * 64) != cudaSuccess) return 2;
+  static int zeros[64];
+  if (cudaMemcpyToSymbol(g_trace_cnt, zeros, sizeof(zeros)) != cudaSuccess) return 2;
+  return 0;
+}
+#endif
+
 cudaError_t launch_cost_sum(const CallParams& p, cudaStream_t stream) {
   if (!p.loss_sum) return cudaSuccess;
   cost_sum_kernel<<<1, 256, 0, stream>>>(p.costs, p.B, p.loss_sum);

@@ -47,6 +47,25 @@
 
 namespace b200ctc {
 
+// Developer timeline trace (tools/trace_lattice.py): compiled in only with -DB200CTC_TRACE.
+#ifdef B200CTC_TRACE
+constexpr int kTraceCap = 4096;
+__device__ long long g_trace[64 * kTraceCap];
+__device__ int g_trace_cnt[64];
+__device__ __forceinline__ void trace_event(int& cnt, int tag) {
+  if (blockIdx.x == 0 && (threadIdx.x & 31) == 0 && cnt < kTraceCap) {
+    g_trace[(threadIdx.x >> 5) * kTraceCap + cnt] = ((long long)clock64() << 8) | tag;
+    ++cnt;
+    g_trace_cnt[threadIdx.x >> 5] = cnt;
+  }
+}
+#define B200CTC_TRACE_DECL(cnt) int cnt = 0
+#define B200CTC_TRACE_EVENT(cnt, tag) trace_event(cnt, tag)
+#else
+#define B200CTC_TRACE_DECL(cnt) int cnt = 0
+#define B200CTC_TRACE_EVENT(cnt, tag) do { (void)cnt; } while (0)
+#endif
+
 constexpr int kEZero = -(1 << 28);  // exponent of an all-zero lane
 constexpr int kRowsRing = 3;        // emission-row chunks in flight (this chunk, the next one, the reducers' one)
 constexpr int kOthRing = 8;         // per-thread ring of the opposite side's records: two chunks of K = 4 frames
@@ -716,6 +735,8 @@ __device__ void fast_side_sweep(const CallParams& p, int b, const UttMeta& m, co
     for (int j = 0; j < NP; ++j) ss.st.A[j] = mk<SIDE>(v[j], v[j + NP]);
   }
   ss.maxbound = -(1 << 30); ss.inv_mP = 0.f; ss.eP = 0;
+  B200CTC_TRACE_DECL(tc);
+  B200CTC_TRACE_EVENT(tc, 10);
 
   const SidePlan pl = side_plan<K, SIDE>(T);
   const int M_side = pl.M_side, nc1 = pl.nc1, nc2 = pl.nc2;
@@ -740,10 +761,14 @@ __device__ void fast_side_sweep(const CallParams& p, int b, const UttMeta& m, co
     const int kc = min(K, M_side - n0);
     const int rs_next = rs == kRowsRing - 1 ? 0 : rs + 1;
     const int nn = n0 + kc;                               // first step of the next chunk (phase 1 or 2)
+    B200CTC_TRACE_EVENT(tc, 1);
     if (nn < T) stage_rows<K, SIDE>(c, rs_next, nn, min(K, (nn < M_side ? M_side : T) - nn));   // lands during this chunk
     cp_async_commit();
+    B200CTC_TRACE_EVENT(tc, 2);
     run_chunk<K, false, SIDE, NT, NS>(c, ss, rs, 0, 0, n0, kc, false);
+    B200CTC_TRACE_EVENT(tc, 3);
     chunk_boundary<K, NWMAX, SIDE, NS>(c, ss, cc, abort_flag);
+    B200CTC_TRACE_EVENT(tc, 5);
     rs = rs_next;
   }
 
@@ -800,14 +825,20 @@ __device__ void fast_side_sweep(const CallParams& p, int b, const UttMeta& m, co
   for (int n0 = M_side; n0 < T; n0 += K, ++k2, ++cc) {
     const int kc = min(K, T - n0), par = k2 & 1;
     const int rs_next = rs == kRowsRing - 1 ? 0 : rs + 1;
+    B200CTC_TRACE_EVENT(tc, 6);
     if (write_post && k2 >= 2) named_bar_sync(bar_free(SIDE, par), (NW + kReducers) * 32);   // reducers done with post[par]
+    B200CTC_TRACE_EVENT(tc, 11);
     if (n0 + K < T) {
       stage_rows<K, SIDE>(c, rs_next, n0 + K, min(K, T - n0 - K));
+      B200CTC_TRACE_EVENT(tc, 12);
       prefetch_other<K, SIDE, NT, NS>(c, ss, par ^ 1, n0 + K, min(K, T - n0 - K));
     }
     cp_async_commit();
+    B200CTC_TRACE_EVENT(tc, 13);
     run_chunk<K, true, SIDE, NT, NS>(c, ss, rs, par, par, n0, kc, write_post);
+    B200CTC_TRACE_EVENT(tc, 14);
     chunk_boundary<K, NWMAX, SIDE, NS>(c, ss, cc, abort_flag);
+    B200CTC_TRACE_EVENT(tc, 15);
     if (write_post) named_bar_arrive(bar_ready(SIDE, par), (NW + kReducers) * 32);    // post[par] of chunk cc is complete
     rs = rs_next;
   }
@@ -858,10 +889,13 @@ __device__ void fast_side_reduce(const CallParams& p, int b, const UttMeta& m, c
   const bool one_row = (R == n_seg);                  // every symbol fits one row: row index == segment index
   const int sym_first = lane < n_seg ? cm.ix.seg_sym[lane] : 0;
   float* rowsum = c.sm.rowsum + (size_t)rj * (post_rows_max(c.L, V) + 4);
+  B200CTC_TRACE_DECL(tc);
   for (int cc = pl.nc1; cc < pl.n_chunks; ++cc) {
     const int k2 = cc - pl.nc1, par = k2 & 1;
     const int n0 = pl.M_side + k2 * K, kc = min(K, T - n0);
+    B200CTC_TRACE_EVENT(tc, 7);
     named_bar_sync(bar_ready(SIDE, par), (NW + kReducers) * 32);
+    B200CTC_TRACE_EVENT(tc, 8);
     if (rj < kc) {
       const float* post = c.sm.post + (size_t)(par * K + rj) * c.PS;
       const float4* post4 = reinterpret_cast<const float4*>(post);
@@ -903,6 +937,7 @@ __device__ void fast_side_reduce(const CallParams& p, int b, const UttMeta& m, c
         else atomicAdd(grow + p.blank, -accb);
       }
     }
+    B200CTC_TRACE_EVENT(tc, 9);
     if (cc + 2 < pl.n_chunks) named_bar_arrive(bar_free(SIDE, par), (NW + kReducers) * 32);
   }
 }

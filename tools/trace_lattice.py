@@ -1,0 +1,67 @@
+"""Developer tool (GPU box): timeline of the lattice kernel's CTA 0 (the longest utterance).
+
+Builds a -DB200CTC_TRACE variant of the library (lib/libb200ctc_trace.so), runs one C3-shaped call
+through it and prints, per warp role, where the cycles of a chunk go:
+  lattice warps, phase 1: [1] chunk start -> [2] rows staged -> [3] frames done -> [5] boundary passed
+                 phase 2: [6] chunk start -> [11] reducers released the buffer -> [12] rows staged ->
+                          [13] records prefetched -> [14] frames done -> [15] boundary passed
+  reducer warps: [7] waiting for posteriors -> [8] got them -> [9] rows written
+Usage: python tools/trace_lattice.py [C3] [--build-only]
+"""
+import ctypes
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from pytorch_end2end_speech_recognition_b200 import build as b  # noqa: E402
+
+LIB = os.path.join(b.LIB_DIR, "libb200ctc_trace.so")
+
+
+def main():
+    key = next((a for a in sys.argv[1:] if a.startswith("C")), "C3")
+    if not os.path.exists(LIB) or "--rebuild" in sys.argv or "--build-only" in sys.argv:
+        b.build_library(extra_flags=["-DB200CTC_TRACE"], lib_path=LIB)
+    if "--build-only" in sys.argv:
+        return
+    import numpy as np
+    import torch
+    b.LIB_PATH = LIB                      # make the package load the trace variant
+    import pytorch_end2end_speech_recognition_b200 as eng
+    from pytorch_end2end_speech_recognition_b200 import _lib, workloads
+    wl = workloads.make_lengths_and_labels(key)
+    acts = workloads.make_acts(wl).cuda()
+    lib = _lib.load()
+    cap = 4096
+    host = (ctypes.c_longlong * (64 * cap))()
+    cnt = (ctypes.c_int * 64)()
+    for _ in range(3):
+        eng.ctc_loss_and_grad(acts, wl.labels, wl.act_lens, wl.label_lens)
+        torch.cuda.synchronize()
+        assert lib.b200ctc_debug_read_trace(host, cnt) == 0
+    ev = np.frombuffer(host, dtype=np.int64).reshape(64, cap)
+    counts = np.frombuffer(cnt, dtype=np.int32)
+    t_all = [ev[w, :counts[w]] >> 8 for w in range(64)]
+    tag_all = [ev[w, :counts[w]] & 0xff for w in range(64)]
+    t0 = min(int(t[0]) for t in t_all if len(t))
+    t1 = max(int(t[-1]) for t in t_all if len(t))
+    print("CTA 0 (utterance with L=%d, T=%d): %d cycles traced" % (wl.label_lens.max(), wl.T, t1 - t0))
+    for w in range(64):
+        t, tag = t_all[w], tag_all[w]
+        if not len(t):
+            continue
+        segs = {}
+        for i in range(1, len(t)):
+            k = (int(tag[i - 1]), int(tag[i]))
+            d = int(t[i] - t[i - 1])
+            s = segs.setdefault(k, [0, 0])
+            s[0] += d
+            s[1] += 1
+        span = int(t[-1] - t[0])
+        desc = ", ".join("%d->%d: %d x %.0f" % (k[0], k[1], v[1], v[0] / v[1]) for k, v in sorted(segs.items()) if v[0] > 0.01 * span)
+        print("warp %2d  first %7d  span %7d  %s" % (w, int(t[0]) - t0, span, desc))
+
+
+if __name__ == "__main__":
+    main()
