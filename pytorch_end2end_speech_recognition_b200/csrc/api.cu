@@ -33,11 +33,15 @@ struct BatchTotals {
 };
 
 // scratch units (32 bytes) per frame: the safe lattice stores 4 doubles per group of four states,
-// the fast lattice 36 bytes per group of eight states
+// the fast lattice a little more than that for very short label sequences
 inline int groups_of(int L) {
   const int j4 = (2 * L + 1 + 3) / 4, j8 = (2 * L + 1 + 7) / 8;
-  const int fast_units = (36 * j8 + 31) / 32;
-  return j4 > fast_units ? j4 : fast_units;
+  // fast lattice: NS*4 bytes of mantissas per group of NS states + an int32 exponent row padded to 4 groups
+  const int fast8 = (36 * j8 + 12 + 31) / 32, fast4 = (20 * j4 + 12 + 31) / 32;
+  int u = j4;                       // safe lattice: 4 doubles per group of four states
+  u = u > fast8 ? u : fast8;
+  u = u > fast4 ? u : fast4;
+  return u;
 }
 inline int em_width_of(int L) { return (L + 1 + 3) / 4 * 4; }
 

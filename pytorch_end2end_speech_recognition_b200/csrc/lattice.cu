@@ -88,11 +88,10 @@ cudaError_t launch_lattice_t(const CallParams& p, int max_L, cudaStream_t stream
 
 cudaError_t launch_lattice(const CallParams& p, int max_L, cudaStream_t stream) {
   if (p.B == 0) return cudaSuccess;
-  // States per lane: four (twice the lattice warps, better latency hiding) while the label sequence
-  // fits eight warps per side, eight beyond.  B200CTC_NS=4|8 overrides the choice (tuning knob).
-  int ns = fast_warps_needed<kChunk, 4>(max_L) <= 8 ? 4 : 8;
+  // States per lane: eight (fewer instructions per lattice state); four states per lane with twice the
+  // lattice warps is kept as a tuning alternative (B200CTC_NS=4, label sequences up to 483).
+  int ns = 8;
   if (const char* e = std::getenv("B200CTC_NS")) {
-    if (e[0] == '8') ns = 8;
     if (e[0] == '4' && fast_warps_needed<kChunk, 4>(max_L) <= 8) ns = 4;
   }
   if (ns == 4) {

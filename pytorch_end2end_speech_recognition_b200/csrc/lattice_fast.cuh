@@ -96,6 +96,30 @@ __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commi
 template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
+// ---- TMA 1-D bulk copy (global -> shared, completion on an mbarrier) ----
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, int count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, unsigned bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "WAIT_%=:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra DONE_%=;\n"
+      "bra WAIT_%=;\n"
+      "DONE_%=:\n"
+      "}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gmem_src, unsigned bytes, unsigned long long* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(smem_u32(smem_dst)), "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+
 // 2^d for d <= 0 (0 when d < -126)
 __device__ __forceinline__ float pow2_neg(int d) { return __int_as_float(max(d + 127, 0) << 23); }
 // 2^d clamped to [2^-127 -> 0, 2^127]
@@ -172,7 +196,7 @@ __host__ __device__ inline int post_rows_max(int L, int V) {
 
 struct FastSideSmem {
   float* rows;      // [kRowsRing][K][RWS]     staged emission rows (+ a zero slot at index RW)
-  float4* oth_m;    // [2][K][NS/4][NT]        opposite side's stored pairs of this thread's group, two chunks
+  float4* oth_m;    // [2][K][NS/4][NT]        opposite side's stored pairs, indexed by position group, two chunks
   int* oth_e;       // [2][K][NT]              ... exponent
   float* post;      // [2][K][PS]              symbol-sorted label posteriors + blank partials + dump slot
   float4* halo_m;   // [2][NWMAX][HL][NS/4]    halo lanes
@@ -180,6 +204,7 @@ struct FastSideSmem {
   float* red_m;     // [NWMAX]
   int* red_e;       // [NWMAX]
   float* rowsum;    // [kReducers][Rmax+4]     reducer scratch (symbols spanning several rows)
+  unsigned long long* mbar;   // [kReducers]   one mbarrier per helper warp (TMA bulk copies of the records)
 };
 
 template <int NWMAX>
@@ -200,6 +225,7 @@ __host__ __device__ inline size_t fast_side_bytes(int L, int RW, int V) {
   b += (size_t)2 * NWMAX * HL * 4;                           // halo_e
   b += NWMAX * 8;                                            // red
   b += (size_t)kReducers * (post_rows_max(L, V) + 4) * 4;    // rowsum (one per reducer warp)
+  b += (size_t)kReducers * 8 + 8;                            // mbar
   return (b + 15) / 16 * 16;
 }
 template <int K, int NWMAX, int NS>
@@ -224,7 +250,9 @@ __device__ __forceinline__ FastSideSmem carve_fast_side(unsigned char* base, int
   s.halo_e = reinterpret_cast<int*>(p);    p += (size_t)2 * NWMAX * HL * 4;
   s.red_m = reinterpret_cast<float*>(p);   p += NWMAX * 4;
   s.red_e = reinterpret_cast<int*>(p);     p += NWMAX * 4;
-  s.rowsum = reinterpret_cast<float*>(p);
+  s.rowsum = reinterpret_cast<float*>(p);  p += (size_t)kReducers * (post_rows_max(L, V) + 4) * 4;
+  p = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(p) + 7) / 8 * 8);
+  s.mbar = reinterpret_cast<unsigned long long*>(p);
   return s;
 }
 
@@ -239,11 +267,9 @@ struct FastCommon {
 };
 
 // named barrier ids (0 is __syncthreads)
-__device__ __forceinline__ int bar_halo(int side) { return 1 + side * 6; }
-__device__ __forceinline__ int bar_total(int side) { return 2 + side * 6; }
-__device__ __forceinline__ int bar_ready(int side, int par) { return 3 + side * 6 + par; }
-__device__ __forceinline__ int bar_free(int side, int par) { return 5 + side * 6 + par; }
-constexpr int kBarMidpoint = 13;
+__device__ __forceinline__ int bar_chunk(int side) { return 1 + side * 2; }   // lattice + helper warps of a side, once per chunk
+__device__ __forceinline__ int bar_total(int side) { return 2 + side * 2; }
+constexpr int kBarMidpoint = 5;
 
 // ---------------------------------------------------------------------------------------------
 // per-lane state of a lattice warp.  NP = NS/2 packed pairs; pair j holds elements (j, j+NP).
@@ -337,36 +363,16 @@ __device__ __forceinline__ void lattice_frame(LaneState<NS>& st, const LaneConst
 template <int SIDE>
 struct FastCtx {
   const CallParams* p;
-  int b, T, L, S, JG, P, NW, RW, RWS, PS, RC;
+  int b, T, L, S, JG, JGE, P, NW, RW, RWS, PS, RC;   // JGE: JG rounded up to 4 (row stride of the exponent array)
   int w, lane, tid_side;
   FastSideSmem sm;
   float4* scr_m;   // [NS/4][T][JG]  stored pre-emission pairs in the READER's group order and packing
-  int* scr_e;      // [T][JG]
+  int* scr_e;      // [T][JGE]
   int per_row;                                // emission rows: cp.async copies per row
   const char* st_src; int st_stride;          // this lane's element of frame t at st_src + t*st_stride (bytes)
   unsigned st_dst; int st_vecB;               // shared address of this lane's element in row 0 of the ring; bytes per copy
-  unsigned oth_dst, oth_dst_e;                // shared addresses of this thread's slot 0 of the record ring
   __device__ __forceinline__ int frame_of(int n) const { return SIDE ? T - 1 - n : n; }
 };
-
-// Stage the emission rows of the kc frames starting at step n0 into ring slot `slot`: one warp per frame,
-// one cp.async per lane and 32 row elements (st_src / st_dst already point at this lane's element).
-template <int K, int SIDE>
-__device__ __forceinline__ void stage_rows(const FastCtx<SIDE>& c, int slot, int n0, int kc) {
-#pragma unroll 1
-  for (int j = c.w; j < kc; j += c.NW) {
-    const char* src = c.st_src + (long long)c.frame_of(n0 + j) * c.st_stride;
-    const unsigned dst = c.st_dst + (unsigned)((slot * K + j) * c.RWS * 4);
-#pragma unroll 1
-    for (int e = c.lane; e < c.per_row; e += 32) {
-      const unsigned d = dst + (unsigned)(e - c.lane) * (unsigned)c.st_vecB;
-      const char* g = src + (e - c.lane) * c.st_vecB;
-      if (c.st_vecB == 16) asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(g) : "memory");
-      else if (c.st_vecB == 8) asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(d), "l"(g) : "memory");
-      else asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(d), "l"(g) : "memory");
-    }
-  }
-}
 
 // Frames [t0, t1] in which the lattice-state window [ws_lo, ws_hi] intersects the reachable band
 // lo_t = max(0, S - 2(T-t)) <= s < hi_t = min(S, 2(t+1)); empty (t0 > t1) when it never does.
@@ -389,46 +395,71 @@ struct SweepState {
 };
 constexpr int kLostBound = 127 + 110 - 24 - 2;   // maxbound above this: FLAG_PRECISION_LOST
 
-// Prefetch the opposite side's stored records of this thread's group for the kc frames starting at
-// step n0 into buffer `obuf` of its private ring; records the other side never wrote (its warp
-// skipped that chunk: out of the band) read as zero.
-template <int K, int SIDE, int NT, int NS>
-__device__ __forceinline__ void prefetch_other(const FastCtx<SIDE>& c, const SweepState<NS>& ss, int obuf, int n0, int kc) {
+// What a helper warp needs to know about the OTHER side's phase-1 stores: lane w' (< NW) holds the
+// steps [wa, wb] (in the writer's own step count, chunk-aligned) during which writer warp w' stored
+// its records, and the position groups [gfirst, glast] (reader's numbering) that warp owns.
+struct WriterInfo {
+  int wa, wb, gfirst, glast;
+};
+
+// Helper warp: prefetch the opposite side's stored records of ALL position groups for the frame of
+// step n into row `slot` (= buffer * K + frame) of the record ring with TMA bulk copies -- per frame the
+// records the other side wrote are ONE contiguous run of groups (its active warps are adjacent), so a
+// frame costs NS/4 + 1 copies issued by one lane; the groups outside that run (never written: the
+// other side's warp skipped the chunk, out of the band) are set to zero.  Returns true when copies
+// were issued (the caller then waits on the mbarrier).
+template <int SIDE, int NT, int NS>
+__device__ __forceinline__ bool prefetch_other(const FastCtx<SIDE>& c, const WriterInfo& wi, int slot, int n,
+                                               unsigned long long* mbar, int& tc) {
   constexpr int NH = NS / 4;                  // 16-byte halves of a record
-  const LaneConst<NS>& lc = ss.lc;
-  if (!lc.owned) return;
-  const unsigned da = c.oth_dst + (unsigned)(obuf * K * NH * NT * 16);
-  const unsigned de = c.oth_dst_e + (unsigned)(obuf * K * NT * 4);
-  int off = c.frame_of(n0) * c.JG + lc.group;
-  const int step = SIDE ? -c.JG : c.JG;
   const int half_stride = c.T * c.JG;         // float4 elements between the halves of a record in the scratch
-  const bool first = (unsigned)(ss.rd_hi - n0) < (unsigned)ss.wr_len;
-  const bool last = (unsigned)(ss.rd_hi - (n0 + K - 1)) < (unsigned)ss.wr_len;
-  if (kc == K && first && last) {   // the written steps are one interval: both ends inside means all inside
+  const int t = c.frame_of(n);
+  float4* sa = c.sm.oth_m + slot * NH * NT;
+  int* se = c.sm.oth_e + slot * NT;
+  // the writer's step for this frame is T-1-n; the warps that were storing then are adjacent
+  const int nw_ = c.T - 1 - n;
+  const unsigned act = __ballot_sync(0xffffffffu, c.lane < c.NW && nw_ >= wi.wa && nw_ <= wi.wb);
+  int g_lo = c.JG, g_hi = -1;                 // written run of groups (reader's numbering; empty by default)
+  if (act) {
+    // writer warp w' owns reader groups [gfirst(w'), glast(w')], decreasing in w'
+    const int w_lo = __ffs(act) - 1, w_hi = 31 - __clz(act);
+    g_lo = __shfl_sync(0xffffffffu, wi.gfirst, w_hi);
+    g_hi = __shfl_sync(0xffffffffu, wi.glast, w_lo);
+  }
+  // zero the groups outside the run
+  for (int g = c.lane; g < c.JG; g += 32) {
+    if (g < g_lo || g > g_hi) {
 #pragma unroll
-    for (int j = 0; j < K; ++j) {
-#pragma unroll
-      for (int h = 0; h < NH; ++h)
-        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(da + (j * NH + h) * NT * 16),
-                     "l"(c.scr_m + h * half_stride + off) : "memory");
-      asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(de + j * NT * 4), "l"(c.scr_e + off) : "memory");
-      off += step;
+      for (int h = 0; h < NH; ++h) sa[h * NT + g] = make_float4(0.f, 0.f, 0.f, 0.f);
     }
-  } else {
-    float4* sa = c.sm.oth_m + obuf * K * NH * NT + c.tid_side;
-    int* se = c.sm.oth_e + obuf * K * NT + c.tid_side;
+  }
+  if (!act) return false;
+  B200CTC_TRACE_EVENT(tc, 21);
+  if (c.lane == 0) {
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    const int ge_lo = g_lo & ~3, ge_n = ((g_hi + 4) & ~3) - ge_lo;      // exponents: 16-byte granules (rows are padded to JGE)
+    const unsigned nm = (unsigned)(g_hi - g_lo + 1) * 16u;
+    mbar_expect_tx(mbar, nm * NH + (unsigned)ge_n * 4u);
+#pragma unroll
+    for (int h = 0; h < NH; ++h) bulk_g2s(sa + h * NT + g_lo, c.scr_m + h * half_stride + t * c.JG + g_lo, nm, mbar);
+    bulk_g2s(se + ge_lo, c.scr_e + t * c.JGE + ge_lo, (unsigned)ge_n * 4u, mbar);
+  }
+  B200CTC_TRACE_EVENT(tc, 22);
+  return true;
+}
+
+// Helper warp: stage the emission row of the frame of step n into row `slot` (= ring slot * K + frame).
+template <int SIDE>
+__device__ __forceinline__ void stage_row(const FastCtx<SIDE>& c, int slot, int n) {
+  const char* src = c.st_src + (long long)c.frame_of(n) * c.st_stride;
+  const unsigned dst = c.st_dst + (unsigned)(slot * c.RWS * 4);
 #pragma unroll 1
-    for (int j = 0; j < kc; ++j) {
-      const bool wr = (unsigned)(ss.rd_hi - (n0 + j)) < (unsigned)ss.wr_len;
-#pragma unroll
-      for (int h = 0; h < NH; ++h) {
-        if (wr) cp_async_16(sa + (j * NH + h) * NT, c.scr_m + h * half_stride + off);
-        else sa[(j * NH + h) * NT] = make_float4(0.f, 0.f, 0.f, 0.f);
-      }
-      if (wr) cp_async_4(se + j * NT, c.scr_e + off);
-      else se[j * NT] = kEZero;
-      off += step;
-    }
+  for (int e = c.lane; e < c.per_row; e += 32) {
+    const unsigned d = dst + (unsigned)(e - c.lane) * (unsigned)c.st_vecB;
+    const char* g = src + (e - c.lane) * c.st_vecB;
+    if (c.st_vecB == 16) asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(g) : "memory");
+    else if (c.st_vecB == 8) asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(d), "l"(g) : "memory");
+    else asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(d), "l"(g) : "memory");
   }
 }
 
@@ -468,7 +499,7 @@ __device__ __forceinline__ void posterior_frame(SweepState<NS>& ss, const float4
   // Evaluated on the exponent fields (a zero maximum has field 0 and can only lower the bound), so
   // it cannot overflow or underflow; the running maximum is tested at the chunk boundary.
   const float omax = f2_max_all<NP>(O);
-  ss.maxbound = max(ss.maxbound, (__float_as_int(omax) >> 23) + dexp);
+  if (omax > 0.f) ss.maxbound = max(ss.maxbound, (__float_as_int(omax) >> 23) + dexp);   // zeroed records carry no exponent
   if (store) {
     float bsum = 0.f;
 #pragma unroll
@@ -501,7 +532,8 @@ __device__ __forceinline__ void run_chunk(const FastCtx<SIDE>& c, SweepState<NS>
     if (!active) return;
     // scratch slot of this lane's group for the opposite side's reader (mirrored group order)
     int off = c.frame_of(n0) * c.JG + (c.JG - 1 - lc.group);
-    const int step = SIDE ? -c.JG : c.JG;
+    int offe = c.frame_of(n0) * c.JGE + (c.JG - 1 - lc.group);
+    const int step = SIDE ? -c.JG : c.JG, stepe = SIDE ? -c.JGE : c.JGE;
     const int half_stride = c.T * c.JG;
 #pragma unroll 1
     for (int j = 0; j < kc; ++j) {
@@ -513,18 +545,19 @@ __device__ __forceinline__ void run_chunk(const FastCtx<SIDE>& c, SweepState<NS>
         for (int h = 0; h < NH; ++h)
           asm volatile("st.global.v2.b64 [%0], {%1, %2};" ::"l"(c.scr_m + h * half_stride + off),
                        "l"(ACC[NP - 1 - 2 * h]), "l"(ACC[NP - 2 - 2 * h]) : "memory");
-        c.scr_e[off] = E;
+        c.scr_e[offe] = E;
       }
       row += row_bytes;
       off += step;
+      offe += stepe;
     }
   } else {
     char* post = reinterpret_cast<char*>(c.sm.post + (size_t)pbuf * K * c.PS);
     const int post_bytes = c.PS * 4;
     const bool store = write_post && lc.owned;
     if (active) {
-      const float4* om = c.sm.oth_m + obuf * K * NH * NT + c.tid_side;
-      const int* oe = c.sm.oth_e + obuf * K * NT + c.tid_side;
+      const float4* om = c.sm.oth_m + obuf * K * NH * NT + lc.group;
+      const int* oe = c.sm.oth_e + obuf * K * NT + lc.group;
 #pragma unroll 1
       for (int j = 0; j < kc; ++j) {
         f2 ACC[NP]; int E;
@@ -547,8 +580,9 @@ __device__ __forceinline__ void run_chunk(const FastCtx<SIDE>& c, SweepState<NS>
   }
 }
 
-// Chunk boundary of the lattice warps: everything this thread prefetched at the start of the chunk
-// has landed, publish the halo lanes, ONE side barrier, import the halo.
+// Chunk boundary of the lattice warps: publish the halo lanes, ONE barrier with the side's lattice and
+// helper warps (after it the helpers' prefetch for the next chunk has landed and the posterior buffer
+// of the previous chunk is consumed), import the halo.
 template <int K, int NWMAX, int SIDE, int NS>
 __device__ __forceinline__ void chunk_boundary(const FastCtx<SIDE>& c, SweepState<NS>& ss, int cc, int* abort_flag) {
   constexpr int NH = NS / 4, HL = 2 * K / NS;
@@ -563,8 +597,7 @@ __device__ __forceinline__ void chunk_boundary(const FastCtx<SIDE>& c, SweepStat
     c.sm.halo_e[slot] = st.e;
   }
   if (ss.lc.owned && ss.maxbound > kLostBound) *abort_flag = 1;
-  cp_async_wait<0>();
-  named_bar_sync(bar_halo(SIDE), NW * 32);
+  named_bar_sync(bar_chunk(SIDE), (NW + kReducers) * 32);
   if (w > 0 && lane < HL) {
     const int slot = (hb * NWMAX + (w - 1)) * HL + lane;
 #pragma unroll
@@ -598,7 +631,7 @@ template <int K, int NWMAX, int SIDE, int NS>
 __device__ __forceinline__ void fill_ctx(FastCtx<SIDE>& c, const CallParams& p, int b, const UttMeta& m,
                                          unsigned char* side_smem, int w, int lane) {
   c.p = &p; c.b = b;
-  c.T = m.T; c.L = m.L; c.S = 2 * m.L + 1; c.JG = (c.S + NS - 1) / NS; c.P = NS * c.JG;
+  c.T = m.T; c.L = m.L; c.S = 2 * m.L + 1; c.JG = (c.S + NS - 1) / NS; c.JGE = (c.JG + 3) & ~3; c.P = NS * c.JG;
   c.NW = fast_warps_needed<K, NS>(m.L);
   c.RW = p.gathered ? m.W : (p.V + 3) / 4 * 4;
   c.RWS = c.RW + 4;
@@ -622,8 +655,6 @@ __device__ __forceinline__ void fill_ctx(FastCtx<SIDE>& c, const CallParams& p, 
   c.st_src = reinterpret_cast<const char*>(row_src) + lane * c.st_vecB;
   c.st_stride = (int)(row_stride * 4);          // api.cu rejects mini-batches whose frame stride exceeds 2^31 bytes
   c.st_dst = (unsigned)__cvta_generic_to_shared(c.sm.rows) + (unsigned)(lane * c.st_vecB);
-  c.oth_dst = (unsigned)__cvta_generic_to_shared(c.sm.oth_m + c.tid_side);
-  c.oth_dst_e = (unsigned)__cvta_generic_to_shared(c.sm.oth_e + c.tid_side);
 }
 
 struct SidePlan {
@@ -742,45 +773,36 @@ __device__ void fast_side_sweep(const CallParams& p, int b, const UttMeta& m, co
   const int M_side = pl.M_side, nc1 = pl.nc1, nc2 = pl.nc2;
   int* abort_flag = cm.abort_flag;
 
-  // zero slots of the row buffers; emission rows of the first chunk
+  // zero slots of the row buffers (the helper warps stage the rows themselves)
   for (int i = c.tid_side; i < kRowsRing * K; i += NW * 32) {
     float* z = c.sm.rows + (size_t)i * c.RWS + c.RW;
     z[0] = 0.f; z[1] = 0.f; z[2] = 0.f; z[3] = 0.f;
   }
   // Step ranges: phase 1 = [0, M_side), phase 2 = [M_side, T); chunks of K steps from the start of each.
-  // `rs` is the row-ring slot of the current chunk; the rows of the next chunk are staged while it runs.
+  // `rs` is the row-ring slot of the current chunk.  Everything a chunk needs (emission rows, the other
+  // side's records) was fetched by the helper warps during the previous chunk.
   int rs = 0;
-  stage_rows<K, SIDE>(c, 0, 0, min(K, nc1 > 0 ? M_side : T));
-  cp_async_commit();
-  cp_async_wait<0>();
-  named_bar_sync(bar_halo(SIDE), NW * 32);
+  B200CTC_TRACE_EVENT(tc, 1);
+  named_bar_sync(bar_chunk(SIDE), (NW + kReducers) * 32);       // rows of chunk 0 staged, wr_tab visible
 
   // ================================ phase 1 ================================
   int cc = 0;
   for (int n0 = 0; n0 < M_side; n0 += K, ++cc) {
     const int kc = min(K, M_side - n0);
-    const int rs_next = rs == kRowsRing - 1 ? 0 : rs + 1;
-    const int nn = n0 + kc;                               // first step of the next chunk (phase 1 or 2)
-    B200CTC_TRACE_EVENT(tc, 1);
-    if (nn < T) stage_rows<K, SIDE>(c, rs_next, nn, min(K, (nn < M_side ? M_side : T) - nn));   // lands during this chunk
-    cp_async_commit();
     B200CTC_TRACE_EVENT(tc, 2);
     run_chunk<K, false, SIDE, NT, NS>(c, ss, rs, 0, 0, n0, kc, false);
     B200CTC_TRACE_EVENT(tc, 3);
     chunk_boundary<K, NWMAX, SIDE, NS>(c, ss, cc, abort_flag);
-    B200CTC_TRACE_EVENT(tc, 5);
-    rs = rs_next;
+    rs = rs == kRowsRing - 1 ? 0 : rs + 1;
   }
 
   // ================================ midpoint ================================
-  // Both sides' lattice warps meet here exactly once: everything phase 1 stored is visible afterwards.
-  named_bar_sync(kBarMidpoint, 2 * NW * 32);
+  // Lattice and helper warps of both sides meet here exactly once: everything phase 1 stored is
+  // visible afterwards.
+  B200CTC_TRACE_EVENT(tc, 4);
+  named_bar_sync(kBarMidpoint, 2 * (NW + kReducers) * 32);
   if (nc2 == 0) return;
-
-  // the opposite side's records of the first phase-2 chunk
-  prefetch_other<K, SIDE, NT, NS>(c, ss, 0, M_side, min(K, T - M_side));
-  cp_async_commit();
-  cp_async_wait<0>();
+  named_bar_sync(bar_chunk(SIDE), (NW + kReducers) * 32);       // the helpers fetched the records of the first phase-2 chunk
 
   // ---- total probability P = sum_s alpha_t(s) beta'_t(s) at the first phase-2 frame (state copy) ----
   {
@@ -795,11 +817,11 @@ __device__ void fast_side_sweep(const CallParams& p, int b, const UttMeta& m, co
         float sum = 0.f;
 #pragma unroll
         for (int h = 0; h < NH; ++h) {
-          const float4 q = c.sm.oth_m[h * NT + c.tid_side];
+          const float4 q = c.sm.oth_m[h * NT + lc.group];
           const f2 p0 = f2_mul(tmp.A[2 * h], f2_pack(q.x, q.y)), p1 = f2_mul(tmp.A[2 * h + 1], f2_pack(q.z, q.w));
           sum += (f2_lo(p0) + f2_hi(p0)) + (f2_lo(p1) + f2_hi(p1));
         }
-        if (sum > 0.f) { part = sum; pe = tmp.e + c.sm.oth_e[c.tid_side]; }
+        if (sum > 0.f) { part = sum; pe = tmp.e + c.sm.oth_e[lc.group]; }
       }
     }
     int emax = pe;
@@ -808,7 +830,7 @@ __device__ void fast_side_sweep(const CallParams& p, int b, const UttMeta& m, co
     float scaled = part * pow2_neg(pe - emax);
     scaled = warp_sum(scaled);
     if (lane == 0) { c.sm.red_m[w] = scaled; c.sm.red_e[w] = emax; }
-    named_bar_sync(bar_total(SIDE), (NW + kReducers) * 32);   // lattice warps + the side's reducers
+    named_bar_sync(bar_total(SIDE), (NW + kReducers) * 32);   // lattice warps + the side's helpers
     double log2P;
     if (!total_probability(c.sm, NW, ss.inv_mP, ss.eP, log2P)) {
       // zero / underflowed / garbage total probability: the safe lattice decides
@@ -824,28 +846,17 @@ __device__ void fast_side_sweep(const CallParams& p, int b, const UttMeta& m, co
   int k2 = 0;
   for (int n0 = M_side; n0 < T; n0 += K, ++k2, ++cc) {
     const int kc = min(K, T - n0), par = k2 & 1;
-    const int rs_next = rs == kRowsRing - 1 ? 0 : rs + 1;
-    B200CTC_TRACE_EVENT(tc, 6);
-    if (write_post && k2 >= 2) named_bar_sync(bar_free(SIDE, par), (NW + kReducers) * 32);   // reducers done with post[par]
-    B200CTC_TRACE_EVENT(tc, 11);
-    if (n0 + K < T) {
-      stage_rows<K, SIDE>(c, rs_next, n0 + K, min(K, T - n0 - K));
-      B200CTC_TRACE_EVENT(tc, 12);
-      prefetch_other<K, SIDE, NT, NS>(c, ss, par ^ 1, n0 + K, min(K, T - n0 - K));
-    }
-    cp_async_commit();
     B200CTC_TRACE_EVENT(tc, 13);
     run_chunk<K, true, SIDE, NT, NS>(c, ss, rs, par, par, n0, kc, write_post);
     B200CTC_TRACE_EVENT(tc, 14);
     chunk_boundary<K, NWMAX, SIDE, NS>(c, ss, cc, abort_flag);
-    B200CTC_TRACE_EVENT(tc, 15);
-    if (write_post) named_bar_arrive(bar_ready(SIDE, par), (NW + kReducers) * 32);    // post[par] of chunk cc is complete
-    rs = rs_next;
+    rs = rs == kRowsRing - 1 ? 0 : rs + 1;
   }
+  B200CTC_TRACE_EVENT(tc, 15);
 }
 
 // ---------------------------------------------------------------------------------------------
-// reducer warps of one side: per-symbol occupancy of every phase-2 frame, gradient rows
+// helper warps of one side: prefetch for the lattice warps; per-symbol occupancy of every phase-2 frame, gradient rows
 // ---------------------------------------------------------------------------------------------
 template <int C4>
 __device__ __forceinline__ float post_row_sum(const float4* __restrict__ row4) {
@@ -866,79 +877,174 @@ __device__ __forceinline__ float post_row_sum_c4(const float4* __restrict__ row4
   }
 }
 
-// Reducer warp rj of the side handles frame rj of every phase-2 chunk.
+// Per-symbol occupancy of one phase-2 frame (posterior row `post`, softmax row `yrow`) and the update
+// of its gradient row.
+template <int NWMAX>
+__device__ __forceinline__ void reduce_frame(const CallParams& p, const FastCommon& cm, const float* __restrict__ post,
+                                             const float* __restrict__ yrow, float* __restrict__ grow, float* rowsum,
+                                             int RC, int NW, int C4, int R, int n_seg, bool one_row, int sym_first,
+                                             int lane) {
+  const float4* post4 = reinterpret_cast<const float4*>(post);
+  const bool gathered = p.gathered != 0;
+  // blank: partial sums of the lattice threads
+  float accb = 0.f;
+#pragma unroll
+  for (int i = 0; i < NWMAX; ++i)
+    if (i < NW) accb += post[RC + i * 32 + lane];
+  if (one_row) {
+    for (int u0 = 0; u0 < n_seg; u0 += 32) {
+      const int u = u0 + lane;
+      if (u < n_seg) {
+        const float tot = post_row_sum_c4(post4 + (size_t)u * C4, C4);
+        const int sym = u0 == 0 ? sym_first : cm.ix.seg_sym[u];
+        if (!gathered) grow[sym] = yrow[sym] - tot;      // the touched symbols of a frame share one 128-byte row
+        else atomicAdd(grow + sym, -tot);
+      }
+    }
+  } else {
+    for (int r0 = 0; r0 < R; r0 += 32) {
+      const int r = r0 + lane;
+      if (r < R) rowsum[r] = post_row_sum_c4(post4 + (size_t)r * C4, C4);
+    }
+    __syncwarp();
+    for (int u = lane; u < n_seg; u += 32) {
+      float tot = 0.f;
+      for (int r = cm.row_start[u]; r < cm.row_start[u + 1]; ++r) tot += rowsum[r];
+      const int sym = cm.ix.seg_sym[u];
+      if (!gathered) grow[sym] = yrow[sym] - tot;
+      else atomicAdd(grow + sym, -tot);
+    }
+    __syncwarp();
+  }
+  accb = warp_sum(accb);
+  if (lane == 0) {
+    if (!gathered) grow[p.blank] = yrow[p.blank] - accb;
+    else atomicAdd(grow + p.blank, -accb);
+  }
+}
+
+// Helper warp hj of the side owns frame hj of every chunk: during chunk c it fetches what that frame
+// of chunk c+1 needs (emission row; in phase 2 the other side's records of all position groups) and,
+// in phase 2, reduces the posteriors the lattice warps produced for its frame of chunk c-1 into the
+// gradient row.  It meets the lattice warps at the one barrier per chunk.
 template <int K, int NWMAX, int SIDE, int NS>
-__device__ void fast_side_reduce(const CallParams& p, int b, const UttMeta& m, const FastCommon& cm,
-                                 unsigned char* side_smem, int rj, int lane) {
-  static_assert(kReducers == K, "one reducer warp per frame of a chunk");
+__device__ void fast_side_helper(const CallParams& p, int b, const UttMeta& m, const FastCommon& cm,
+                                 unsigned char* side_smem, int hj, int lane) {
+  static_assert(kReducers == K, "one helper warp per frame of a chunk");
+  constexpr int NT = NWMAX * 32;
   FastCtx<SIDE> c;
-  fill_ctx<K, NWMAX, SIDE, NS>(c, p, b, m, side_smem, NWMAX + rj, lane);
+  fill_ctx<K, NWMAX, SIDE, NS>(c, p, b, m, side_smem, NWMAX + hj, lane);
   const int T = c.T, NW = c.NW, V = p.V;
   const SidePlan pl = side_plan<K, SIDE>(T);
+  const int M_side = pl.M_side;
+  const int nbar = (NW + kReducers) * 32;
+  B200CTC_TRACE_DECL(tc);
+
+  // what the other side's warp `lane` stored in phase 1 (prefetch_other)
+  WriterInfo wi;
+  {
+    constexpr int WIN = 32 * NS, OWN = WIN - 2 * K, OWNG = OWN / NS, HL = 2 * K / NS;
+    const int wq = lane < NW ? lane : 0;
+    const int q_lo = wq * OWN, q_hi = min(wq * OWN + WIN - 1, c.P - 1);
+    const int s_lo = SIDE ? q_lo : (c.P - 1 - q_hi);            // the writer is the opposite side
+    const int s_hi = SIDE ? q_hi : (c.P - 1 - q_lo);
+    int t0, t1;
+    band_frames(s_lo, s_hi, c.S, T, t0, t1);
+    const int M_other = SIDE ? (T - T / 2) : (T / 2);           // frames the other side covers in phase 1
+    int na = SIDE ? t0 : T - 1 - t1;                            // in the writer's steps
+    int nb = min(SIDE ? t1 : T - 1 - t0, M_other - 1);
+    wi.wa = 1; wi.wb = 0;
+    if (t0 <= t1 && na <= nb) { wi.wa = na / K * K; wi.wb = nb / K * K + K - 1; }
+    const int G_lo = wq * OWNG + (wq > 0 ? HL : 0), G_hi = min(wq * OWNG + 31, c.JG - 1);   // its owned groups
+    wi.gfirst = c.JG - 1 - G_hi;                                // in this (the reader's) numbering
+    wi.glast = c.JG - 1 - G_lo;
+  }
+  unsigned long long* mbar = c.sm.mbar + hj;
+  unsigned mphase = 0;
+  if (lane == 0) {
+    mbar_init(mbar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncwarp();
+
+  // rows of chunk 0
+  int rs = 0;
+  if (hj < T) stage_row<SIDE>(c, hj, hj);           // chunk 0 holds steps 0..min(K, M_side or T)-1; extra rows are harmless
+  cp_async_commit();
+  cp_async_wait<0>();
+  named_bar_sync(bar_chunk(SIDE), nbar);
+
+  // ================================ phase 1 ================================
+  for (int n0 = 0; n0 < M_side; n0 += K) {
+    const int rs_next = rs == kRowsRing - 1 ? 0 : rs + 1;
+    const int nn = n0 + min(K, M_side - n0);                      // first step of the next chunk (phase 1 or 2)
+    if (nn + hj < T) stage_row<SIDE>(c, rs_next * K + hj, nn + hj);
+    cp_async_commit();
+    cp_async_wait<0>();
+    named_bar_sync(bar_chunk(SIDE), nbar);
+    rs = rs_next;
+  }
+
+  // ================================ midpoint ================================
+  named_bar_sync(kBarMidpoint, 2 * nbar);
   if (pl.nc2 == 0) return;
-  named_bar_sync(bar_total(SIDE), (NW + kReducers) * 32);
+  if (M_side + hj < T && prefetch_other<SIDE, NT, NS>(c, wi, hj, M_side + hj, mbar, tc)) {   // records of the first phase-2 chunk
+    mbar_wait(mbar, mphase);
+    mphase ^= 1;
+  }
+  named_bar_sync(bar_chunk(SIDE), nbar);
+  named_bar_sync(bar_total(SIDE), nbar);
   {
     float inv_mP; int eP; double log2P;
     if (!total_probability(c.sm, NW, inv_mP, eP, log2P)) return;
   }
-  if (p.grads == nullptr) return;
+  const bool reduce = p.grads != nullptr;
 
   const int C4 = post_row_width(c.L, V) / 4;          // 16-byte chunks per row
   const int R = *cm.n_rows, n_seg = *cm.ix.n_seg;
-  const bool gathered = p.gathered != 0;
   const bool one_row = (R == n_seg);                  // every symbol fits one row: row index == segment index
   const int sym_first = lane < n_seg ? cm.ix.seg_sym[lane] : 0;
-  float* rowsum = c.sm.rowsum + (size_t)rj * (post_rows_max(c.L, V) + 4);
-  B200CTC_TRACE_DECL(tc);
-  for (int cc = pl.nc1; cc < pl.n_chunks; ++cc) {
-    const int k2 = cc - pl.nc1, par = k2 & 1;
-    const int n0 = pl.M_side + k2 * K, kc = min(K, T - n0);
+  float* rowsum = c.sm.rowsum + (size_t)hj * (post_rows_max(c.L, V) + 4);
+
+  // ================================ phase 2 ================================
+  int k2 = 0, rs_prev = 0;
+  for (int n0 = M_side; n0 < T; n0 += K, ++k2) {
+    const int par = k2 & 1;
+    const int rs_next = rs == kRowsRing - 1 ? 0 : rs + 1;
     B200CTC_TRACE_EVENT(tc, 7);
-    named_bar_sync(bar_ready(SIDE, par), (NW + kReducers) * 32);
+    bool copying = false;
+    if (n0 + K + hj < T) {                            // what frame hj of the next chunk needs
+      stage_row<SIDE>(c, rs_next * K + hj, n0 + K + hj);
+      B200CTC_TRACE_EVENT(tc, 20);
+      copying = prefetch_other<SIDE, NT, NS>(c, wi, (par ^ 1) * K + hj, n0 + K + hj, mbar, tc);
+    }
+    cp_async_commit();
     B200CTC_TRACE_EVENT(tc, 8);
-    if (rj < kc) {
-      const float* post = c.sm.post + (size_t)(par * K + rj) * c.PS;
-      const float4* post4 = reinterpret_cast<const float4*>(post);
-      const float* yrow = c.sm.rows + (size_t)((cc % kRowsRing) * K + rj) * c.RWS;
-      float* grow = p.grads + ((long long)c.frame_of(n0 + rj) * p.B + b) * V;
-      // blank: partial sums of the lattice threads
-      float accb = 0.f;
-#pragma unroll
-      for (int i = 0; i < NWMAX; ++i)
-        if (i < NW) accb += post[c.RC + i * 32 + lane];
-      if (one_row) {
-        for (int u0 = 0; u0 < n_seg; u0 += 32) {
-          const int u = u0 + lane;
-          if (u < n_seg) {
-            const float tot = post_row_sum_c4(post4 + (size_t)u * C4, C4);
-            const int sym = u0 == 0 ? sym_first : cm.ix.seg_sym[u];
-            if (!gathered) grow[sym] = yrow[sym] - tot;      // the touched symbols of a frame share one 128-byte row
-            else atomicAdd(grow + sym, -tot);
-          }
-        }
-      } else {
-        for (int r0 = 0; r0 < R; r0 += 32) {
-          const int r = r0 + lane;
-          if (r < R) rowsum[r] = post_row_sum_c4(post4 + (size_t)r * C4, C4);
-        }
-        __syncwarp();
-        for (int u = lane; u < n_seg; u += 32) {
-          float tot = 0.f;
-          for (int r = cm.row_start[u]; r < cm.row_start[u + 1]; ++r) tot += rowsum[r];
-          const int sym = cm.ix.seg_sym[u];
-          if (!gathered) grow[sym] = yrow[sym] - tot;
-          else atomicAdd(grow + sym, -tot);
-        }
-        __syncwarp();
-      }
-      accb = warp_sum(accb);
-      if (lane == 0) {
-        if (!gathered) grow[p.blank] = yrow[p.blank] - accb;
-        else atomicAdd(grow + p.blank, -accb);
-      }
+    if (reduce && k2 >= 1) {                          // frame hj of the previous chunk (it was a full chunk)
+      const int n = n0 - K + hj;
+      reduce_frame<NWMAX>(p, cm, c.sm.post + (size_t)((par ^ 1) * K + hj) * c.PS,
+                          c.sm.rows + (size_t)(rs_prev * K + hj) * c.RWS,
+                          p.grads + ((long long)c.frame_of(n) * p.B + b) * V, rowsum, c.RC, NW, C4, R, n_seg,
+                          one_row, sym_first, lane);
     }
     B200CTC_TRACE_EVENT(tc, 9);
-    if (cc + 2 < pl.n_chunks) named_bar_arrive(bar_free(SIDE, par), (NW + kReducers) * 32);
+    cp_async_wait<0>();
+    if (copying) {
+      mbar_wait(mbar, mphase);
+      mphase ^= 1;
+    }
+    named_bar_sync(bar_chunk(SIDE), nbar);
+    rs_prev = rs;
+    rs = rs_next;
+  }
+  // the last chunk
+  if (reduce) {
+    const int n0 = M_side + (k2 - 1) * K, par = (k2 - 1) & 1;
+    if (n0 + hj < T)
+      reduce_frame<NWMAX>(p, cm, c.sm.post + (size_t)(par * K + hj) * c.PS,
+                          c.sm.rows + (size_t)(rs_prev * K + hj) * c.RWS,
+                          p.grads + ((long long)c.frame_of(n0 + hj) * p.B + b) * V, rowsum, c.RC, NW, C4, R, n_seg,
+                          one_row, sym_first, lane);
   }
 }
 
@@ -1016,8 +1122,8 @@ __device__ void lattice_fast_utterance(const CallParams& p, int b, unsigned char
     if (side == 0) fast_side_sweep<K, NWMAX, 0, NS>(p, b, m, cm, smem + common, w, lane);
     else           fast_side_sweep<K, NWMAX, 1, NS>(p, b, m, cm, smem + common + side_bytes, w, lane);
   } else if (w >= NWMAX) {
-    if (side == 0) fast_side_reduce<K, NWMAX, 0, NS>(p, b, m, cm, smem + common, w - NWMAX, lane);
-    else           fast_side_reduce<K, NWMAX, 1, NS>(p, b, m, cm, smem + common + side_bytes, w - NWMAX, lane);
+    if (side == 0) fast_side_helper<K, NWMAX, 0, NS>(p, b, m, cm, smem + common, w - NWMAX, lane);
+    else           fast_side_helper<K, NWMAX, 1, NS>(p, b, m, cm, smem + common + side_bytes, w - NWMAX, lane);
   }
   // idle warps wait at the caller's __syncthreads()
 }

@@ -2,10 +2,10 @@
 
 Builds a -DB200CTC_TRACE variant of the library (lib/libb200ctc_trace.so), runs one C3-shaped call
 through it and prints, per warp role, where the cycles of a chunk go:
-  lattice warps, phase 1: [1] chunk start -> [2] rows staged -> [3] frames done -> [5] boundary passed
-                 phase 2: [6] chunk start -> [11] reducers released the buffer -> [12] rows staged ->
-                          [13] records prefetched -> [14] frames done -> [15] boundary passed
-  reducer warps: [7] waiting for posteriors -> [8] got them -> [9] rows written
+  lattice warps: [2] phase-1 chunk start -> [3] frames done -> (barrier, halo) -> [2] ...; [4] midpoint;
+                 [13] phase-2 chunk start -> [14] frames + posteriors done -> (barrier, halo) -> [13] ...
+  helper warps:  [7] phase-2 chunk start -> [8] prefetch for the next chunk issued -> [9] previous chunk's
+                 frame reduced -> (cp.async wait, barrier) -> [7] ...
 Usage: python tools/trace_lattice.py [C3] [--build-only]
 """
 import ctypes
