@@ -182,6 +182,14 @@ __host__ __device__ inline int fast_warps_needed(int L) {
   const int win = 32 * NS, own = win - 2 * K;
   return P <= win ? 1 : 1 + (P - win + own - 1) / own;
 }
+// One frame of stored records ("frame block"), the same layout in the HBM scratch and in shared memory:
+// NS/4 planes of JG float4 (the packed mantissa pairs of every position group) followed by JG int32
+// exponents, padded to 16 bytes -- one TMA bulk copy moves a whole frame.
+template <int NS>
+__host__ __device__ inline int frame_block_bytes(int L) {
+  const int JG = (2 * L + 1 + NS - 1) / NS;
+  return (NS / 4) * JG * 16 + ((JG + 3) & ~3) * 4;
+}
 // Symbol-sorted posterior row: every symbol of the label sequence owns whole rows of C slots.
 __host__ __device__ inline int post_row_width(int L, int V) {
   const int n_sym = L < V - 1 ? L : V - 1;
@@ -196,8 +204,7 @@ __host__ __device__ inline int post_rows_max(int L, int V) {
 
 struct FastSideSmem {
   float* rows;      // [kRowsRing][K][RWS]     staged emission rows (+ a zero slot at index RW)
-  float4* oth_m;    // [2][K][NS/4][NT]        opposite side's stored pairs, indexed by position group, two chunks
-  int* oth_e;       // [2][K][NT]              ... exponent
+  unsigned char* oth;   // [2][K] frame blocks   the opposite side's stored records, two chunks (+ one all-zero block)
   float* post;      // [2][K][PS]              symbol-sorted label posteriors + blank partials + dump slot
   float4* halo_m;   // [2][NWMAX][HL][NS/4]    halo lanes
   int* halo_e;      // [2][NWMAX][HL]
@@ -217,11 +224,10 @@ __host__ __device__ inline size_t fast_side_bytes(int L, int RW, int V) {
   const size_t NT = NWMAX * 32;
   constexpr int HL = 2 * K / NS;
   size_t b = 0;
-  b += (size_t)2 * K * (NS / 4) * NT * 16;                   // oth_m
+  b += (size_t)(2 * K + 1) * frame_block_bytes<NS>(L);       // oth (+ the zero block)
   b += (size_t)2 * NWMAX * HL * (NS / 4) * 16;               // halo_m
   b += (size_t)kRowsRing * K * (size_t)(RW + 4) * 4;         // rows
   b += 2 * (size_t)K * post_stride<NWMAX>(L, V) * 4;         // post
-  b += (size_t)2 * K * NT * 4;                               // oth_e
   b += (size_t)2 * NWMAX * HL * 4;                           // halo_e
   b += NWMAX * 8;                                            // red
   b += (size_t)kReducers * (post_rows_max(L, V) + 4) * 4;    // rowsum (one per reducer warp)
@@ -242,11 +248,10 @@ __device__ __forceinline__ FastSideSmem carve_fast_side(unsigned char* base, int
   constexpr int HL = 2 * K / NS;
   FastSideSmem s;
   unsigned char* p = base;
-  s.oth_m = reinterpret_cast<float4*>(p);  p += (size_t)2 * K * (NS / 4) * NT * 16;
+  s.oth = p;                               p += (size_t)(2 * K + 1) * frame_block_bytes<NS>(L);
   s.halo_m = reinterpret_cast<float4*>(p); p += (size_t)2 * NWMAX * HL * (NS / 4) * 16;
   s.rows = reinterpret_cast<float*>(p);    p += (size_t)kRowsRing * K * (size_t)(RW + 4) * 4;
   s.post = reinterpret_cast<float*>(p);    p += 2 * (size_t)K * post_stride<NWMAX>(L, V) * 4;
-  s.oth_e = reinterpret_cast<int*>(p);     p += (size_t)2 * K * NT * 4;
   s.halo_e = reinterpret_cast<int*>(p);    p += (size_t)2 * NWMAX * HL * 4;
   s.red_m = reinterpret_cast<float*>(p);   p += NWMAX * 4;
   s.red_e = reinterpret_cast<int*>(p);     p += NWMAX * 4;
@@ -283,6 +288,7 @@ struct LaneConst {
   f2 Kf[NS / 4];    // skip-transition factors (1.0 allowed / 0.0 not) of the label pairs
   int posB[NS / 2]; // byte offset of the label positions in the symbol-sorted posterior row (dump slot if dummy)
   int blankB;       // byte offset of this thread's blank partial sum in the posterior row
+  int recB, expB;   // byte offsets of this lane's group in a frame block: first mantissa plane, exponent
   bool owned;       // this lane's group belongs to the warp (not to the halo) and exists
   int group;        // global position group (pos0 / NS)
 };
@@ -363,11 +369,10 @@ __device__ __forceinline__ void lattice_frame(LaneState<NS>& st, const LaneConst
 template <int SIDE>
 struct FastCtx {
   const CallParams* p;
-  int b, T, L, S, JG, JGE, P, NW, RW, RWS, PS, RC;   // JGE: JG rounded up to 4 (row stride of the exponent array)
+  int b, T, L, S, JG, FB, P, NW, RW, RWS, PS, RC;    // FB: bytes of a frame block
   int w, lane, tid_side;
   FastSideSmem sm;
-  float4* scr_m;   // [NS/4][T][JG]  stored pre-emission pairs in the READER's group order and packing
-  int* scr_e;      // [T][JGE]
+  unsigned char* scr;   // [T] frame blocks: stored pre-emission pairs in the READER's group order and packing
   int per_row;                                // emission rows: cp.async copies per row
   const char* st_src; int st_stride;          // this lane's element of frame t at st_src + t*st_stride (bytes)
   unsigned st_dst; int st_vecB;               // shared address of this lane's element in row 0 of the ring; bytes per copy
@@ -395,57 +400,16 @@ struct SweepState {
 };
 constexpr int kLostBound = 127 + 110 - 24 - 2;   // maxbound above this: FLAG_PRECISION_LOST
 
-// What a helper warp needs to know about the OTHER side's phase-1 stores: lane w' (< NW) holds the
-// steps [wa, wb] (in the writer's own step count, chunk-aligned) during which writer warp w' stored
-// its records, and the position groups [gfirst, glast] (reader's numbering) that warp owns.
-struct WriterInfo {
-  int wa, wb, gfirst, glast;
-};
-
-// Helper warp: prefetch the opposite side's stored records of ALL position groups for the frame of
-// step n into row `slot` (= buffer * K + frame) of the record ring with TMA bulk copies -- per frame the
-// records the other side wrote are ONE contiguous run of groups (its active warps are adjacent), so a
-// frame costs NS/4 + 1 copies issued by one lane; the groups outside that run (never written: the
-// other side's warp skipped the chunk, out of the band) are set to zero.  Returns true when copies
-// were issued (the caller then waits on the mbarrier).
-template <int SIDE, int NT, int NS>
-__device__ __forceinline__ bool prefetch_other(const FastCtx<SIDE>& c, const WriterInfo& wi, int slot, int n,
-                                               unsigned long long* mbar, int& tc) {
-  constexpr int NH = NS / 4;                  // 16-byte halves of a record
-  const int half_stride = c.T * c.JG;         // float4 elements between the halves of a record in the scratch
-  const int t = c.frame_of(n);
-  float4* sa = c.sm.oth_m + slot * NH * NT;
-  int* se = c.sm.oth_e + slot * NT;
-  // the writer's step for this frame is T-1-n; the warps that were storing then are adjacent
-  const int nw_ = c.T - 1 - n;
-  const unsigned act = __ballot_sync(0xffffffffu, c.lane < c.NW && nw_ >= wi.wa && nw_ <= wi.wb);
-  int g_lo = c.JG, g_hi = -1;                 // written run of groups (reader's numbering; empty by default)
-  if (act) {
-    // writer warp w' owns reader groups [gfirst(w'), glast(w')], decreasing in w'
-    const int w_lo = __ffs(act) - 1, w_hi = 31 - __clz(act);
-    g_lo = __shfl_sync(0xffffffffu, wi.gfirst, w_hi);
-    g_hi = __shfl_sync(0xffffffffu, wi.glast, w_lo);
-  }
-  // zero the groups outside the run
-  for (int g = c.lane; g < c.JG; g += 32) {
-    if (g < g_lo || g > g_hi) {
-#pragma unroll
-      for (int h = 0; h < NH; ++h) sa[h * NT + g] = make_float4(0.f, 0.f, 0.f, 0.f);
-    }
-  }
-  if (!act) return false;
-  B200CTC_TRACE_EVENT(tc, 21);
+// Helper warp: prefetch the opposite side's frame block of step n into slot `slot` (= buffer * K + frame)
+// of the record ring with ONE TMA bulk copy.  Records the other side never wrote (its warp skipped the
+// chunk: out of the band) arrive as garbage; the lattice lanes know which of their records exist
+// (SweepState::rd_hi / wr_len) and read the all-zero block instead.
+template <int SIDE>
+__device__ __forceinline__ void prefetch_other(const FastCtx<SIDE>& c, int slot, int n, unsigned long long* mbar) {
   if (c.lane == 0) {
-    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-    const int ge_lo = g_lo & ~3, ge_n = ((g_hi + 4) & ~3) - ge_lo;      // exponents: 16-byte granules (rows are padded to JGE)
-    const unsigned nm = (unsigned)(g_hi - g_lo + 1) * 16u;
-    mbar_expect_tx(mbar, nm * NH + (unsigned)ge_n * 4u);
-#pragma unroll
-    for (int h = 0; h < NH; ++h) bulk_g2s(sa + h * NT + g_lo, c.scr_m + h * half_stride + t * c.JG + g_lo, nm, mbar);
-    bulk_g2s(se + ge_lo, c.scr_e + t * c.JGE + ge_lo, (unsigned)ge_n * 4u, mbar);
+    mbar_expect_tx(mbar, (unsigned)c.FB);
+    bulk_g2s(c.sm.oth + (size_t)slot * c.FB, c.scr + (size_t)c.frame_of(n) * c.FB, (unsigned)c.FB, mbar);
   }
-  B200CTC_TRACE_EVENT(tc, 22);
-  return true;
 }
 
 // Helper warp: stage the emission row of the frame of step n into row `slot` (= ring slot * K + frame).
@@ -471,20 +435,20 @@ __device__ __forceinline__ void stage_row(const FastCtx<SIDE>& c, int slot, int 
 // value is 0, or the record was never written and reads as zero -- prefetch_other).
 // The fresh state is normalised to [1,2) per lane, so the one scale factor cannot push a product
 // that matters out of the fp32 range.
-template <int SIDE, int NT, int NS>
-__device__ __forceinline__ void posterior_frame(SweepState<NS>& ss, const float4* __restrict__ oth_m,
-                                                const int* __restrict__ oth_e, void* __restrict__ post, bool store) {
+template <int SIDE, int NS>
+__device__ __forceinline__ void posterior_frame(SweepState<NS>& ss, const unsigned char* __restrict__ blk, int plane_bytes,
+                                                void* __restrict__ post, bool store) {
   constexpr int NP = NS / 2, NH = NS / 4;
   const LaneConst<NS>& lc = ss.lc;
   const LaneState<NS>& st = ss.st;
   f2 O[NP];
 #pragma unroll
   for (int h = 0; h < NH; ++h) {
-    const float4 q = oth_m[h * NT];
+    const float4 q = *reinterpret_cast<const float4*>(blk + lc.recB + h * plane_bytes);
     O[2 * h] = f2_pack(q.x, q.y);
     O[2 * h + 1] = f2_pack(q.z, q.w);
   }
-  const int oe = oth_e[0];
+  const int oe = *reinterpret_cast<const int*>(blk + lc.expB);
   const int dexp = st.e + oe - ss.eP;
   const float s = pow2_clamped(dexp) * ss.inv_mP;   // inv_mP in (0.5, 1]
   const f2 s2 = f2_pack(s, s);
@@ -499,7 +463,7 @@ __device__ __forceinline__ void posterior_frame(SweepState<NS>& ss, const float4
   // Evaluated on the exponent fields (a zero maximum has field 0 and can only lower the bound), so
   // it cannot overflow or underflow; the running maximum is tested at the chunk boundary.
   const float omax = f2_max_all<NP>(O);
-  if (omax > 0.f) ss.maxbound = max(ss.maxbound, (__float_as_int(omax) >> 23) + dexp);   // zeroed records carry no exponent
+  ss.maxbound = max(ss.maxbound, (__float_as_int(omax) >> 23) + dexp);
   if (store) {
     float bsum = 0.f;
 #pragma unroll
@@ -531,10 +495,10 @@ __device__ __forceinline__ void run_chunk(const FastCtx<SIDE>& c, SweepState<NS>
   if (!PH2) {
     if (!active) return;
     // scratch slot of this lane's group for the opposite side's reader (mirrored group order)
-    int off = c.frame_of(n0) * c.JG + (c.JG - 1 - lc.group);
-    int offe = c.frame_of(n0) * c.JGE + (c.JG - 1 - lc.group);
-    const int step = SIDE ? -c.JG : c.JG, stepe = SIDE ? -c.JGE : c.JGE;
-    const int half_stride = c.T * c.JG;
+    const int gm = c.JG - 1 - lc.group;
+    unsigned char* blk = c.scr + (size_t)c.frame_of(n0) * c.FB;
+    const long long step = SIDE ? -(long long)c.FB : (long long)c.FB;
+    const int plane = c.JG * 16;
 #pragma unroll 1
     for (int j = 0; j < kc; ++j) {
       f2 ACC[NP]; int E;
@@ -543,30 +507,30 @@ __device__ __forceinline__ void run_chunk(const FastCtx<SIDE>& c, SweepState<NS>
         // the reader's pair j is this lane's pair NP-1-j (mirrored group, mirrored packing)
 #pragma unroll
         for (int h = 0; h < NH; ++h)
-          asm volatile("st.global.v2.b64 [%0], {%1, %2};" ::"l"(c.scr_m + h * half_stride + off),
+          asm volatile("st.global.v2.b64 [%0], {%1, %2};" ::"l"(blk + h * plane + gm * 16),
                        "l"(ACC[NP - 1 - 2 * h]), "l"(ACC[NP - 2 - 2 * h]) : "memory");
-        c.scr_e[offe] = E;
+        *reinterpret_cast<int*>(blk + NH * plane + gm * 4) = E;
       }
       row += row_bytes;
-      off += step;
-      offe += stepe;
+      blk += step;
     }
   } else {
     char* post = reinterpret_cast<char*>(c.sm.post + (size_t)pbuf * K * c.PS);
     const int post_bytes = c.PS * 4;
     const bool store = write_post && lc.owned;
     if (active) {
-      const float4* om = c.sm.oth_m + obuf * K * NH * NT + lc.group;
-      const int* oe = c.sm.oth_e + obuf * K * NT + lc.group;
+      const unsigned char* blk = c.sm.oth + (size_t)obuf * K * c.FB;
+      const unsigned char* zero_blk = c.sm.oth + (size_t)2 * K * c.FB;
+      const int plane = c.JG * 16;
 #pragma unroll 1
       for (int j = 0; j < kc; ++j) {
         f2 ACC[NP]; int E;
         lattice_frame<SIDE, NS>(ss.st, lc, row, lane0, ACC, E);
-        posterior_frame<SIDE, NT, NS>(ss, om, oe, post, store);
+        const bool wr = (unsigned)(ss.rd_hi - (n0 + j)) < (unsigned)ss.wr_len;   // did the other side store this record?
+        posterior_frame<SIDE, NS>(ss, wr ? blk : zero_blk, plane, post, store);
         row += row_bytes;
         post += post_bytes;
-        om += NH * NT;
-        oe += NT;
+        blk += c.FB;
       }
     } else if (store) {
 #pragma unroll 1
@@ -631,7 +595,7 @@ template <int K, int NWMAX, int SIDE, int NS>
 __device__ __forceinline__ void fill_ctx(FastCtx<SIDE>& c, const CallParams& p, int b, const UttMeta& m,
                                          unsigned char* side_smem, int w, int lane) {
   c.p = &p; c.b = b;
-  c.T = m.T; c.L = m.L; c.S = 2 * m.L + 1; c.JG = (c.S + NS - 1) / NS; c.JGE = (c.JG + 3) & ~3; c.P = NS * c.JG;
+  c.T = m.T; c.L = m.L; c.S = 2 * m.L + 1; c.JG = (c.S + NS - 1) / NS; c.FB = frame_block_bytes<NS>(m.L); c.P = NS * c.JG;
   c.NW = fast_warps_needed<K, NS>(m.L);
   c.RW = p.gathered ? m.W : (p.V + 3) / 4 * 4;
   c.RWS = c.RW + 4;
@@ -639,9 +603,7 @@ __device__ __forceinline__ void fill_ctx(FastCtx<SIDE>& c, const CallParams& p, 
   c.RC = c.PS - NWMAX * 32 - 4;                 // label slots come first, then the blank partials, then the dump slot
   c.w = w; c.lane = lane; c.tid_side = w * 32 + lane;
   c.sm = carve_fast_side<K, NWMAX, NS>(side_smem, m.L, c.RW, p.V);
-  unsigned char* scr = p.scratch + m.scratch_off * kGroupBytes;
-  c.scr_m = reinterpret_cast<float4*>(scr);
-  c.scr_e = reinterpret_cast<int*>(scr + (size_t)c.T * c.JG * (NS * 4));
+  c.scr = p.scratch + m.scratch_off * kGroupBytes;
   const float* row_src; long long row_stride; int row_vec;
   if (p.gathered) {
     row_src = p.em + m.em_off; row_stride = m.W; row_vec = 4; c.per_row = m.W / 4;
@@ -698,6 +660,8 @@ __device__ void fast_side_sweep(const CallParams& p, int b, const UttMeta& m, co
   lc.owned = ((w == 0) || (lane >= HL)) && (lc.group < JG);
   lc.idxB_blank = 4 * (p.gathered ? 0 : p.blank);
   lc.blankB = 4 * (c.RC + c.tid_side);
+  lc.recB = min(lc.group, JG - 1) * 16;
+  lc.expB = NH * JG * 16 + min(lc.group, JG - 1) * 4;
   {
     float kk[NP];
 #pragma unroll
@@ -773,6 +737,8 @@ __device__ void fast_side_sweep(const CallParams& p, int b, const UttMeta& m, co
   const int M_side = pl.M_side, nc1 = pl.nc1, nc2 = pl.nc2;
   int* abort_flag = cm.abort_flag;
 
+  // the all-zero frame block (stands in for records the other side never wrote)
+  for (int i = c.tid_side; i < c.FB / 4; i += NW * 32) reinterpret_cast<int*>(c.sm.oth + (size_t)2 * K * c.FB)[i] = (i >= NH * JG * 4) ? kEZero : 0;
   // zero slots of the row buffers (the helper warps stage the rows themselves)
   for (int i = c.tid_side; i < kRowsRing * K; i += NW * 32) {
     float* z = c.sm.rows + (size_t)i * c.RWS + c.RW;
@@ -814,14 +780,16 @@ __device__ void fast_side_sweep(const CallParams& p, int b, const UttMeta& m, co
       lattice_frame<SIDE, NS>(tmp, lc, c.sm.rows + (size_t)rs * K * c.RWS, lane == 0, ACC, E);
       if (lc.owned) {
         // no band masks: outside the band one of the two factors is exactly zero (posterior_frame)
+        const bool wr = (unsigned)(ss.rd_hi - n0) < (unsigned)ss.wr_len;
+        const unsigned char* blk = c.sm.oth + (wr ? (size_t)0 : (size_t)2 * K * c.FB);
         float sum = 0.f;
 #pragma unroll
         for (int h = 0; h < NH; ++h) {
-          const float4 q = c.sm.oth_m[h * NT + lc.group];
+          const float4 q = *reinterpret_cast<const float4*>(blk + lc.recB + h * JG * 16);
           const f2 p0 = f2_mul(tmp.A[2 * h], f2_pack(q.x, q.y)), p1 = f2_mul(tmp.A[2 * h + 1], f2_pack(q.z, q.w));
           sum += (f2_lo(p0) + f2_hi(p0)) + (f2_lo(p1) + f2_hi(p1));
         }
-        if (sum > 0.f) { part = sum; pe = tmp.e + c.sm.oth_e[lc.group]; }
+        if (sum > 0.f) { part = sum; pe = tmp.e + *reinterpret_cast<const int*>(blk + lc.expB); }
       }
     }
     int emax = pe;
@@ -940,25 +908,6 @@ __device__ void fast_side_helper(const CallParams& p, int b, const UttMeta& m, c
   const int nbar = (NW + kReducers) * 32;
   B200CTC_TRACE_DECL(tc);
 
-  // what the other side's warp `lane` stored in phase 1 (prefetch_other)
-  WriterInfo wi;
-  {
-    constexpr int WIN = 32 * NS, OWN = WIN - 2 * K, OWNG = OWN / NS, HL = 2 * K / NS;
-    const int wq = lane < NW ? lane : 0;
-    const int q_lo = wq * OWN, q_hi = min(wq * OWN + WIN - 1, c.P - 1);
-    const int s_lo = SIDE ? q_lo : (c.P - 1 - q_hi);            // the writer is the opposite side
-    const int s_hi = SIDE ? q_hi : (c.P - 1 - q_lo);
-    int t0, t1;
-    band_frames(s_lo, s_hi, c.S, T, t0, t1);
-    const int M_other = SIDE ? (T - T / 2) : (T / 2);           // frames the other side covers in phase 1
-    int na = SIDE ? t0 : T - 1 - t1;                            // in the writer's steps
-    int nb = min(SIDE ? t1 : T - 1 - t0, M_other - 1);
-    wi.wa = 1; wi.wb = 0;
-    if (t0 <= t1 && na <= nb) { wi.wa = na / K * K; wi.wb = nb / K * K + K - 1; }
-    const int G_lo = wq * OWNG + (wq > 0 ? HL : 0), G_hi = min(wq * OWNG + 31, c.JG - 1);   // its owned groups
-    wi.gfirst = c.JG - 1 - G_hi;                                // in this (the reader's) numbering
-    wi.glast = c.JG - 1 - G_lo;
-  }
   unsigned long long* mbar = c.sm.mbar + hj;
   unsigned mphase = 0;
   if (lane == 0) {
@@ -988,7 +937,8 @@ __device__ void fast_side_helper(const CallParams& p, int b, const UttMeta& m, c
   // ================================ midpoint ================================
   named_bar_sync(kBarMidpoint, 2 * nbar);
   if (pl.nc2 == 0) return;
-  if (M_side + hj < T && prefetch_other<SIDE, NT, NS>(c, wi, hj, M_side + hj, mbar, tc)) {   // records of the first phase-2 chunk
+  if (M_side + hj < T) {                             // records of the first phase-2 chunk
+    prefetch_other<SIDE>(c, hj, M_side + hj, mbar);
     mbar_wait(mbar, mphase);
     mphase ^= 1;
   }
@@ -1015,8 +965,8 @@ __device__ void fast_side_helper(const CallParams& p, int b, const UttMeta& m, c
     bool copying = false;
     if (n0 + K + hj < T) {                            // what frame hj of the next chunk needs
       stage_row<SIDE>(c, rs_next * K + hj, n0 + K + hj);
-      B200CTC_TRACE_EVENT(tc, 20);
-      copying = prefetch_other<SIDE, NT, NS>(c, wi, (par ^ 1) * K + hj, n0 + K + hj, mbar, tc);
+      prefetch_other<SIDE>(c, (par ^ 1) * K + hj, n0 + K + hj, mbar);
+      copying = true;
     }
     cp_async_commit();
     B200CTC_TRACE_EVENT(tc, 8);
