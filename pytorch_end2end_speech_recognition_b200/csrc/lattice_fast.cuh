@@ -397,6 +397,7 @@ struct SweepState {
   int rd_hi, wr_len;        // the other side stored this lane's record of step n iff (unsigned)(rd_hi - n) < wr_len
   float inv_mP; int eP;     // total probability P = mP * 2^eP (phase 2)
   int maxbound;             // running maximum of the range-check bound (phase 2), as a power-of-two exponent
+  unsigned char* wblk;      // phase 1: this lane's slot in the frame block of the current step (running pointer)
 };
 constexpr int kLostBound = 127 + 110 - 24 - 2;   // maxbound above this: FLAG_PRECISION_LOST
 
@@ -493,12 +494,15 @@ __device__ __forceinline__ void run_chunk(const FastCtx<SIDE>& c, SweepState<NS>
   const int row_bytes = c.RWS * 4;
   const bool active = n0 <= ss.act_hi && n0 + kc - 1 >= ss.act_lo;
   if (!PH2) {
-    if (!active) return;
+    if (!active) {
+      ss.wblk += (SIDE ? -(long long)c.FB : (long long)c.FB) * kc;
+      return;
+    }
     // scratch slot of this lane's group for the opposite side's reader (mirrored group order)
-    const int gm = c.JG - 1 - lc.group;
-    unsigned char* blk = c.scr + (size_t)c.frame_of(n0) * c.FB;
     const long long step = SIDE ? -(long long)c.FB : (long long)c.FB;
     const int plane = c.JG * 16;
+    const int eoff = NH * plane - 12 * (c.JG - 1 - lc.group);     // exponent slot relative to the first mantissa plane slot
+    unsigned char* blk = ss.wblk;
 #pragma unroll 1
     for (int j = 0; j < kc; ++j) {
       f2 ACC[NP]; int E;
@@ -507,13 +511,14 @@ __device__ __forceinline__ void run_chunk(const FastCtx<SIDE>& c, SweepState<NS>
         // the reader's pair j is this lane's pair NP-1-j (mirrored group, mirrored packing)
 #pragma unroll
         for (int h = 0; h < NH; ++h)
-          asm volatile("st.global.v2.b64 [%0], {%1, %2};" ::"l"(blk + h * plane + gm * 16),
+          asm volatile("st.global.v2.b64 [%0], {%1, %2};" ::"l"(blk + h * plane),
                        "l"(ACC[NP - 1 - 2 * h]), "l"(ACC[NP - 2 - 2 * h]) : "memory");
-        *reinterpret_cast<int*>(blk + NH * plane + gm * 4) = E;
+        *reinterpret_cast<int*>(blk + eoff) = E;
       }
       row += row_bytes;
       blk += step;
     }
+    ss.wblk = blk;
   } else {
     char* post = reinterpret_cast<char*>(c.sm.post + (size_t)pbuf * K * c.PS);
     const int post_bytes = c.PS * 4;
@@ -548,7 +553,7 @@ __device__ __forceinline__ void run_chunk(const FastCtx<SIDE>& c, SweepState<NS>
 // helper warps (after it the helpers' prefetch for the next chunk has landed and the posterior buffer
 // of the previous chunk is consumed), import the halo.
 template <int K, int NWMAX, int SIDE, int NS>
-__device__ __forceinline__ void chunk_boundary(const FastCtx<SIDE>& c, SweepState<NS>& ss, int cc, int* abort_flag) {
+__device__ __forceinline__ void chunk_boundary(const FastCtx<SIDE>& c, SweepState<NS>& ss, int cc, int* abort_flag, int& tc) {
   constexpr int NH = NS / 4, HL = 2 * K / NS;
   static_assert(HL * NS == 2 * K && HL >= 1, "the halo must be whole lanes");
   const int hb = cc & 1, NW = c.NW, w = c.w, lane = c.lane;
@@ -561,7 +566,9 @@ __device__ __forceinline__ void chunk_boundary(const FastCtx<SIDE>& c, SweepStat
     c.sm.halo_e[slot] = st.e;
   }
   if (ss.lc.owned && ss.maxbound > kLostBound) *abort_flag = 1;
+  B200CTC_TRACE_EVENT(tc, 30);
   named_bar_sync(bar_chunk(SIDE), (NW + kReducers) * 32);
+  B200CTC_TRACE_EVENT(tc, 31);
   if (w > 0 && lane < HL) {
     const int slot = (hb * NWMAX + (w - 1)) * HL + lane;
 #pragma unroll
@@ -730,6 +737,7 @@ __device__ void fast_side_sweep(const CallParams& p, int b, const UttMeta& m, co
     for (int j = 0; j < NP; ++j) ss.st.A[j] = mk<SIDE>(v[j], v[j + NP]);
   }
   ss.maxbound = -(1 << 30); ss.inv_mP = 0.f; ss.eP = 0;
+  ss.wblk = c.scr + (size_t)c.frame_of(0) * c.FB + (size_t)(JG - 1 - min(lc.group, JG - 1)) * 16;
   B200CTC_TRACE_DECL(tc);
   B200CTC_TRACE_EVENT(tc, 10);
 
@@ -758,7 +766,7 @@ __device__ void fast_side_sweep(const CallParams& p, int b, const UttMeta& m, co
     B200CTC_TRACE_EVENT(tc, 2);
     run_chunk<K, false, SIDE, NT, NS>(c, ss, rs, 0, 0, n0, kc, false);
     B200CTC_TRACE_EVENT(tc, 3);
-    chunk_boundary<K, NWMAX, SIDE, NS>(c, ss, cc, abort_flag);
+    chunk_boundary<K, NWMAX, SIDE, NS>(c, ss, cc, abort_flag, tc);
     rs = rs == kRowsRing - 1 ? 0 : rs + 1;
   }
 
@@ -817,7 +825,7 @@ __device__ void fast_side_sweep(const CallParams& p, int b, const UttMeta& m, co
     B200CTC_TRACE_EVENT(tc, 13);
     run_chunk<K, true, SIDE, NT, NS>(c, ss, rs, par, par, n0, kc, write_post);
     B200CTC_TRACE_EVENT(tc, 14);
-    chunk_boundary<K, NWMAX, SIDE, NS>(c, ss, cc, abort_flag);
+    chunk_boundary<K, NWMAX, SIDE, NS>(c, ss, cc, abort_flag, tc);
     rs = rs == kRowsRing - 1 ? 0 : rs + 1;
   }
   B200CTC_TRACE_EVENT(tc, 15);
