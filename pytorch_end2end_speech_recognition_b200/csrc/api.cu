@@ -63,7 +63,7 @@ WorkspaceLayout make_layout(const BatchTotals& t, int T, int B) {
   size_t off = 0;
   w.off_meta = off;   off += align_up((size_t)B * sizeof(UttMeta));
   w.off_order = off;  off += align_up((size_t)B * sizeof(int));
-  w.off_flags = off;  off += align_up((size_t)B * sizeof(int));
+  w.off_flags = off;  off += align_up((size_t)(B + 1) * sizeof(int));   // + the finished-utterance counter
   w.off_labels = off; off += align_up((size_t)t.sum_labels * sizeof(int));
   w.blob_bytes = off;
   w.off_lse = off;    off += align_up((size_t)T * B * sizeof(float));
@@ -232,6 +232,7 @@ int b200ctc_loss_and_grad(b200ctc_handle* h, const float* acts, int64_t acts_str
     order[b] = b;
     flags[b] = 0;
   }
+  flags[B] = 0;   // finished-utterance counter (the last CTA of the lattice kernel sums the costs)
   if (tot.sum_labels > 0) std::memcpy(labels, flat_labels, (size_t)tot.sum_labels * sizeof(int));
   // longest lattice first: CTAs are dispatched in index order, so the tail of the launch is short
   std::stable_sort(order, order + B, [&](int x, int y) {
@@ -256,6 +257,7 @@ int b200ctc_loss_and_grad(b200ctc_handle* h, const float* acts, int64_t acts_str
   p.meta = reinterpret_cast<const UttMeta*>(ws + lay.off_meta);
   p.order = reinterpret_cast<const int*>(ws + lay.off_order);
   p.flags = reinterpret_cast<int*>(ws + lay.off_flags);
+  p.done_counter = p.flags + B;
   p.labels = reinterpret_cast<const int*>(ws + lay.off_labels);
   p.lse = reinterpret_cast<float*>(ws + lay.off_lse);
   p.em = reinterpret_cast<float*>(ws + lay.off_em);
@@ -270,9 +272,8 @@ int b200ctc_loss_and_grad(b200ctc_handle* h, const float* acts, int64_t acts_str
   if (prof) cudaEventRecord(h->prof[0], stream);
   cudaError_t e = launch_softmax_rows(p, stream);
   if (prof) cudaEventRecord(h->prof[1], stream);
-  if (e == cudaSuccess) e = launch_lattice(p, max_L, stream);
+  if (e == cudaSuccess) e = launch_lattice(p, max_L, stream);   // its last CTA also writes loss_sum (fixed-order sum)
   if (prof) cudaEventRecord(h->prof[2], stream);
-  if (e == cudaSuccess) e = launch_cost_sum(p, stream);
   if (prof) {
     cudaEventRecord(h->prof[3], stream);
     h->prof_valid = true;

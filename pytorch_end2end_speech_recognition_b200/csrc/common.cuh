@@ -34,6 +34,7 @@ struct CallParams {
   const int* order;       // [B] utterances sorted by decreasing lattice work (longest first)
   const int* labels;      // flat labels (device copy)
   int* flags;             // [B] per-utterance flags written by the kernels
+  int* done_counter;      // [1] utterances finished by the lattice kernel (zeroed with the plan upload)
   float* lse;             // [T*B] row log-sum-exp, natural log, time-major (t*B+b)
   float* em;              // gathered emissions (gathered mode) or nullptr
   unsigned char* scratch; // alpha/beta scratch
@@ -52,7 +53,6 @@ constexpr int kGroupBytes = 32;  // scratch bytes per (frame, group): the safe l
 // host launchers (each in its own .cu)
 cudaError_t launch_softmax_rows(const CallParams& p, cudaStream_t stream);
 cudaError_t launch_lattice(const CallParams& p, int max_L, cudaStream_t stream);
-cudaError_t launch_cost_sum(const CallParams& p, cudaStream_t stream);
 cudaError_t launch_greedy(const float* logits, long long stride_b, long long stride_t, const int* lens,
                           int T, int V, int B, int blank, int* out_tokens, int* out_lens,
                           cudaStream_t stream);

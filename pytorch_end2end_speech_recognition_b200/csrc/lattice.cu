@@ -1,5 +1,5 @@
 // K2: alpha/beta lattice recursion + posterior occupancy update of the gradient rows.
-// K3: fixed-order sum of the per-utterance costs.
+// K3 (fused into K2's last CTA): fixed-order sum of the per-utterance costs.
 #include <cstdlib>
 
 #include "common.cuh"
@@ -23,42 +23,50 @@ __global__ void __launch_bounds__(2 * (NWMAX + kReducers) * 32, 1) lattice_kerne
   const UttMeta m = p.meta[b];
   if (!m.feasible) {  // K1 already zero-filled its gradient rows
     if (threadIdx.x == 0) p.costs[b] = INFINITY;
-    return;
-  }
-  if (m.T == 0) {  // empty utterance with an empty target: probability one
+  } else if (m.T == 0) {  // empty utterance with an empty target: probability one
     if (threadIdx.x == 0) p.costs[b] = 0.f;
-    return;
-  }
-  bool use_safe = (p.flags[b] & FLAG_EXTREME_ROW) != 0 || fast_warps_needed<K, NS>(m.L) > NWMAX;
-  bool dirty = false;
-  if (!use_safe) {
-    int* abort_word = nullptr;
-    lattice_fast_utterance<K, NWMAX, NS>(p, b, smem, &abort_word);
-    __syncthreads();
-    use_safe = *abort_word != 0;
-    if (use_safe) {
-      dirty = p.grads != nullptr;  // part of the gradient rows may already have been rewritten
-      if (threadIdx.x == 0) atomicOr(p.flags + b, FLAG_PRECISION_LOST);
-      __threadfence();             // order this thread's row updates before the rows are rebuilt
+  } else {
+    bool use_safe = (p.flags[b] & FLAG_EXTREME_ROW) != 0 || fast_warps_needed<K, NS>(m.L) > NWMAX;
+    bool dirty = false;
+    if (!use_safe) {
+      int* abort_word = nullptr;
+      lattice_fast_utterance<K, NWMAX, NS>(p, b, smem, &abort_word);
       __syncthreads();
+      use_safe = *abort_word != 0;
+      if (use_safe) {
+        dirty = p.grads != nullptr;  // part of the gradient rows may already have been rewritten
+        if (threadIdx.x == 0) atomicOr(p.flags + b, FLAG_PRECISION_LOST);
+        __threadfence();             // order this thread's row updates before the rows are rebuilt
+        __syncthreads();
+      }
     }
+    if (use_safe) lattice_safe_utterance(p, b, smem, dirty);
   }
-  if (use_safe) lattice_safe_utterance(p, b, smem, dirty);
-}
 
-// Single CTA, fixed summation tree: the returned loss is bit-reproducible run to run.
-__global__ void __launch_bounds__(256) cost_sum_kernel(const float* __restrict__ costs, int B,
-                                                        float* __restrict__ loss_sum) {
-  __shared__ double part[256];
-  double acc = 0.0;
-  for (int i = threadIdx.x; i < B; i += 256) acc += (double)costs[i];
-  part[threadIdx.x] = acc;
+  // K3, fused: the CTA that finishes last sums the per-utterance costs in a fixed order (256 strided
+  // partial sums in double, then a tree), so the returned loss is bit-reproducible run to run.
+  if (p.loss_sum == nullptr) return;
+  __shared__ int s_last;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();                 // this CTA's cost is visible before the ticket is taken
+    s_last = atomicAdd(p.done_counter, 1) == p.B - 1;
+  }
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence();
+  double* part = reinterpret_cast<double*>(smem);
+  if (threadIdx.x < 256) {
+    double acc = 0.0;
+    for (int i = threadIdx.x; i < p.B; i += 256) acc += (double)__ldcg(p.costs + i);
+    part[threadIdx.x] = acc;
+  }
   __syncthreads();
   for (int o = 128; o > 0; o >>= 1) {
     if ((int)threadIdx.x < o) part[threadIdx.x] += part[threadIdx.x + o];
     __syncthreads();
   }
-  if (threadIdx.x == 0) *loss_sum = (float)part[0];
+  if (threadIdx.x == 0) *p.loss_sum = (float)part[0];
 }
 
 template <int K, int NWMAX, int NS>
@@ -74,6 +82,7 @@ cudaError_t launch_lattice_t(const CallParams& p, int max_L, cudaStream_t stream
     smem = s > smem ? s : smem;
   }
   smem = smem > safe_smem_bytes(max_L) ? smem : safe_smem_bytes(max_L);
+  smem = smem > 256 * sizeof(double) ? smem : 256 * sizeof(double);   // the fused cost sum
   if (smem > 227 * 1024) return cudaErrorInvalidConfiguration;
   if (smem > 48 * 1024) {
     cudaError_t e = cudaFuncSetAttribute(lattice_kernel<K, NWMAX, NS>,
@@ -117,11 +126,5 @@ extern "C" __attribute__((visibility("default"))) int b200ctc_debug_read_trace(l
   return 0;
 }
 #endif
-
-cudaError_t launch_cost_sum(const CallParams& p, cudaStream_t stream) {
-  if (!p.loss_sum) return cudaSuccess;
-  cost_sum_kernel<<<1, 256, 0, stream>>>(p.costs, p.B, p.loss_sum);
-  return cudaGetLastError();
-}
 
 }  // namespace b200ctc

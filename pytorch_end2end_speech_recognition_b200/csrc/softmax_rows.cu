@@ -19,74 +19,93 @@ namespace {
 
 constexpr float kExtremeLogProb = -69.0f;  // y < 2^-100 (natural log -69.3): outside the fast lattice's range
 
-// ---- small vocabulary: one warp per row, the row lives in registers ----------------------------
-template <int NV>  // values per lane, V <= 32*NV
+// ---- small vocabulary: LPR lanes per row (8, 16 or 32), the row lives in registers ---------------
+// Lane q of a row's lane group holds elements q, q+LPR, q+2*LPR, ...: every load/store instruction of
+// the warp touches 32/LPR rows with LPR consecutive floats each, and the reductions are log2(LPR)
+// shuffle steps.  V <= LPR*NV.
+template <int LPR>
+__device__ __forceinline__ float group_max(float v) {
+#pragma unroll
+  for (int o = LPR / 2; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+template <int LPR>
+__device__ __forceinline__ float group_sum(float v) {
+#pragma unroll
+  for (int o = LPR / 2; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+template <int LPR, int NV>
 __global__ void __launch_bounds__(256) softmax_rows_warp_kernel(CallParams p) {
+  constexpr int RPW = 32 / LPR;                       // rows per warp
   const int lane = threadIdx.x & 31;
-  const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int q = lane & (LPR - 1), sub = lane / LPR;
   const long long n_rows = (long long)p.T * p.B;
-  if (row >= n_rows) return;
+  long long row = ((long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * RPW + sub;
+  const bool row_ok = row < n_rows;
+  if (!row_ok) row = n_rows - 1;                      // keep the lane in the shuffles; it stores nothing
   const int t = (int)(row / p.B);
   const int b = (int)(row - (long long)t * p.B);
   const UttMeta m = p.meta[b];
-  float* grow = p.grads ? p.grads + row * p.V : nullptr;
-  if (t >= m.T || !m.feasible) {
-    if (grow) {
-#pragma unroll
-      for (int i = 0; i < NV; ++i) {
-        int v = lane + 32 * i;
-        if (v < p.V) grow[v] = 0.f;
-      }
-    }
-    return;
-  }
+  float* grow = (p.grads && row_ok) ? p.grads + row * p.V : nullptr;
+  const bool live = t < m.T && m.feasible;
   const float* arow = p.acts + (long long)t * p.as_t + (long long)b * p.as_b;
   float x[NV];
-  float mx = -INFINITY, mn = INFINITY;
+  float mx = -INFINITY;
 #pragma unroll
   for (int i = 0; i < NV; ++i) {
-    int v = lane + 32 * i;
-    x[i] = (v < p.V) ? __ldg(arow + v) : -INFINITY;
+    const int v = q + LPR * i;
+    x[i] = (live && v < p.V) ? __ldg(arow + v) : -INFINITY;
     mx = fmaxf(mx, x[i]);
-    if (v < p.V) mn = fminf(mn, x[i]);
   }
-  mx = warp_max(mx);
-  mn = warp_min(mn);
+  mx = group_max<LPR>(mx);
+  if (!live) mx = 0.f;                                // avoid inf - inf in dead rows
   float s = 0.f;
+  float e[NV];
 #pragma unroll
   for (int i = 0; i < NV; ++i) {
-    x[i] = __expf(x[i] - mx);  // exp(-inf) = 0 for the padding lanes
-    s += x[i];
+    e[i] = __expf(x[i] - mx);                         // exp(-inf) = 0 for the padding lanes
+    s += e[i];
   }
-  s = warp_sum(s);
-  const float inv = 1.0f / s;
+  s = group_sum<LPR>(s);
+  const float inv = live ? 1.0f / s : 0.f;
   const float lse = mx + logf(s);
-  if (lane == 0) {
+  // any probability of the row below 2^-100?  (outside the fast lattice's range)
+  bool extreme = false;
+#pragma unroll
+  for (int i = 0; i < NV; ++i) extreme |= (q + LPR * i < p.V) && (x[i] - lse < kExtremeLogProb);
+  const unsigned ext = __ballot_sync(0xffffffffu, extreme && live && row_ok);
+  if (live && row_ok && q == 0) {
     p.lse[row] = lse;
-    if (mn - lse < kExtremeLogProb) atomicOr(p.flags + b, FLAG_EXTREME_ROW);
+    if ((ext >> (sub * LPR)) & ((LPR == 32) ? 0xffffffffu : ((1u << LPR) - 1u))) atomicOr(p.flags + b, FLAG_EXTREME_ROW);
   }
   if (grow) {
 #pragma unroll
     for (int i = 0; i < NV; ++i) {
-      int v = lane + 32 * i;
-      if (v < p.V) grow[v] = x[i] * inv;
+      const int v = q + LPR * i;
+      if (v < p.V) grow[v] = e[i] * inv;              // zero for rows t >= act_lens[b] and infeasible utterances
     }
   }
   if (p.gathered) {
-    // label-indexed emissions, taken from the register-resident row by shuffle
+    // label-indexed emissions, taken from the register-resident row by shuffle (all lanes take part)
     float* erow = p.em + m.em_off + (long long)t * m.W;
     const int* lab = p.labels + m.lab_off;
-    for (int base = 0; base < m.W; base += 32) {
-      int i = base + lane;
-      int sym = (i == 0) ? p.blank : ((i <= m.L) ? lab[i - 1] : -1);
+    const bool wr = live && row_ok;
+    int w_max = wr ? m.W : 0;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) w_max = max(w_max, __shfl_xor_sync(0xffffffffu, w_max, o));
+    for (int base = 0; base < w_max; base += LPR) {
+      const int i = base + q;
+      const int sym = (!wr || i >= m.W) ? -1 : ((i == 0) ? p.blank : ((i <= m.L) ? lab[i - 1] : -1));
       float val = 0.f;
 #pragma unroll
       for (int k = 0; k < NV; ++k) {
-        // every lane asks lane (sym & 31) for its k-th value; keep the one whose slot matches
-        float cand = __shfl_sync(0xffffffffu, x[k], sym & 31);
-        if (sym >= 0 && (sym >> 5) == k) val = cand * inv;
+        // every lane asks the lane of its own row that holds element sym for its k-th value
+        const float cand = __shfl_sync(0xffffffffu, e[k], (lane & ~(LPR - 1)) | (sym & (LPR - 1)));
+        if (sym >= 0 && sym / LPR == k) val = cand * inv;
       }
-      if (i < m.W) erow[i] = val;
+      if (wr && i < m.W) erow[i] = val;
     }
   }
 }
@@ -225,11 +244,14 @@ cudaError_t launch_softmax_rows(const CallParams& p, cudaStream_t stream) {
   if (n_rows == 0) return cudaSuccess;
   if (p.V <= 256) {
     const int warps = 8;
-    const unsigned grid = (unsigned)((n_rows + warps - 1) / warps);
-    if (p.V <= 32) softmax_rows_warp_kernel<1><<<grid, warps * 32, 0, stream>>>(p);
-    else if (p.V <= 64) softmax_rows_warp_kernel<2><<<grid, warps * 32, 0, stream>>>(p);
-    else if (p.V <= 128) softmax_rows_warp_kernel<4><<<grid, warps * 32, 0, stream>>>(p);
-    else softmax_rows_warp_kernel<8><<<grid, warps * 32, 0, stream>>>(p);
+    auto grid_for = [&](int rows_per_warp) {
+      const long long per_cta = (long long)warps * rows_per_warp;
+      return (unsigned)((n_rows + per_cta - 1) / per_cta);
+    };
+    if (p.V <= 32) softmax_rows_warp_kernel<8, 4><<<grid_for(4), warps * 32, 0, stream>>>(p);
+    else if (p.V <= 64) softmax_rows_warp_kernel<16, 4><<<grid_for(2), warps * 32, 0, stream>>>(p);
+    else if (p.V <= 128) softmax_rows_warp_kernel<32, 4><<<grid_for(1), warps * 32, 0, stream>>>(p);
+    else softmax_rows_warp_kernel<32, 8><<<grid_for(1), warps * 32, 0, stream>>>(p);
   } else {
     const size_t smem = (size_t)(p.V + 4) * sizeof(float);
     if (smem > 48 * 1024) {
