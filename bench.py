@@ -105,14 +105,22 @@ class ClockSampler(threading.Thread):
                 "reasons": sorted(self.reasons), "samples": len(self.sm)}
 
 
+def _host_threads():
+    """All the host cores this process may use (torchrun exports OMP_NUM_THREADS=1: ignore it)."""
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except AttributeError:
+        return max(1, os.cpu_count() or 1)
+
+
 def cpu_baseline(wl, acts_np, budget_s=12.0, kind_note=""):
     """The oracle's C++/OpenMP restatement of the warp-ctc CPU path (float), timed on this host."""
     from oracle import ctc_cpu
-    threads = ctc_cpu.max_threads()
+    threads = _host_threads()
     ctc_cpu.ctc_cpu(acts_np[:, :min(8, wl.B)], *_slice(wl, min(8, wl.B)))      # warm-up (page in, build)
     reps, t0 = 0, time.perf_counter()
     while True:
-        ctc_cpu.ctc_cpu(acts_np, wl.labels, wl.act_lens, wl.label_lens, precision="f32")
+        ctc_cpu.ctc_cpu(acts_np, wl.labels, wl.act_lens, wl.label_lens, precision="f32", num_threads=threads)
         reps += 1
         dt = time.perf_counter() - t0
         if dt > budget_s or reps >= 20:
@@ -140,11 +148,12 @@ def run_reference(args):
     wl = workloads.make_lengths_and_labels(args.workload)
     acts = workloads.make_acts(wl).numpy()
     frames = int(wl.act_lens.sum())
+    threads = _host_threads()
     for _ in range(max(args.warmup, 1)):
-        ctc_cpu.ctc_cpu(acts, wl.labels, wl.act_lens, wl.label_lens, precision="f32")
+        ctc_cpu.ctc_cpu(acts, wl.labels, wl.act_lens, wl.label_lens, precision="f32", num_threads=threads)
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        ctc_cpu.ctc_cpu(acts, wl.labels, wl.act_lens, wl.label_lens, precision="f32")
+        ctc_cpu.ctc_cpu(acts, wl.labels, wl.act_lens, wl.label_lens, precision="f32", num_threads=threads)
     dt = time.perf_counter() - t0
     value = frames * args.steps / dt
     total, strict, _ = workloads.algorithmic_bytes(wl)
@@ -153,7 +162,7 @@ def run_reference(args):
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": wl.name, "frames_per_step": frames, "algorithmic_bytes_per_step": total},
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": ctc_cpu.max_threads(), "kind": "port",
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port",
                          "sample": "one full mini-batch per step; C++/OpenMP fp32 restatement of the warp-ctc CPU path "
                                    "(warp-ctc is not vendored in the reference)"},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
