@@ -66,6 +66,9 @@ __device__ __forceinline__ void trace_event(int& cnt, int tag) {
 #define B200CTC_TRACE_EVENT(cnt, tag) do { (void)cnt; } while (0)
 #endif
 
+#ifndef B200CTC_ABLATE
+#define B200CTC_ABLATE 0   // developer timing experiments (tools/ablate_lattice.py); 0 = product
+#endif
 constexpr int kEZero = -(1 << 28);  // exponent of an all-zero lane
 constexpr int kRowsRing = 3;        // emission-row chunks in flight (this chunk, the next one, the reducers' one)
 constexpr int kOthRing = 8;         // per-thread ring of the opposite side's records: two chunks of K = 4 frames
@@ -306,11 +309,14 @@ __device__ __forceinline__ void sts_f32(void* base, int byte_off, float v) {
   *reinterpret_cast<float*>(reinterpret_cast<char*>(base) + byte_off) = v;
 }
 template <int N>
-__device__ __forceinline__ float f2_max_all(const f2 (&v)[N]) {   // max over the 2N floats
-  float m = fmax3(f2_lo(v[0]), f2_hi(v[0]), f2_lo(v[1]));
-  m = fmaxf(m, f2_hi(v[1]));
-  if (N == 4) m = fmaxf(fmax3(m, f2_lo(v[2]), f2_hi(v[2])), fmaxf(f2_lo(v[N - 1]), f2_hi(v[N - 1])));
-  return m;
+__device__ __forceinline__ float f2_max_all(const f2 (&v)[N]) {   // max over the 2N floats, two levels deep for N = 4
+  if (N == 4) {
+    const float t1 = fmax3(f2_lo(v[0]), f2_hi(v[0]), f2_lo(v[1]));
+    const float t2 = fmax3(f2_hi(v[1]), f2_lo(v[2]), f2_hi(v[2]));
+    const float t3 = fmaxf(f2_lo(v[N - 1]), f2_hi(v[N - 1]));
+    return fmax3(t1, t2, t3);
+  }
+  return fmaxf(fmax3(f2_lo(v[0]), f2_hi(v[0]), f2_lo(v[1])), f2_hi(v[1]));
 }
 
 // One frame of the recursion for one lane.  ACC: pre-emission sums at exponent E; st: the new
@@ -320,14 +326,26 @@ __device__ __forceinline__ void lattice_frame(LaneState<NS>& st, const LaneConst
                                               bool lane0, f2 (&ACC)[NS / 2], int& E) {
   constexpr int NP = NS / 2;
   const float a_top = el_j4<SIDE>(st.A[NP - 1]), a_top2 = el_j4<SIDE>(st.A[NP - 2]);
+#if B200CTC_ABLATE == 4
+  const float n1 = a_top, n2 = a_top2;
+  int ne = st.e;
+#else
   const float n1 = __shfl_up_sync(0xffffffffu, a_top, 1);
   const float n2 = __shfl_up_sync(0xffffffffu, a_top2, 1);
   int ne = __shfl_up_sync(0xffffffffu, st.e, 1);
+#endif
   // emissions: one broadcast load for the blank positions, one gather per label position
+#if B200CTC_ABLATE == 2
+  const float yb = 0.5f;
+  float y[NP];
+#pragma unroll
+  for (int m = 0; m < NP; ++m) y[m] = 0.25f + 0.01f * m;
+#else
   const float yb = lds_f32(row, lc.idxB_blank);
   float y[NP];
 #pragma unroll
   for (int m = 0; m < NP; ++m) y[m] = lds_f32(row, lc.idxB[m]);
+#endif
   if (lane0) ne = kEZero;                      // nothing below the window: scales n1, n2 to zero
   E = max(st.e, ne);
   const float so = pow2_neg(st.e - E), sn = pow2_neg(ne - E);
@@ -355,7 +373,11 @@ __device__ __forceinline__ void lattice_frame(LaneState<NS>& st, const LaneConst
       W[j] = f2_mul(ACC[j], YB);
     }
   }
+#if B200CTC_ABLATE == 3
+  const float mx = 1.0f;
+#else
   const float mx = f2_max_all<NP>(W);
+#endif
   // renormalise: largest mantissa -> [1,2).  mx == 0 (or NaN from garbage): the lane is empty.
   const int eb = __float_as_int(mx) >> 23;                       // biased exponent
   const bool nz = mx > 0.f;
@@ -507,7 +529,7 @@ __device__ __forceinline__ void run_chunk(const FastCtx<SIDE>& c, SweepState<NS>
     for (int j = 0; j < kc; ++j) {
       f2 ACC[NP]; int E;
       lattice_frame<SIDE, NS>(ss.st, lc, row, lane0, ACC, E);
-      if (lc.owned) {
+      if (lc.owned && B200CTC_ABLATE != 1) {
         // the reader's pair j is this lane's pair NP-1-j (mirrored group, mirrored packing)
 #pragma unroll
         for (int h = 0; h < NH; ++h)
@@ -532,7 +554,7 @@ __device__ __forceinline__ void run_chunk(const FastCtx<SIDE>& c, SweepState<NS>
         f2 ACC[NP]; int E;
         lattice_frame<SIDE, NS>(ss.st, lc, row, lane0, ACC, E);
         const bool wr = (unsigned)(ss.rd_hi - (n0 + j)) < (unsigned)ss.wr_len;   // did the other side store this record?
-        posterior_frame<SIDE, NS>(ss, wr ? blk : zero_blk, plane, post, store);
+        if (B200CTC_ABLATE != 5) posterior_frame<SIDE, NS>(ss, wr ? blk : zero_blk, plane, post, store && B200CTC_ABLATE != 6);
         row += row_bytes;
         post += post_bytes;
         blk += c.FB;
@@ -567,6 +589,9 @@ __device__ __forceinline__ void chunk_boundary(const FastCtx<SIDE>& c, SweepStat
   }
   if (ss.lc.owned && ss.maxbound > kLostBound) *abort_flag = 1;
   B200CTC_TRACE_EVENT(tc, 30);
+#if B200CTC_ABLATE == 7
+  if ((cc & 7) == 7)
+#endif
   named_bar_sync(bar_chunk(SIDE), (NW + kReducers) * 32);
   B200CTC_TRACE_EVENT(tc, 31);
   if (w > 0 && lane < HL) {
@@ -1016,7 +1041,11 @@ __device__ void lattice_fast_utterance(const CallParams& p, int b, unsigned char
   const int NW = fast_warps_needed<K, NS>(L);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int side = warp / (NWMAX + kReducers);
-  const int w = warp - side * (NWMAX + kReducers);
+  int w = warp - side * (NWMAX + kReducers);
+  // Scheduler balance: warp i issues on SM sub-partition i % 4.  Early in phase 1 (and late in phase 2)
+  // only the lowest lattice windows of each side are inside the reachable band; giving the backward
+  // side its windows in reverse warp order puts the two busy windows on different sub-partitions.
+  if (side == 1 && w < NWMAX) w = NWMAX - 1 - w;
 
   // ---- shared memory: common part, then one block per side ----
   FastCommon cm;
