@@ -52,7 +52,7 @@ int totals_from_lens(const int* label_lens, const int* act_lens, int T, int B, B
     if (L < 0 || Tb < 0 || Tb > T) return B200CTC_STATUS_INVALID_VALUE;
     t.sum_labels += L;
     t.em_floats += (long long)Tb * em_width_of(L);
-    t.scratch_units += (long long)Tb * groups_of(L);
+    t.scratch_units += (long long)(Tb + 1) * groups_of(L);   // + one dump frame block
   }
   *out = t;
   return B200CTC_STATUS_SUCCESS;
@@ -227,7 +227,7 @@ int b200ctc_loss_and_grad(b200ctc_handle* h, const float* acts, int64_t acts_str
     m.em_off = em_off;
     lab_off += L;
     em_off += (long long)Tb * m.W;
-    scratch_off += (long long)Tb * m.J;
+    scratch_off += (long long)(Tb + 1) * m.J;
     if (m.feasible) max_L = std::max(max_L, L);
     order[b] = b;
     flags[b] = 0;

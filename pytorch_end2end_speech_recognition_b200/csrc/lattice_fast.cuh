@@ -420,6 +420,7 @@ struct SweepState {
   float inv_mP; int eP;     // total probability P = mP * 2^eP (phase 2)
   int maxbound;             // running maximum of the range-check bound (phase 2), as a power-of-two exponent
   unsigned char* wblk;      // phase 1: this lane's slot in the frame block of the current step (running pointer)
+  int wstep, weoff;         // its stride per step (0 for lanes that own no group: they hit the dump block) and exponent offset
 };
 constexpr int kLostBound = 127 + 110 - 24 - 2;   // maxbound above this: FLAG_PRECISION_LOST
 
@@ -517,20 +518,26 @@ __device__ __forceinline__ void run_chunk(const FastCtx<SIDE>& c, SweepState<NS>
   const bool active = n0 <= ss.act_hi && n0 + kc - 1 >= ss.act_lo;
   if (!PH2) {
     if (!active) {
-      ss.wblk += (SIDE ? -(long long)c.FB : (long long)c.FB) * kc;
+      ss.wblk += (long long)ss.wstep * kc;
       return;
     }
     // scratch slot of this lane's group for the opposite side's reader (mirrored group order)
-    const long long step = SIDE ? -(long long)c.FB : (long long)c.FB;
     const int plane = c.JG * 16;
-    const int eoff = NH * plane - 12 * (c.JG - 1 - lc.group);     // exponent slot relative to the first mantissa plane slot
+    const int eoff = ss.weoff;                                    // exponent slot relative to the first mantissa plane slot
     unsigned char* blk = ss.wblk;
-#pragma unroll 1
+#if B200CTC_ABLATE == 8
+    LaneState<NS> dummy = ss.st;
+#endif
+#pragma unroll 2
     for (int j = 0; j < kc; ++j) {
       f2 ACC[NP]; int E;
+#if B200CTC_ABLATE == 8
+      { f2 ACC2[NP]; int E2; lattice_frame<SIDE, NS>(dummy, lc, row, lane0, ACC2, E2); }
+#endif
       lattice_frame<SIDE, NS>(ss.st, lc, row, lane0, ACC, E);
-      if (lc.owned && B200CTC_ABLATE != 1) {
-        // the reader's pair j is this lane's pair NP-1-j (mirrored group, mirrored packing)
+      if (B200CTC_ABLATE != 1) {
+        // the reader's pair j is this lane's pair NP-1-j (mirrored group, mirrored packing); lanes that
+        // own no group (halo, beyond the lattice) store into the dump block: no branch in the loop
 #pragma unroll
         for (int h = 0; h < NH; ++h)
           asm volatile("st.global.v2.b64 [%0], {%1, %2};" ::"l"(blk + h * plane),
@@ -538,18 +545,21 @@ __device__ __forceinline__ void run_chunk(const FastCtx<SIDE>& c, SweepState<NS>
         *reinterpret_cast<int*>(blk + eoff) = E;
       }
       row += row_bytes;
-      blk += step;
+      blk += ss.wstep;
     }
     ss.wblk = blk;
+#if B200CTC_ABLATE == 8
+    if (dummy.e == 12345) ss.maxbound = 1 << 20;   // keep the duplicate chain alive
+#endif
   } else {
     char* post = reinterpret_cast<char*>(c.sm.post + (size_t)pbuf * K * c.PS);
     const int post_bytes = c.PS * 4;
-    const bool store = write_post && lc.owned;
+    const bool store = write_post;   // lanes that own no group scatter into the dump slot
     if (active) {
       const unsigned char* blk = c.sm.oth + (size_t)obuf * K * c.FB;
       const unsigned char* zero_blk = c.sm.oth + (size_t)2 * K * c.FB;
       const int plane = c.JG * 16;
-#pragma unroll 1
+#pragma unroll 2
       for (int j = 0; j < kc; ++j) {
         f2 ACC[NP]; int E;
         lattice_frame<SIDE, NS>(ss.st, lc, row, lane0, ACC, E);
@@ -691,7 +701,7 @@ __device__ void fast_side_sweep(const CallParams& p, int b, const UttMeta& m, co
   lc.group = pos0 / NS;
   lc.owned = ((w == 0) || (lane >= HL)) && (lc.group < JG);
   lc.idxB_blank = 4 * (p.gathered ? 0 : p.blank);
-  lc.blankB = 4 * (c.RC + c.tid_side);
+  lc.blankB = 4 * (lc.owned ? c.RC + c.tid_side : c.PS - 4);
   lc.recB = min(lc.group, JG - 1) * 16;
   lc.expB = NH * JG * 16 + min(lc.group, JG - 1) * 4;
   {
@@ -707,7 +717,7 @@ __device__ void fast_side_sweep(const CallParams& p, int b, const UttMeta& m, co
       if (ok) {
         const int li = s >> 1;
         lc.idxB[mslot] = 4 * (p.gathered ? li + 1 : lab[li]);
-        lc.posB[mslot] = 4 * cm.slot_of_label[li];
+        if (lc.owned) lc.posB[mslot] = 4 * cm.slot_of_label[li];   // halo lanes scatter into the dump slot
         const bool sk = SIDE ? (s + 2 < S && lab[li] != lab[li + 1]) : (s >= 3 && lab[li] != lab[li - 1]);
         kk[mslot] = sk ? 1.f : 0.f;
       }
@@ -762,7 +772,12 @@ __device__ void fast_side_sweep(const CallParams& p, int b, const UttMeta& m, co
     for (int j = 0; j < NP; ++j) ss.st.A[j] = mk<SIDE>(v[j], v[j + NP]);
   }
   ss.maxbound = -(1 << 30); ss.inv_mP = 0.f; ss.eP = 0;
-  ss.wblk = c.scr + (size_t)c.frame_of(0) * c.FB + (size_t)(JG - 1 - min(lc.group, JG - 1)) * 16;
+  {
+    const int gm = JG - 1 - min(lc.group, JG - 1);             // the reader's (mirrored) group index
+    ss.weoff = NH * JG * 16 - 12 * gm;
+    ss.wstep = lc.owned ? (SIDE ? -c.FB : c.FB) : 0;
+    ss.wblk = c.scr + (size_t)(lc.owned ? c.frame_of(0) : T) * c.FB + (size_t)gm * 16;   // block T: the dump block
+  }
   B200CTC_TRACE_DECL(tc);
   B200CTC_TRACE_EVENT(tc, 10);
 

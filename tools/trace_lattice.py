@@ -61,6 +61,15 @@ def main():
         span = int(t[-1] - t[0])
         desc = ", ".join("%d->%d: %d x %.0f" % (k[0], k[1], v[1], v[0] / v[1]) for k, v in sorted(segs.items()) if v[0] > 0.01 * span)
         print("warp %2d  first %7d  span %7d  %s" % (w, int(t[0]) - t0, span, desc))
+    if "--raw" in sys.argv:            # raw event sequences (tag@cycle) of every warp around the middle of phase 1 and of phase 2
+        for lo_frac in (0.2, 0.7):
+            lo = t0 + int((t1 - t0) * lo_frac)
+            print("---- events in [%d, %d)" % (lo - t0, lo - t0 + 8000))
+            for w in range(64):
+                t, tag = t_all[w], tag_all[w]
+                sel = [(int(x) - t0, int(g)) for x, g in zip(t, tag) if lo <= x < lo + 8000]
+                if sel:
+                    print("warp %2d: %s" % (w, " ".join("%d@%d" % (g, x - (lo - t0)) for x, g in sel)))
 
 
 if __name__ == "__main__":
