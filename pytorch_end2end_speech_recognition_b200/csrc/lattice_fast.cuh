@@ -70,7 +70,7 @@ __device__ __forceinline__ void trace_event(int& cnt, int tag) {
 #define B200CTC_ABLATE 0   // developer timing experiments (tools/ablate_lattice.py); 0 = product
 #endif
 constexpr int kEZero = -(1 << 28);  // exponent of an all-zero lane
-constexpr int kRowsRing = 3;        // emission-row chunks in flight (this chunk, the next one, the reducers' one)
+constexpr int kRowsRing = 4;        // emission-row chunks in the ring: the reducers' one, this chunk, the next one (landed), the one after (in flight)
 constexpr int kOthRing = 8;         // per-thread ring of the opposite side's records: two chunks of K = 4 frames
 constexpr int kReducers = 4;        // reducer warps per side: warp j takes frame j of every phase-2 chunk (== K)
 
@@ -907,6 +907,19 @@ __device__ __forceinline__ void reduce_frame(const CallParams& p, const FastComm
 #pragma unroll
   for (int i = 0; i < NWMAX; ++i)
     if (i < NW) accb += post[RC + i * 32 + lane];
+  if (one_row && n_seg <= 32 && !gathered) {
+    // the common small-vocabulary case, straight line: lane u owns symbol u's single row
+    float tot = 0.f, y = 0.f;
+    if (lane < n_seg) {
+      tot = post_row_sum_c4(post4 + (size_t)lane * C4, C4);
+      y = yrow[sym_first];
+    }
+    const float yb = yrow[p.blank];
+    accb = warp_sum(accb);
+    if (lane < n_seg) grow[sym_first] = y - tot;       // the touched symbols of a frame share one 128-byte row
+    if (lane == 0) grow[p.blank] = yb - accb;
+    return;
+  }
   if (one_row) {
     for (int u0 = 0; u0 < n_seg; u0 += 32) {
       const int u = u0 + lane;
@@ -964,22 +977,28 @@ __device__ void fast_side_helper(const CallParams& p, int b, const UttMeta& m, c
   }
   __syncwarp();
 
-  // rows of chunk 0
-  int rs = 0;
-  if (hj < T) stage_row<SIDE>(c, hj, hj);           // chunk 0 holds steps 0..min(K, M_side or T)-1; extra rows are harmless
-  cp_async_commit();
-  cp_async_wait<0>();
+  // Emission rows are staged TWO chunks ahead (ring slot = chunk & 3), so that the global-memory latency
+  // of a row never sits between the lattice warps and the chunk barrier.
+  const int nc1 = pl.nc1, n_chunks = pl.n_chunks;
+  auto chunk_start = [&](int cc) { return cc < nc1 ? cc * K : M_side + (cc - nc1) * K; };
+  auto stage_chunk = [&](int cc) {
+    if (cc < n_chunks) {
+      const int n = chunk_start(cc) + hj;
+      if (n < T) stage_row<SIDE>(c, (cc & (kRowsRing - 1)) * K + hj, n);   // a row past a short chunk is harmless
+    }
+    cp_async_commit();
+  };
+  stage_chunk(0);
+  stage_chunk(1);
+  cp_async_wait<1>();
   named_bar_sync(bar_chunk(SIDE), nbar);
 
   // ================================ phase 1 ================================
-  for (int n0 = 0; n0 < M_side; n0 += K) {
-    const int rs_next = rs == kRowsRing - 1 ? 0 : rs + 1;
-    const int nn = n0 + min(K, M_side - n0);                      // first step of the next chunk (phase 1 or 2)
-    if (nn + hj < T) stage_row<SIDE>(c, rs_next * K + hj, nn + hj);
-    cp_async_commit();
-    cp_async_wait<0>();
+  int cc = 0;
+  for (; cc < nc1; ++cc) {
+    stage_chunk(cc + 2);
+    cp_async_wait<1>();                       // rows of chunk cc+1 have landed
     named_bar_sync(bar_chunk(SIDE), nbar);
-    rs = rs_next;
   }
 
   // ================================ midpoint ================================
@@ -1005,45 +1024,42 @@ __device__ void fast_side_helper(const CallParams& p, int b, const UttMeta& m, c
   float* rowsum = c.sm.rowsum + (size_t)hj * (post_rows_max(c.L, V) + 4);
 
   // ================================ phase 2 ================================
-  int k2 = 0, rs_prev = 0;
-  for (int n0 = M_side; n0 < T; n0 += K, ++k2) {
+  int k2 = 0;
+  for (int n0 = M_side; n0 < T; n0 += K, ++k2, ++cc) {
     const int par = k2 & 1;
-    const int rs_next = rs == kRowsRing - 1 ? 0 : rs + 1;
     B200CTC_TRACE_EVENT(tc, 7);
     bool copying = false;
-    if (n0 + K + hj < T) {                            // what frame hj of the next chunk needs
-      stage_row<SIDE>(c, rs_next * K + hj, n0 + K + hj);
+    stage_chunk(cc + 2);
+    if (n0 + K + hj < T) {                            // the other side's records frame hj of the next chunk needs
       prefetch_other<SIDE>(c, (par ^ 1) * K + hj, n0 + K + hj, mbar);
       copying = true;
     }
-    cp_async_commit();
     B200CTC_TRACE_EVENT(tc, 8);
     if (reduce && k2 >= 1) {                          // frame hj of the previous chunk (it was a full chunk)
       const int n = n0 - K + hj;
       reduce_frame<NWMAX>(p, cm, c.sm.post + (size_t)((par ^ 1) * K + hj) * c.PS,
-                          c.sm.rows + (size_t)(rs_prev * K + hj) * c.RWS,
+                          c.sm.rows + (size_t)(((cc - 1) & (kRowsRing - 1)) * K + hj) * c.RWS,
                           p.grads + ((long long)c.frame_of(n) * p.B + b) * V, rowsum, c.RC, NW, C4, R, n_seg,
                           one_row, sym_first, lane);
     }
     B200CTC_TRACE_EVENT(tc, 9);
-    cp_async_wait<0>();
+    cp_async_wait<1>();
     if (copying) {
       mbar_wait(mbar, mphase);
       mphase ^= 1;
     }
     named_bar_sync(bar_chunk(SIDE), nbar);
-    rs_prev = rs;
-    rs = rs_next;
   }
   // the last chunk
   if (reduce) {
     const int n0 = M_side + (k2 - 1) * K, par = (k2 - 1) & 1;
     if (n0 + hj < T)
       reduce_frame<NWMAX>(p, cm, c.sm.post + (size_t)(par * K + hj) * c.PS,
-                          c.sm.rows + (size_t)(rs_prev * K + hj) * c.RWS,
+                          c.sm.rows + (size_t)(((cc - 1) & (kRowsRing - 1)) * K + hj) * c.RWS,
                           p.grads + ((long long)c.frame_of(n0 + hj) * p.B + b) * V, rowsum, c.RC, NW, C4, R, n_seg,
                           one_row, sym_first, lane);
   }
+  cp_async_wait<0>();
 }
 
 // The whole fast path for one utterance; every thread of the CTA calls it.  On return the shared
