@@ -210,3 +210,65 @@ def test_reentrancy_two_shapes_back_to_back():
         c_ref, g_ref = ctc_ref.ctc_cost_and_grad(a.cpu().numpy(), w.labels, w.act_lens, w.label_lens)
         assert np.allclose(r[0].cpu().numpy(), c_ref, rtol=LOSS_RTOL)
         assert np.max(np.abs(r[2].cpu().numpy() - g_ref)) < GRAD_ATOL
+
+
+def _seq(rng, L, V):
+    lab = rng.randint(1, V, size=L)
+    for j in range(1, L):
+        if rng.uniform() < 0.1:
+            lab[j] = lab[j - 1]
+    return lab.astype(np.int32)
+
+
+def test_every_short_length_and_chunk_tail():
+    """T = 1..26 crosses every chunk-tail / phase-split case of the lattice kernel (chunks of four
+    frames, the two sweeps meet in the middle, helper warps fetch two chunks ahead)."""
+    rng = np.random.RandomState(11)
+    for T in range(1, 27):
+        for L in sorted({0, 1, T // 3, T // 2}):
+            lab = _seq(rng, L, 7)
+            while len(lab) + ctc_ref.count_repeats(lab) > T:
+                lab = lab[:-1]
+            acts = rng.randn(T, 2, 7).astype(np.float32)
+            check(acts, np.concatenate([lab, lab]), [T, T], [len(lab), len(lab)])
+
+
+@pytest.mark.parametrize("L", [127, 128, 251, 252, 375, 376, 499])
+def test_lattice_window_boundaries(L):
+    """Label lengths at which the number of 256-state lattice windows per sweep changes (1..4 warps)."""
+    rng = np.random.RandomState(L)
+    V = 30
+    lab = _seq(rng, L, V)
+    T = L + ctc_ref.count_repeats(lab) + 40
+    acts = rng.randn(T, 2, V).astype(np.float32)
+    lab2 = _seq(rng, L // 2, V)
+    check(acts, np.concatenate([lab, lab2]), [T, T - 17], [L, len(lab2)], oracle="cpp")
+    assert ctc_mod.last_fallbacks() == (0, 0)
+
+
+def test_label_sequence_beyond_the_fast_lattice_takes_the_safe_path():
+    rng = np.random.RandomState(13)
+    L, V = 520, 12
+    lab = _seq(rng, L, V)
+    T = L + ctc_ref.count_repeats(lab) + 25
+    acts = rng.randn(T, 1, V).astype(np.float32)
+    check(acts, lab, [T], [L], oracle="cpp")
+
+
+def test_four_states_per_lane_variant_matches(monkeypatch):
+    """B200CTC_NS=4 selects the tuning variant with four lattice states per lane (twice the warps)."""
+    wl = workloads.make_lengths_and_labels(None, B=6, T=300, V=30, Lmax=140, kind="var", seed=14)
+    acts = workloads.make_acts(wl).numpy()
+    c8, _, g8 = run_gpu(acts, wl.labels, wl.act_lens, wl.label_lens)
+    monkeypatch.setenv("B200CTC_NS", "4")
+    c4, g4 = check(acts, wl.labels, wl.act_lens, wl.label_lens, oracle="cpp")
+    assert ctc_mod.last_fallbacks() == (0, 0)
+    assert np.allclose(c4, c8, rtol=1e-6) and np.max(np.abs(g4 - g8)) < 1e-5
+
+
+def test_results_are_bit_reproducible():
+    wl = workloads.make_lengths_and_labels(None, B=8, T=200, V=30, Lmax=80, kind="var", seed=15)
+    acts = workloads.make_acts(wl).numpy()
+    c1, l1, g1 = run_gpu(acts, wl.labels, wl.act_lens, wl.label_lens)
+    c2, l2, g2 = run_gpu(acts, wl.labels, wl.act_lens, wl.label_lens)
+    assert np.array_equal(c1, c2) and l1 == l2 and np.array_equal(g1, g2)
