@@ -453,7 +453,8 @@ __device__ __forceinline__ void stage_row(const FastCtx<SIDE>& c, int slot, int 
 
 // Posterior of one frame for one lane: the fresh renormalised state times the stored record of the
 // opposite side, normalised by P:  post = a * o * 2^(e + oe - eP) / mP.  Scatters the label
-// posteriors and the blank partial sum.  Every lane of the warp runs it; only owned lanes store.
+// posteriors and the blank partial sum.  Every lane of the warp runs it and stores: lanes that own no
+// group scatter into the dump slot, and a cost-only call points `post` at a dump row.
 // No band masks: for every state outside the reachable band at least one factor is exactly zero
 // (unreachable from this side's start: a == 0; unreachable from the other side's start: the stored
 // value is 0, or the record was never written and reads as zero -- prefetch_other).
@@ -461,7 +462,7 @@ __device__ __forceinline__ void stage_row(const FastCtx<SIDE>& c, int slot, int 
 // that matters out of the fp32 range.
 template <int SIDE, int NS>
 __device__ __forceinline__ void posterior_frame(SweepState<NS>& ss, const unsigned char* __restrict__ blk, int plane_bytes,
-                                                void* __restrict__ post, bool store) {
+                                                void* __restrict__ post) {
   constexpr int NP = NS / 2, NH = NS / 4;
   const LaneConst<NS>& lc = ss.lc;
   const LaneState<NS>& st = ss.st;
@@ -488,8 +489,9 @@ __device__ __forceinline__ void posterior_frame(SweepState<NS>& ss, const unsign
   // it cannot overflow or underflow; the running maximum is tested at the chunk boundary.
   const float omax = f2_max_all<NP>(O);
   ss.maxbound = max(ss.maxbound, (__float_as_int(omax) >> 23) + dexp);
-  if (store) {
-    float bsum = 0.f;
+  {
+    f2 bacc;
+    bool first = true;
 #pragma unroll
     for (int j = 0; j < NP; ++j) {
       const bool is_label = SIDE ? (j % 2 == 0) : (j % 2 == 1);
@@ -498,10 +500,11 @@ __device__ __forceinline__ void posterior_frame(SweepState<NS>& ss, const unsign
         sts_f32(post, lc.posB[u], el_j<SIDE>(PO[j]));
         sts_f32(post, lc.posB[u + NP / 2], el_j4<SIDE>(PO[j]));
       } else {
-        bsum += f2_lo(PO[j]) + f2_hi(PO[j]);
+        bacc = first ? PO[j] : f2_add(bacc, PO[j]);
+        first = false;
       }
     }
-    sts_f32(post, lc.blankB, bsum);
+    sts_f32(post, lc.blankB, f2_lo(bacc) + f2_hi(bacc));
   }
 }
 
@@ -552,9 +555,10 @@ __device__ __forceinline__ void run_chunk(const FastCtx<SIDE>& c, SweepState<NS>
     if (dummy.e == 12345) ss.maxbound = 1 << 20;   // keep the duplicate chain alive
 #endif
   } else {
+    // cost-only calls (no gradient buffer) walk phase 2 for the range check: their posteriors land in one dump row
     char* post = reinterpret_cast<char*>(c.sm.post + (size_t)pbuf * K * c.PS);
-    const int post_bytes = c.PS * 4;
-    const bool store = write_post;   // lanes that own no group scatter into the dump slot
+    const int post_bytes = write_post ? c.PS * 4 : 0;
+    const bool store = write_post;
     if (active) {
       const unsigned char* blk = c.sm.oth + (size_t)obuf * K * c.FB;
       const unsigned char* zero_blk = c.sm.oth + (size_t)2 * K * c.FB;
@@ -564,7 +568,7 @@ __device__ __forceinline__ void run_chunk(const FastCtx<SIDE>& c, SweepState<NS>
         f2 ACC[NP]; int E;
         lattice_frame<SIDE, NS>(ss.st, lc, row, lane0, ACC, E);
         const bool wr = (unsigned)(ss.rd_hi - (n0 + j)) < (unsigned)ss.wr_len;   // did the other side store this record?
-        if (B200CTC_ABLATE != 5) posterior_frame<SIDE, NS>(ss, wr ? blk : zero_blk, plane, post, store && B200CTC_ABLATE != 6);
+        if (B200CTC_ABLATE != 5) posterior_frame<SIDE, NS>(ss, wr ? blk : zero_blk, plane, post);
         row += row_bytes;
         post += post_bytes;
         blk += c.FB;

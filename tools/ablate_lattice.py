@@ -2,7 +2,7 @@
 results are WRONG in those builds, only the timing is of interest).  Build the variants on the CPU box
 (`--build`), run on the GPU box (no arguments).
   1 no phase-1 scratch stores   2 constant emissions (no gathers)   3 no renormalisation (no max tree)
-  4 no neighbour shuffles       5 no posterior at all               6 posterior without shared-memory stores
+  4 no neighbour shuffles       5 no posterior at all
   8 phase 1 runs the recursion twice per frame (independent duplicate): latency- or throughput-bound?
 """
 import json
@@ -14,7 +14,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 from pytorch_end2end_speech_recognition_b200 import build as b  # noqa: E402
 
-VARIANTS = [int(a) for a in os.environ.get('ABLATE_VARIANTS', '0,2,5,6,8').split(',')]
+VARIANTS = [int(a) for a in os.environ.get('ABLATE_VARIANTS', '0,2,5,8').split(',')]
 
 
 def lib_of(n):
