@@ -38,6 +38,18 @@ def parse():
     return ap.parse_args()
 
 
+def measured_traffic(workload_key):
+    """DRAM bytes per lattice launch from the committed ncu capture (profiles/r01_traffic.json, C3 only)."""
+    if workload_key != "C3":
+        return None
+    try:
+        with open(os.path.join(ROOT, "profiles", "r01_traffic.json")) as f:
+            k = json.load(f)["lattice_kernel"]
+        return int(k["dram_bytes_read"]) + int(k["dram_bytes_write"])
+    except Exception:
+        return None
+
+
 def peaks():
     try:
         with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
@@ -254,7 +266,7 @@ def main():
     lattice_gbs = lattice_bytes / (k_ms[1] * 1e-3) / 1e9 if k_ms[1] > 0 else 0.0
     roofline = {"bound": "hbm", "kernel": "lattice (alpha/beta recursion + occupancy update)",
                 "achieved": lattice_gbs, "peak": peak, "peak_kind": peak_kind + " hbm copy GB/s", "unit": "GB/s",
-                "frac": lattice_gbs / peak, "traffic": None,
+                "frac": lattice_gbs / peak, "traffic": measured_traffic(args.workload),
                 "kernel_ms": {"softmax_rows": k_ms[0], "lattice_and_cost_sum": k_ms[1]},
                 "algorithmic_bytes_per_launch": lattice_bytes,
                 "whole_step": {"algorithmic_bytes": total_bytes, "strict_dram_bytes": strict_bytes,

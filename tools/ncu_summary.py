@@ -1,7 +1,7 @@
 """Summarise an ncu report (.ncu-rep) on a box without a GPU: headline metrics of the first kernel in
 the report and the source lines where the warp-stall samples concentrate.
 
-  python tools/ncu_summary.py gpurun_out/prof.ncu-rep [n_lines] > profiles/rNN_<kernel>_ncu_summary.txt
+  python tools/ncu_summary.py gpurun_out/prof.ncu-rep [n_lines] [kernel-name-regex] > profiles/rNN_<kernel>_ncu_summary.txt
 """
 import csv
 import io
@@ -19,13 +19,18 @@ RAW = [
 ]
 
 
+KERNEL = []
+
+
 def run(args):
-    return subprocess.run(["ncu", "-i"] + args, capture_output=True, text=True).stdout
+    return subprocess.run(["ncu", "-i"] + args + KERNEL, capture_output=True, text=True).stdout
 
 
 def main():
     rep = sys.argv[1]
     n_lines = int(sys.argv[2]) if len(sys.argv) > 2 else 25
+    if len(sys.argv) > 3:
+        KERNEL.extend(["--kernel-name", "regex:" + sys.argv[3]])
     raw = list(csv.reader(io.StringIO(run([rep, "--page", "raw", "--csv"]))))
     if len(raw) >= 3:
         names, units, vals = raw[0], raw[1], raw[2]
