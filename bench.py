@@ -65,6 +65,7 @@ class ClockSampler(threading.Thread):
         super().__init__(daemon=True)
         self.index = index
         self.stop_flag = threading.Event()
+        self.active = threading.Event()          # set while the timed region runs: only those samples count
         self.sm, self.reasons, self.sm_max = [], set(), None
 
     def run(self):
@@ -80,15 +81,16 @@ class ClockSampler(threading.Thread):
                 getattr(pynvml, "nvmlClocksThrottleReasonSwPowerCap", 0x4): "sw_power_cap",
             }
             while not self.stop_flag.is_set():
-                self.sm.append(pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM))
-                try:
-                    r = pynvml.nvmlDeviceGetCurrentClocksThrottleReasons(h)
-                    for bit, name in names.items():
-                        if r & bit:
-                            self.reasons.add(name)
-                except Exception:
-                    pass
-                time.sleep(0.02)
+                if self.active.is_set():
+                    self.sm.append(pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM))
+                    try:
+                        r = pynvml.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+                        for bit, name in names.items():
+                            if r & bit:
+                                self.reasons.add(name)
+                    except Exception:
+                        pass
+                time.sleep(0.001)
         except Exception:
             self._smi()
 
@@ -98,6 +100,9 @@ class ClockSampler(threading.Thread):
              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         while not self.stop_flag.is_set():
+            if not self.active.is_set():
+                time.sleep(0.001)
+                continue
             try:
                 out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q,
                                       "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
@@ -248,7 +253,14 @@ def main():
         step(i)
     sampler = ClockSampler(local_rank)
     sampler.start()
+    time.sleep(0.05)                          # NVML is initialised before the timed region starts
+    sampler.active.set()
     ms = timed(step, args.steps)
+    sampler.active.clear()
+    if not sampler.sm:                        # a very short timed region: sample under the same load right after it
+        sampler.active.set()
+        timed(step, max(args.steps, 200))
+        sampler.active.clear()
     clocks = sampler.result()
     ms_per_step = ms / args.steps
     value = frames * world / (ms_per_step * 1e-3)
@@ -275,26 +287,51 @@ def main():
                                "frac_of_8000": total_bytes / (ms_per_step * 1e-3) / 1e9 / 8000.0}}
 
     # ---- end to end: host buffers, H2D of the step's inputs and D2H of the loss inside the timed region ----
+    # Double-buffered input pipeline (what a training loop with a prefetching data loader does): while
+    # step i computes, the logits of step i+1 travel host -> device on a copy stream.  Every step still
+    # pays its own H2D copy of the pinned logits and its own D2H read of the loss inside the timed loop.
     pinned = [a.pin_memory() for a in acts_host]
     stage = [torch.empty_like(a) for a in acts_dev[:2]]
     h2d = acts_bytes + wl.labels.nbytes + wl.act_lens.nbytes + wl.label_lens.nbytes
     e2e_loss = []
+    copy_stream = torch.cuda.Stream(device=dev)
+    copied = [torch.cuda.Event(), torch.cuda.Event()]
+    consumed = [torch.cuda.Event(), torch.cuda.Event()]
+    compute_stream = torch.cuda.current_stream(dev)
+
+    def issue_copy(i):
+        d = i % 2
+        with torch.cuda.stream(copy_stream):
+            copy_stream.wait_event(consumed[d])                          # the step that last read stage[d] is done
+            stage[d].copy_(pinned[i % n_rot], non_blocking=True)          # H2D of step i's logits
+            copied[d].record(copy_stream)
 
     def e2e_step(i):
-        j = i % n_rot
-        d = stage[i % 2]
-        d.copy_(pinned[j], non_blocking=True)                      # H2D of this step's logits
-        b200.ctc_loss_and_grad(d, wl.labels, wl.act_lens, wl.label_lens, grads=grads_dev[j], costs=costs,
-                               loss_sum=loss)                       # labels/lens go host -> device inside the call
+        d = i % 2
+        compute_stream.wait_event(copied[d])
+        b200.ctc_loss_and_grad(stage[d], wl.labels, wl.act_lens, wl.label_lens, grads=grads_dev[i % n_rot],
+                               costs=costs, loss_sum=loss)              # labels/lens go host -> device inside the call
+        consumed[d].record(compute_stream)
+        issue_copy(i + 1)                                               # next step's logits travel while this one computes
         if world > 1:
             dist.all_reduce(loss)
-        e2e_loss.append(float(loss.cpu()[0]))                       # D2H read of the step's result
+        e2e_loss.append(float(loss.cpu()[0]))                           # D2H read of the step's result
 
-    for i in range(3):
-        e2e_step(i)
-    e2e_ms = timed(e2e_step, args.steps) / args.steps
+    def e2e_run(steps, first):
+        # `first`..`first+steps-1`; the copy of step `first` is issued here, inside the timed region
+        issue_copy(first)
+        for i in range(first, first + steps):
+            e2e_step(i)
+        copy_stream.synchronize()
+
+    for d in (0, 1):
+        consumed[d].record(compute_stream)
+    e2e_run(3, 0)
+    torch.cuda.synchronize()
+    e2e_ms = timed(lambda i: e2e_run(args.steps, 4) if i == 0 else None, 1) / args.steps
     e2e = {"value": frames * world / (e2e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": int(h2d),
-           "d2h_bytes_per_step": 4, "ms_per_step": e2e_ms}
+           "d2h_bytes_per_step": 4, "ms_per_step": e2e_ms,
+           "pipeline": "double-buffered: H2D of step i+1 overlaps the kernels of step i (one extra prefetch copy per run is also inside the timed region)"}
 
     out = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
