@@ -41,15 +41,15 @@ __global__ void __launch_bounds__(256) softmax_rows_warp_kernel(CallParams p) {
   constexpr int RPW = 32 / LPR;                       // rows per warp
   const int lane = threadIdx.x & 31;
   const int q = lane & (LPR - 1), sub = lane / LPR;
-  const long long n_rows = (long long)p.T * p.B;
-  long long row = ((long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * RPW + sub;
-  const bool row_ok = row < n_rows;
-  if (!row_ok) row = n_rows - 1;                      // keep the lane in the shuffles; it stores nothing
-  const int t = (int)(row / p.B);
-  const int b = (int)(row - (long long)t * p.B);
-  const UttMeta m = p.meta[b];
+  // grid: x over the mini-batch (RPW rows per warp, 8 warps per CTA), y = frame: no index division
+  const int t = blockIdx.y;
+  int b = (blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * RPW + sub;
+  const bool row_ok = b < p.B;
+  if (!row_ok) b = p.B - 1;                           // keep the lane in the shuffles; it stores nothing
+  const long long row = (long long)t * p.B + b;
+  const int m_T = p.meta[b].T, m_feasible = p.meta[b].feasible;
   float* grow = (p.grads && row_ok) ? p.grads + row * p.V : nullptr;
-  const bool live = t < m.T && m.feasible;
+  const bool live = t < m_T && m_feasible;
   const float* arow = p.acts + (long long)t * p.as_t + (long long)b * p.as_b;
   float x[NV];
   float mx = -INFINITY;
@@ -89,6 +89,7 @@ __global__ void __launch_bounds__(256) softmax_rows_warp_kernel(CallParams p) {
   }
   if (p.gathered) {
     // label-indexed emissions, taken from the register-resident row by shuffle (all lanes take part)
+    const UttMeta m = p.meta[b];
     float* erow = p.em + m.em_off + (long long)t * m.W;
     const int* lab = p.labels + m.lab_off;
     const bool wr = live && row_ok;
@@ -244,9 +245,10 @@ cudaError_t launch_softmax_rows(const CallParams& p, cudaStream_t stream) {
   if (n_rows == 0) return cudaSuccess;
   if (p.V <= 256) {
     const int warps = 8;
+    if (p.T > 65535) return cudaErrorInvalidConfiguration;
     auto grid_for = [&](int rows_per_warp) {
-      const long long per_cta = (long long)warps * rows_per_warp;
-      return (unsigned)((n_rows + per_cta - 1) / per_cta);
+      const int per_cta = warps * rows_per_warp;
+      return dim3((unsigned)((p.B + per_cta - 1) / per_cta), (unsigned)p.T, 1);
     };
     if (p.V <= 32) softmax_rows_warp_kernel<8, 4><<<grid_for(4), warps * 32, 0, stream>>>(p);
     else if (p.V <= 64) softmax_rows_warp_kernel<16, 4><<<grid_for(2), warps * 32, 0, stream>>>(p);
