@@ -4,6 +4,7 @@ results are WRONG in those builds, only the timing is of interest).  Build the v
   1 no phase-1 scratch stores   2 constant emissions (no gathers)   3 no renormalisation (no max tree)
   4 no neighbour shuffles       5 no posterior at all
   8 phase 1 runs the recursion twice per frame (independent duplicate): latency- or throughput-bound?
+  9 the helper warps skip the per-symbol reduction (how much does their work slow the lattice warps?)
 """
 import json
 import os
