@@ -219,14 +219,31 @@ def main():
     grads_dev = [torch.empty_like(a) for a in acts_dev]
     costs = torch.empty(wl.B, device=dev)
     loss = torch.empty(1, device=dev)
+    # N > 1: the scalar loss of step i is all-reduced asynchronously (NCCL's own stream) while step i+1
+    # computes -- a training loop only needs the number for logging.  Four loss buffers rotate; a buffer is
+    # reused only after its all-reduce has completed.
+    loss_ring = [torch.empty(1, device=dev) for _ in range(4)]
+    pending = [None] * 4
 
     def step(i):
         j = i % n_rot
+        if world == 1:
+            b200.ctc_loss_and_grad(acts_dev[j], wl.labels, wl.act_lens, wl.label_lens, grads=grads_dev[j],
+                                   costs=costs, loss_sum=loss)
+            return loss
+        k = i % 4
+        if pending[k] is not None:
+            pending[k].wait()
         b200.ctc_loss_and_grad(acts_dev[j], wl.labels, wl.act_lens, wl.label_lens, grads=grads_dev[j],
-                               costs=costs, loss_sum=loss)
-        if world > 1:
-            dist.all_reduce(loss)        # the one exchange step of the path: the scalar loss
-        return loss
+                               costs=costs, loss_sum=loss_ring[k])
+        pending[k] = dist.all_reduce(loss_ring[k], async_op=True)   # the one exchange step of the path: the scalar loss
+        return loss_ring[k]
+
+    def drain():
+        for k in range(4):
+            if pending[k] is not None:
+                pending[k].wait()
+                pending[k] = None
 
     def barrier():
         torch.cuda.synchronize()
@@ -240,6 +257,7 @@ def main():
         ev0.record()
         for i in range(steps):
             fn(i)
+        drain()                          # every all-reduce issued in the timed region completes inside it
         ev1.record()
         barrier()
         ms = ev0.elapsed_time(ev1)
@@ -314,7 +332,7 @@ def main():
         consumed[d].record(compute_stream)
         issue_copy(i + 1)                                               # next step's logits travel while this one computes
         if world > 1:
-            dist.all_reduce(loss)
+            dist.all_reduce(loss)                                       # the result is read on the host right away: synchronous
         e2e_loss.append(float(loss.cpu()[0]))                           # D2H read of the step's result
 
     def e2e_run(steps, first):

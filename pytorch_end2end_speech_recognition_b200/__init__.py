@@ -2,7 +2,8 @@
 carolinebear/pytorch_end2end_speech_recognition."""
 
 from ._lib import B200CTCError  # noqa: F401
-from .ctc import CTCLoss, _CTC, cpu_ctc, ctc_loss, ctc_loss_and_grad, gpu_ctc, workspace_bytes  # noqa: F401
+from .ctc import (CTCLoss, _CTC, concatenate_labels, cpu_ctc, ctc_loss, ctc_loss_and_grad,  # noqa: F401
+                  ctc_loss_from_padded, gpu_ctc, workspace_bytes)
 from .decode import GreedyDecoder, greedy_decode  # noqa: F401
 from .shard import allreduce_loss, balance_shards, shard_batch, sharded_ctc_loss  # noqa: F401
 

@@ -262,3 +262,41 @@ def ctc_loss(acts, labels, act_lens, label_lens, blank=0, reduction="sum"):
     if reduction not in ("sum", "mean", "none"):
         raise B200CTCError("reduction must be 'sum', 'mean' or 'none'")
     return _CTCDevice.apply(acts, labels, act_lens, label_lens, blank, reduction)
+
+
+# ------------------------------------------------------------------------------------------------
+# call-site helpers: what CTC.forward does around the op, without the python loop,
+# the transpose copy and the host round trips
+# ------------------------------------------------------------------------------------------------
+
+def concatenate_labels(ys, y_lens):
+    """Vectorised ``_concatenate_labels`` (reference: models/pytorch_v3/ctc/ctc.py:532-549, a python loop
+    over the mini-batch): padded ``ys[B, Lmax]`` + ``y_lens[B]`` -> flat int32 ``[sum(y_lens)]`` on the host."""
+    ys = ys.detach().cpu().numpy() if isinstance(ys, torch.Tensor) else np.asarray(ys)
+    y_lens = _host_i32(y_lens, "y_lens")
+    if ys.ndim != 2 or ys.shape[0] != len(y_lens):
+        raise B200CTCError("ys must be [B, Lmax] with one length per row")
+    if len(y_lens) and int(y_lens.max(initial=0)) > ys.shape[1]:
+        raise B200CTCError("y_lens exceeds the padded label width")
+    mask = np.arange(ys.shape[1])[None, :] < y_lens[:, None]
+    return np.ascontiguousarray(ys[mask], dtype=np.int32)
+
+
+def ctc_loss_from_padded(logits, ys, x_lens, y_lens, label_offset=1, logits_temperature=1.0, average=True):
+    """The loss computation of ``CTC.forward`` (reference: ctc.py:299-326) as one call, device resident.
+
+    logits ``[B, T, V]`` CUDA (batch-major, as the encoder returns them; consumed through a strided view,
+    no ``transpose().contiguous()`` copy), ys ``[B, Lmax]`` padded labels WITHOUT the blank offset
+    (``label_offset=1`` reproduces ``ys = ys + 1``, ctc.py:300: index 0 is the blank), x_lens / y_lens ``[B]``.
+    Returns a CUDA scalar tensor: ``sum_b cost_b / B`` (``average=True`` is the reference's ``/ len(xs)``,
+    ctc.py:323) that back-propagates into ``logits``.
+    """
+    if logits.dim() != 3:
+        raise B200CTCError("logits must be [B, T, V]")
+    if logits_temperature != 1:
+        logits = logits / logits_temperature              # "output smoothing", ctc.py:306-307
+    labels = concatenate_labels(ys, y_lens)
+    if label_offset:
+        labels = labels + np.int32(label_offset)
+    loss = ctc_loss(logits.transpose(0, 1), labels, x_lens, y_lens, blank=0, reduction="sum")
+    return loss / logits.size(0) if average else loss

@@ -114,3 +114,22 @@ def test_invalid_inputs_raise_runtime_error():
     # and the engine still works afterwards
     c, _, _ = b200.ctc_loss_and_grad(a, *good)
     assert torch.isfinite(c).all()
+
+
+def test_ctc_loss_from_padded_matches_the_reference_call_site():
+    """ctc.py:299-326: ys + 1, concatenate, time-major view, sum of costs / len(xs); gradient w.r.t. logits."""
+    rng = np.random.RandomState(21)
+    B, T, V, Lmax = 5, 40, 11, 9
+    logits = torch.randn(B, T, V, device="cuda", requires_grad=True)
+    y_lens = rng.randint(1, Lmax + 1, size=B).astype(np.int32)
+    ys = np.zeros((B, Lmax), dtype=np.int64)
+    for b in range(B):
+        ys[b, :y_lens[b]] = rng.randint(0, V - 1, size=y_lens[b])      # 0-based, blank offset not applied yet
+    x_lens = np.array([40, 38, 33, 30, 25], dtype=np.int32)
+    loss = b200.ctc_loss_from_padded(logits, ys, x_lens, y_lens)
+    loss.backward()
+    flat = np.concatenate([ys[b, :y_lens[b]] + 1 for b in range(B)]).astype(np.int32)
+    acts = logits.detach().cpu().numpy().transpose(1, 0, 2)
+    c_ref, g_ref = ctc_ref.ctc_cost_and_grad(acts, flat, x_lens, y_lens)
+    assert abs(float(loss) - c_ref.sum() / B) < 1e-5 * c_ref.sum()
+    assert np.max(np.abs(logits.grad.cpu().numpy().transpose(1, 0, 2) - g_ref / B)) < 1e-4

@@ -106,3 +106,20 @@ def test_workloads_are_feasible_and_seeded(key):
     total, strict, frames = workloads.algorithmic_bytes(wl)
     assert total > strict > 0 and frames == int(wl.act_lens.sum())
     assert np.all(np.diff(wl.act_lens) <= 0)
+
+
+def test_concatenate_labels_matches_the_reference_loop():
+    """Same result as the python loop of models/pytorch_v3/ctc/ctc.py:544-547 (restated inline)."""
+    import pytorch_end2end_speech_recognition_b200 as b200
+    rng = np.random.RandomState(3)
+    ys = rng.randint(0, 50, size=(7, 12))
+    y_lens = np.array([12, 0, 5, 1, 12, 7, 3], dtype=np.int32)
+    expect = []
+    for b in range(7):
+        expect.extend(ys[b][:y_lens[b]])
+    out = b200.concatenate_labels(ys, y_lens)
+    assert out.dtype == np.int32 and out.tolist() == expect
+    import torch
+    assert b200.concatenate_labels(torch.tensor(ys), torch.tensor(y_lens)).tolist() == expect
+    with pytest.raises(b200.B200CTCError):
+        b200.concatenate_labels(ys, np.array([13, 0, 0, 0, 0, 0, 0]))
