@@ -107,16 +107,19 @@ __device__ __forceinline__ void mbar_init(unsigned long long* bar, int count) {
 __device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, unsigned bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
 }
-__device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned parity) {
-  asm volatile(
-      "{\n"
-      ".reg .pred p;\n"
-      "WAIT_%=:\n"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
-      "@p bra DONE_%=;\n"
-      "bra WAIT_%=;\n"
-      "DONE_%=:\n"
-      "}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+// Bounded wait (a bulk copy that never completes must not hang the GPU): false after ~2^22 polls.
+__device__ __forceinline__ bool mbar_wait(unsigned long long* bar, unsigned parity) {
+  for (int it = 0; it < (1 << 22); ++it) {
+    unsigned done;
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}\n" : "=r"(done) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+    if (done) return true;
+  }
+  return false;
 }
 __device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gmem_src, unsigned bytes, unsigned long long* bar) {
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
@@ -1017,7 +1020,7 @@ __device__ void fast_side_helper(const CallParams& p, int b, const UttMeta& m, c
   if (pl.nc2 == 0) return;
   if (M_side + hj < T) {                             // records of the first phase-2 chunk
     prefetch_other<SIDE>(c, hj, M_side + hj, mbar);
-    mbar_wait(mbar, mphase);
+    if (!mbar_wait(mbar, mphase) && lane == 0) *cm.abort_flag = 1;   // never observed; the safe lattice would redo the utterance
     mphase ^= 1;
   }
   named_bar_sync(bar_chunk(SIDE), nbar);
@@ -1056,7 +1059,7 @@ __device__ void fast_side_helper(const CallParams& p, int b, const UttMeta& m, c
     B200CTC_TRACE_EVENT(tc, 9);
     cp_async_wait<1>();
     if (copying) {
-      mbar_wait(mbar, mphase);
+      if (!mbar_wait(mbar, mphase) && lane == 0) *cm.abort_flag = 1;
       mphase ^= 1;
     }
     named_bar_sync(bar_chunk(SIDE), nbar);
