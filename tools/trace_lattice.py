@@ -16,7 +16,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 from pytorch_end2end_speech_recognition_b200 import build as b  # noqa: E402
 
-LIB = os.path.join(b.LIB_DIR, "libb200ctc_trace.so")
+LIB = os.environ.get("B200CTC_TRACE_LIB") or os.path.join(b.LIB_DIR, "libb200ctc_trace.so")
 
 
 def main():
