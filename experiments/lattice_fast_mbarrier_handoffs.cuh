@@ -73,6 +73,11 @@ constexpr int kEZero = -(1 << 28);  // exponent of an all-zero lane
 constexpr int kRowsRing = 4;        // emission-row chunks in the ring: the reducers' one, this chunk, the next one (landed), the one after (in flight)
 constexpr int kOthRing = 8;         // per-thread ring of the opposite side's records: two chunks of K = 4 frames
 constexpr int kReducers = 4;        // reducer warps per side: warp j takes frame j of every phase-2 chunk (== K)
+constexpr int kHaloRing = 4;        // halo slots per lattice warp: a producer is never four chunks ahead of its reader
+// mbarriers of one side (FastSideSmem::mbar): chunk hand-offs without a CTA-wide barrier
+constexpr int kMbarReady = 0;       // [2] helpers -> lattice warps: rows staged, records landed, posterior buffer free (chunk & 1)
+constexpr int kMbarDone = 2;        // [2] lattice warps -> helpers: the chunk's frames are computed (chunk & 1)
+constexpr int kMbarHalo = 4;        // [kHaloRing][NWMAX] lattice warp w -> w+1: halo of the chunk published (chunk & 3)
 
 // ---------------------------------------------------------------------------------------------
 // PTX helpers
@@ -104,21 +109,35 @@ __device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)_
 __device__ __forceinline__ void mbar_init(unsigned long long* bar, int count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
 }
+// transaction bytes of a bulk copy about to be issued, WITHOUT the arrival (that comes with mbar_arrive)
 __device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, unsigned bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+  asm volatile("mbarrier.expect_tx.relaxed.cta.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
 }
-// Bounded wait (a bulk copy that never completes must not hang the GPU): false after ~2^22 polls.
-__device__ __forceinline__ bool mbar_wait(unsigned long long* bar, unsigned parity) {
-  for (int it = 0; it < (1 << 22); ++it) {
-    unsigned done;
-    asm volatile(
-        "{\n"
-        ".reg .pred p;\n"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
-        "selp.u32 %0, 1, 0, p;\n"
-        "}\n" : "=r"(done) : "r"(smem_u32(bar)), "r"(parity) : "memory");
-    if (done) return true;
+__device__ __forceinline__ void mbar_arrive(unsigned long long* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(unsigned long long* bar, unsigned parity) {
+  unsigned done;
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+      "selp.u32 %0, 1, 0, p;\n"
+      "}\n" : "=r"(done) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+  return done != 0;
+}
+// Abort word of the utterance: kAbortRedo = the fast result cannot be trusted (the hand-offs keep working),
+// kAbortSync = a hand-off timed out (every later wait gives up at once; never observed).
+constexpr int kAbortRedo = 1, kAbortSync = 2;
+// Bounded wait: a hand-off that never completes must not hang the GPU.  After ~2^18 polls the wait sets
+// kAbortSync and returns false; the safe lattice then redoes the utterance.
+__device__ __forceinline__ bool mbar_wait(unsigned long long* bar, unsigned parity, volatile int* abort_flag) {
+  if (mbar_try_wait(bar, parity)) return true;
+  for (int it = 0; it < (1 << 18); ++it) {
+    if (mbar_try_wait(bar, parity)) return true;
+    if ((it & 63) == 63 && (*abort_flag & kAbortSync)) return false;
   }
+  atomicOr(const_cast<int*>(abort_flag), kAbortSync);
   return false;
 }
 __device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gmem_src, unsigned bytes, unsigned long long* bar) {
@@ -212,12 +231,12 @@ struct FastSideSmem {
   float* rows;      // [kRowsRing][K][RWS]     staged emission rows (+ a zero slot at index RW)
   unsigned char* oth;   // [2][K] frame blocks   the opposite side's stored records, two chunks (+ one all-zero block)
   float* post;      // [2][K][PS]              symbol-sorted label posteriors + blank partials + dump slot
-  float4* halo_m;   // [2][NWMAX][HL][NS/4]    halo lanes
-  int* halo_e;      // [2][NWMAX][HL]
+  float4* halo_m;   // [kHaloRing][NWMAX][HL][NS/4]    halo lanes
+  int* halo_e;      // [kHaloRing][NWMAX][HL]
   float* red_m;     // [NWMAX]
   int* red_e;       // [NWMAX]
   float* rowsum;    // [kReducers][Rmax+4]     reducer scratch (symbols spanning several rows)
-  unsigned long long* mbar;   // [kReducers]   one mbarrier per helper warp (TMA bulk copies of the records)
+  unsigned long long* mbar;   // [kMbarHalo + kHaloRing * NWMAX]   chunk hand-offs (kMbarReady / kMbarDone / kMbarHalo)
 };
 
 template <int NWMAX>
@@ -231,13 +250,13 @@ __host__ __device__ inline size_t fast_side_bytes(int L, int RW, int V) {
   constexpr int HL = 2 * K / NS;
   size_t b = 0;
   b += (size_t)(2 * K + 1) * frame_block_bytes<NS>(L);       // oth (+ the zero block)
-  b += (size_t)2 * NWMAX * HL * (NS / 4) * 16;               // halo_m
+  b += (size_t)kHaloRing * NWMAX * HL * (NS / 4) * 16;       // halo_m
   b += (size_t)kRowsRing * K * (size_t)(RW + 4) * 4;         // rows
   b += 2 * (size_t)K * post_stride<NWMAX>(L, V) * 4;         // post
-  b += (size_t)2 * NWMAX * HL * 4;                           // halo_e
+  b += (size_t)kHaloRing * NWMAX * HL * 4;                   // halo_e
   b += NWMAX * 8;                                            // red
   b += (size_t)kReducers * (post_rows_max(L, V) + 4) * 4;    // rowsum (one per reducer warp)
-  b += (size_t)kReducers * 8 + 8;                            // mbar
+  b += (size_t)(kMbarHalo + kHaloRing * NWMAX) * 8 + 8;      // mbar
   return (b + 15) / 16 * 16;
 }
 template <int K, int NWMAX, int NS>
@@ -255,10 +274,10 @@ __device__ __forceinline__ FastSideSmem carve_fast_side(unsigned char* base, int
   FastSideSmem s;
   unsigned char* p = base;
   s.oth = p;                               p += (size_t)(2 * K + 1) * frame_block_bytes<NS>(L);
-  s.halo_m = reinterpret_cast<float4*>(p); p += (size_t)2 * NWMAX * HL * (NS / 4) * 16;
+  s.halo_m = reinterpret_cast<float4*>(p); p += (size_t)kHaloRing * NWMAX * HL * (NS / 4) * 16;
   s.rows = reinterpret_cast<float*>(p);    p += (size_t)kRowsRing * K * (size_t)(RW + 4) * 4;
   s.post = reinterpret_cast<float*>(p);    p += 2 * (size_t)K * post_stride<NWMAX>(L, V) * 4;
-  s.halo_e = reinterpret_cast<int*>(p);    p += (size_t)2 * NWMAX * HL * 4;
+  s.halo_e = reinterpret_cast<int*>(p);    p += (size_t)kHaloRing * NWMAX * HL * 4;
   s.red_m = reinterpret_cast<float*>(p);   p += NWMAX * 4;
   s.red_e = reinterpret_cast<int*>(p);     p += NWMAX * 4;
   s.rowsum = reinterpret_cast<float*>(p);  p += (size_t)kReducers * (post_rows_max(L, V) + 4) * 4;
@@ -428,13 +447,13 @@ struct SweepState {
 constexpr int kLostBound = 127 + 110 - 24 - 2;   // maxbound above this: FLAG_PRECISION_LOST
 
 // Helper warp: prefetch the opposite side's frame block of step n into slot `slot` (= buffer * K + frame)
-// of the record ring with ONE TMA bulk copy.  Records the other side never wrote (its warp skipped the
+// of the record ring with ONE TMA bulk copy that completes on the chunk's "ready" mbarrier.  Records the other side never wrote (its warp skipped the
 // chunk: out of the band) arrive as garbage; the lattice lanes know which of their records exist
 // (SweepState::rd_hi / wr_len) and read the all-zero block instead.
 template <int SIDE>
 __device__ __forceinline__ void prefetch_other(const FastCtx<SIDE>& c, int slot, int n, unsigned long long* mbar) {
   if (c.lane == 0) {
-    mbar_expect_tx(mbar, (unsigned)c.FB);
+    mbar_expect_tx(mbar, (unsigned)c.FB);          // the arrival follows in publish (fast_side_helper)
     bulk_g2s(c.sm.oth + (size_t)slot * c.FB, c.scr + (size_t)c.frame_of(n) * c.FB, (unsigned)c.FB, mbar);
   }
 }
@@ -588,39 +607,56 @@ __device__ __forceinline__ void run_chunk(const FastCtx<SIDE>& c, SweepState<NS>
   }
 }
 
-// Chunk boundary of the lattice warps: publish the halo lanes, ONE barrier with the side's lattice and
-// helper warps (after it the helpers' prefetch for the next chunk has landed and the posterior buffer
-// of the previous chunk is consumed), import the halo.
+// Chunk hand-offs of the lattice warps.  No CTA-wide barrier inside the sweeps: every warp runs freely and
+// meets the others only through mbarriers --
+//   enter(cc): wait until the helpers declared chunk cc ready (emission rows staged, the other side's records
+//              landed, the posterior buffer reduced and free), then wait for and import the halo the lower
+//              neighbour window published after its chunk cc-1;
+//   leave(cc): publish this window's halo lanes for the upper neighbour, tell the helpers the chunk is done.
+// A warp is never more than two chunks ahead of the slowest warp of its side ("ready" of chunk cc needs
+// "done" of chunk cc-2 from all of them), so a ring of kHaloRing = 4 halo slots is never overrun.
 template <int K, int NWMAX, int SIDE, int NS>
-__device__ __forceinline__ void chunk_boundary(const FastCtx<SIDE>& c, SweepState<NS>& ss, int cc, int* abort_flag, int& tc) {
+__device__ __forceinline__ void chunk_enter(const FastCtx<SIDE>& c, SweepState<NS>& ss, int cc, int* abort_flag, int& tc) {
   constexpr int NH = NS / 4, HL = 2 * K / NS;
   static_assert(HL * NS == 2 * K && HL >= 1, "the halo must be whole lanes");
-  const int hb = cc & 1, NW = c.NW, w = c.w, lane = c.lane;
+  const int w = c.w, lane = c.lane;
   LaneState<NS>& st = ss.st;
+  B200CTC_TRACE_EVENT(tc, 30);
+  mbar_wait(c.sm.mbar + kMbarReady + (cc & 1), (cc >> 1) & 1, abort_flag);
+  if (w > 0 && cc > 0) {
+    const int hs = (cc - 1) & (kHaloRing - 1);
+    mbar_wait(c.sm.mbar + kMbarHalo + hs * NWMAX + (w - 1), ((cc - 1) / kHaloRing) & 1, abort_flag);
+    if (lane < HL) {
+      const int slot = (hs * NWMAX + (w - 1)) * HL + lane;
+#pragma unroll
+      for (int h = 0; h < NH; ++h) {
+        const float4 hv = c.sm.halo_m[slot * NH + h];
+        st.A[2 * h] = f2_pack(hv.x, hv.y);
+        st.A[2 * h + 1] = f2_pack(hv.z, hv.w);
+      }
+      st.e = c.sm.halo_e[slot];
+    }
+  }
+  B200CTC_TRACE_EVENT(tc, 31);
+}
+
+template <int K, int NWMAX, int SIDE, int NS>
+__device__ __forceinline__ void chunk_leave(const FastCtx<SIDE>& c, SweepState<NS>& ss, int cc, int* abort_flag) {
+  constexpr int NH = NS / 4, HL = 2 * K / NS;
+  const int NW = c.NW, w = c.w, lane = c.lane;
+  const LaneState<NS>& st = ss.st;
+  const int hs = cc & (kHaloRing - 1);
   if (w + 1 < NW && lane >= 32 - HL) {
-    const int slot = (hb * NWMAX + w) * HL + (lane - (32 - HL));
+    const int slot = (hs * NWMAX + w) * HL + (lane - (32 - HL));
 #pragma unroll
     for (int h = 0; h < NH; ++h)
       c.sm.halo_m[slot * NH + h] = make_float4(f2_lo(st.A[2 * h]), f2_hi(st.A[2 * h]), f2_lo(st.A[2 * h + 1]), f2_hi(st.A[2 * h + 1]));
     c.sm.halo_e[slot] = st.e;
   }
-  if (ss.lc.owned && ss.maxbound > kLostBound) *abort_flag = 1;
-  B200CTC_TRACE_EVENT(tc, 30);
-#if B200CTC_ABLATE == 7
-  if ((cc & 7) == 7)
-#endif
-  named_bar_sync(bar_chunk(SIDE), (NW + kReducers) * 32);
-  B200CTC_TRACE_EVENT(tc, 31);
-  if (w > 0 && lane < HL) {
-    const int slot = (hb * NWMAX + (w - 1)) * HL + lane;
-#pragma unroll
-    for (int h = 0; h < NH; ++h) {
-      const float4 hv = c.sm.halo_m[slot * NH + h];
-      st.A[2 * h] = f2_pack(hv.x, hv.y);
-      st.A[2 * h + 1] = f2_pack(hv.z, hv.w);
-    }
-    st.e = c.sm.halo_e[slot];
-  }
+  if (ss.lc.owned && ss.maxbound > kLostBound) atomicOr(abort_flag, kAbortRedo);
+  __syncwarp();                                   // the lanes' shared-memory writes of this chunk precede the arrivals
+  if (lane == 31 && w + 1 < NW) mbar_arrive(c.sm.mbar + kMbarHalo + hs * NWMAX + w);
+  if (lane == 0) mbar_arrive(c.sm.mbar + kMbarDone + (cc & 1));
 }
 
 // Total probability from the per-warp partial sums (every thread of the side, reducers included,
@@ -804,16 +840,17 @@ __device__ void fast_side_sweep(const CallParams& p, int b, const UttMeta& m, co
   // side's records) was fetched by the helper warps during the previous chunk.
   int rs = 0;
   B200CTC_TRACE_EVENT(tc, 1);
-  named_bar_sync(bar_chunk(SIDE), (NW + kReducers) * 32);       // rows of chunk 0 staged, wr_tab visible
+  named_bar_sync(bar_chunk(SIDE), (NW + kReducers) * 32);       // the zero slots and the zero block are visible
 
   // ================================ phase 1 ================================
   int cc = 0;
   for (int n0 = 0; n0 < M_side; n0 += K, ++cc) {
     const int kc = min(K, M_side - n0);
+    chunk_enter<K, NWMAX, SIDE, NS>(c, ss, cc, abort_flag, tc);
     B200CTC_TRACE_EVENT(tc, 2);
     run_chunk<K, false, SIDE, NT, NS>(c, ss, rs, 0, 0, n0, kc, false);
     B200CTC_TRACE_EVENT(tc, 3);
-    chunk_boundary<K, NWMAX, SIDE, NS>(c, ss, cc, abort_flag, tc);
+    chunk_leave<K, NWMAX, SIDE, NS>(c, ss, cc, abort_flag);
     rs = rs == kRowsRing - 1 ? 0 : rs + 1;
   }
 
@@ -823,7 +860,8 @@ __device__ void fast_side_sweep(const CallParams& p, int b, const UttMeta& m, co
   B200CTC_TRACE_EVENT(tc, 4);
   named_bar_sync(kBarMidpoint, 2 * (NW + kReducers) * 32);
   if (nc2 == 0) return;
-  named_bar_sync(bar_chunk(SIDE), (NW + kReducers) * 32);       // the helpers fetched the records of the first phase-2 chunk
+  chunk_enter<K, NWMAX, SIDE, NS>(c, ss, cc, abort_flag, tc);   // the helpers fetched the records of the first phase-2 chunk
+  const int ob0 = cc & 1;                                       // its record / posterior buffer
 
   // ---- total probability P = sum_s alpha_t(s) beta'_t(s) at the first phase-2 frame (state copy) ----
   {
@@ -836,7 +874,7 @@ __device__ void fast_side_sweep(const CallParams& p, int b, const UttMeta& m, co
       if (lc.owned) {
         // no band masks: outside the band one of the two factors is exactly zero (posterior_frame)
         const bool wr = (unsigned)(ss.rd_hi - n0) < (unsigned)ss.wr_len;
-        const unsigned char* blk = c.sm.oth + (wr ? (size_t)0 : (size_t)2 * K * c.FB);
+        const unsigned char* blk = c.sm.oth + (size_t)(wr ? ob0 : 2) * K * c.FB;
         float sum = 0.f;
 #pragma unroll
         for (int h = 0; h < NH; ++h) {
@@ -857,7 +895,7 @@ __device__ void fast_side_sweep(const CallParams& p, int b, const UttMeta& m, co
     double log2P;
     if (!total_probability(c.sm, NW, ss.inv_mP, ss.eP, log2P)) {
       // zero / underflowed / garbage total probability: the safe lattice decides
-      if (c.tid_side == 0) *abort_flag = 1;
+      if (c.tid_side == 0) atomicOr(abort_flag, kAbortRedo);
       return;                                            // every thread of the side computed the same value
     }
     if (SIDE == 1 && c.tid_side == 0) p.costs[b] = (float)(-log2P * 0.69314718055994530942);
@@ -866,13 +904,13 @@ __device__ void fast_side_sweep(const CallParams& p, int b, const UttMeta& m, co
   const bool write_post = p.grads != nullptr;
 
   // ================================ phase 2 ================================
-  int k2 = 0;
-  for (int n0 = M_side; n0 < T; n0 += K, ++k2, ++cc) {
-    const int kc = min(K, T - n0), par = k2 & 1;
+  for (int n0 = M_side; n0 < T; n0 += K, ++cc) {
+    const int kc = min(K, T - n0), par = cc & 1;
+    if (n0 > M_side) chunk_enter<K, NWMAX, SIDE, NS>(c, ss, cc, abort_flag, tc);
     B200CTC_TRACE_EVENT(tc, 13);
     run_chunk<K, true, SIDE, NT, NS>(c, ss, rs, par, par, n0, kc, write_post);
     B200CTC_TRACE_EVENT(tc, 14);
-    chunk_boundary<K, NWMAX, SIDE, NS>(c, ss, cc, abort_flag, tc);
+    chunk_leave<K, NWMAX, SIDE, NS>(c, ss, cc, abort_flag);
     rs = rs == kRowsRing - 1 ? 0 : rs + 1;
   }
   B200CTC_TRACE_EVENT(tc, 15);
@@ -966,10 +1004,12 @@ __device__ __forceinline__ void reduce_frame(const CallParams& p, const FastComm
   }
 }
 
-// Helper warp hj of the side owns frame hj of every chunk: during chunk c it fetches what that frame
-// of chunk c+1 needs (emission row; in phase 2 the other side's records of all position groups) and,
-// in phase 2, reduces the posteriors the lattice warps produced for its frame of chunk c-1 into the
-// gradient row.  It meets the lattice warps at the one barrier per chunk.
+// Helper warp hj of the side owns frame hj of every chunk.  Iteration j of its loop starts when all lattice
+// warps of the side have finished chunk j ("done"): it requests the other side's records of chunk j+2
+// (phase 2; one TMA bulk copy into the buffer chunk j just released), reduces the posteriors of its frame
+// of chunk j into the gradient row (phase 2), stages the emission row of chunk j+3, and then declares
+// chunk j+2 "ready" -- its rows have landed, its posterior buffer is free, its records complete the same
+// mbarrier by their byte count.  The lattice warps work on chunk j+1 meanwhile.
 template <int K, int NWMAX, int SIDE, int NS>
 __device__ void fast_side_helper(const CallParams& p, int b, const UttMeta& m, const FastCommon& cm,
                                  unsigned char* side_smem, int hj, int lane) {
@@ -981,20 +1021,15 @@ __device__ void fast_side_helper(const CallParams& p, int b, const UttMeta& m, c
   const SidePlan pl = side_plan<K, SIDE>(T);
   const int M_side = pl.M_side;
   const int nbar = (NW + kReducers) * 32;
+  int* abort_flag = cm.abort_flag;
   B200CTC_TRACE_DECL(tc);
 
-  unsigned long long* mbar = c.sm.mbar + hj;
-  unsigned mphase = 0;
-  if (lane == 0) {
-    mbar_init(mbar, 1);
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-  }
-  __syncwarp();
-
-  // Emission rows are staged TWO chunks ahead (ring slot = chunk & 3), so that the global-memory latency
-  // of a row never sits between the lattice warps and the chunk barrier.
+  unsigned long long* ready = c.sm.mbar + kMbarReady;
+  unsigned long long* done = c.sm.mbar + kMbarDone;
   const int nc1 = pl.nc1, n_chunks = pl.n_chunks;
   auto chunk_start = [&](int cc) { return cc < nc1 ? cc * K : M_side + (cc - nc1) * K; };
+  // Emission rows are staged THREE chunks ahead of the chunk the helpers wait for (ring slot = chunk & 3:
+  // the chunk being reduced, the one the lattice warps run, the next one -- landed --, the one in flight).
   auto stage_chunk = [&](int cc) {
     if (cc < n_chunks) {
       const int n = chunk_start(cc) + hj;
@@ -1002,32 +1037,46 @@ __device__ void fast_side_helper(const CallParams& p, int b, const UttMeta& m, c
     }
     cp_async_commit();
   };
+  auto request_records = [&](int cc) {               // phase-2 chunk cc: the other side's frame block of this helper's frame
+    const int n = chunk_start(cc) + hj;
+    if (n < T) prefetch_other<SIDE>(c, (cc & 1) * K + hj, n, ready + (cc & 1));
+  };
+  auto publish = [&](int cc) {                       // this warp's share of "chunk cc is ready"
+    __syncwarp();
+    if (lane == 0) mbar_arrive(ready + (cc & 1));
+  };
   stage_chunk(0);
   stage_chunk(1);
-  cp_async_wait<1>();
+  stage_chunk(2);
+  cp_async_wait<1>();                                // rows of chunks 0 and 1
   named_bar_sync(bar_chunk(SIDE), nbar);
+  if (0 < nc1) publish(0);
+  if (1 < nc1) publish(1);
 
   // ================================ phase 1 ================================
-  int cc = 0;
-  for (; cc < nc1; ++cc) {
-    stage_chunk(cc + 2);
-    cp_async_wait<1>();                       // rows of chunk cc+1 have landed
-    named_bar_sync(bar_chunk(SIDE), nbar);
+  int j = 0;
+  for (; j < nc1; ++j) {
+    mbar_wait(done + (j & 1), (j >> 1) & 1, abort_flag);
+    stage_chunk(j + 3);
+    cp_async_wait<1>();                              // rows of chunk j+2 have landed
+    if (j + 2 < nc1) publish(j + 2);
   }
 
   // ================================ midpoint ================================
   named_bar_sync(kBarMidpoint, 2 * nbar);
   if (pl.nc2 == 0) return;
-  if (M_side + hj < T) {                             // records of the first phase-2 chunk
-    prefetch_other<SIDE>(c, hj, M_side + hj, mbar);
-    if (!mbar_wait(mbar, mphase) && lane == 0) *cm.abort_flag = 1;   // never observed; the safe lattice would redo the utterance
-    mphase ^= 1;
+  for (int x = nc1; x < min(nc1 + 2, n_chunks); ++x) {   // the first two phase-2 chunks (their rows have landed)
+    request_records(x);
+    publish(x);
   }
-  named_bar_sync(bar_chunk(SIDE), nbar);
   named_bar_sync(bar_total(SIDE), nbar);
   {
     float inv_mP; int eP; double log2P;
-    if (!total_probability(c.sm, NW, inv_mP, eP, log2P)) return;
+    if (!total_probability(c.sm, NW, inv_mP, eP, log2P)) {
+      // the lattice warps give up here: no bulk copy may still be in flight when the shared memory is reused
+      for (int x = nc1; x < min(nc1 + 2, n_chunks); ++x) mbar_wait(ready + (x & 1), (x >> 1) & 1, abort_flag);
+      return;
+    }
   }
   const bool reduce = p.grads != nullptr && B200CTC_ABLATE != 9;   // ablation 9: helpers do not reduce (timing only)
 
@@ -1038,42 +1087,29 @@ __device__ void fast_side_helper(const CallParams& p, int b, const UttMeta& m, c
   float* rowsum = c.sm.rowsum + (size_t)hj * (post_rows_max(c.L, V) + 4);
 
   // ================================ phase 2 ================================
-  int k2 = 0;
-  for (int n0 = M_side; n0 < T; n0 += K, ++k2, ++cc) {
-    const int par = k2 & 1;
+  for (; j < n_chunks; ++j) {
+    B200CTC_TRACE_EVENT(tc, 6);
+    mbar_wait(done + (j & 1), (j >> 1) & 1, abort_flag);
     B200CTC_TRACE_EVENT(tc, 7);
-    bool copying = false;
-    stage_chunk(cc + 2);
-    if (n0 + K + hj < T) {                            // the other side's records frame hj of the next chunk needs
-      prefetch_other<SIDE>(c, (par ^ 1) * K + hj, n0 + K + hj, mbar);
-      copying = true;
-    }
+    if (j + 2 < n_chunks) request_records(j + 2);     // into the record buffer chunk j just released
     B200CTC_TRACE_EVENT(tc, 8);
-    if (reduce && k2 >= 1) {                          // frame hj of the previous chunk (it was a full chunk)
-      const int n = n0 - K + hj;
-      reduce_frame<NWMAX>(p, cm, c.sm.post + (size_t)((par ^ 1) * K + hj) * c.PS,
-                          c.sm.rows + (size_t)(((cc - 1) & (kRowsRing - 1)) * K + hj) * c.RWS,
+    const int n = chunk_start(j) + hj;
+    if (reduce && n < T)
+      reduce_frame<NWMAX>(p, cm, c.sm.post + (size_t)((j & 1) * K + hj) * c.PS,
+                          c.sm.rows + (size_t)((j & (kRowsRing - 1)) * K + hj) * c.RWS,
                           p.grads + ((long long)c.frame_of(n) * p.B + b) * V, rowsum, c.RC, NW, C4, R, n_seg,
                           one_row, sym_first, lane);
-    }
     B200CTC_TRACE_EVENT(tc, 9);
+    stage_chunk(j + 3);
     cp_async_wait<1>();
-    if (copying) {
-      if (!mbar_wait(mbar, mphase) && lane == 0) *cm.abort_flag = 1;
-      mphase ^= 1;
-    }
-    named_bar_sync(bar_chunk(SIDE), nbar);
-  }
-  // the last chunk
-  if (reduce) {
-    const int n0 = M_side + (k2 - 1) * K, par = (k2 - 1) & 1;
-    if (n0 + hj < T)
-      reduce_frame<NWMAX>(p, cm, c.sm.post + (size_t)(par * K + hj) * c.PS,
-                          c.sm.rows + (size_t)(((cc - 1) & (kRowsRing - 1)) * K + hj) * c.RWS,
-                          p.grads + ((long long)c.frame_of(n0 + hj) * p.B + b) * V, rowsum, c.RC, NW, C4, R, n_seg,
-                          one_row, sym_first, lane);
+    if (j + 2 < n_chunks) publish(j + 2);
   }
   cp_async_wait<0>();
+  // Every bulk copy has landed: the lattice warps waited for the records of every chunk they ran.  Only
+  // after a hand-off timeout (kAbortSync, never observed) may one still be in flight; give it time.
+  if (*abort_flag & kAbortSync)
+    for (int x = max(nc1, n_chunks - 2); x < n_chunks; ++x)
+      for (int it = 0; it < (1 << 16) && !mbar_try_wait(ready + (x & 1), (x >> 1) & 1); ++it) {}
 }
 
 // The whole fast path for one utterance; every thread of the CTA calls it.  On return the shared
@@ -1122,7 +1158,15 @@ __device__ void lattice_fast_utterance(const CallParams& p, int b, unsigned char
     for (int sd = 0; sd < 2; ++sd) {
       FastSideSmem s = carve_fast_side<K, NWMAX, NS>(smem + common + sd * side_bytes, L, RW, p.V);
       for (int i = threadIdx.x; i < 2 * K * PS; i += blockDim.x) s.post[i] = 0.f;
+      if (threadIdx.x == 0) {
+        for (int i = 0; i < 2; ++i) {
+          mbar_init(s.mbar + kMbarReady + i, kReducers);   // one arrival per helper warp (+ the bytes of the bulk copies)
+          mbar_init(s.mbar + kMbarDone + i, NW);           // one arrival per lattice warp
+        }
+        for (int i = 0; i < kHaloRing * NWMAX; ++i) mbar_init(s.mbar + kMbarHalo + i, 1);
+      }
     }
+    if (threadIdx.x == 0) asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   __syncthreads();
   build_symbol_index(cm.lab, L, p.V, cm.ix);

@@ -20,32 +20,73 @@ struct SymbolIndex {
 };
 
 // All threads of the CTA call this; lab[] must already be in shared memory and visible.
-// Ends with a __syncthreads().
-__device__ __forceinline__ void build_symbol_index(const int* lab, int L, SymbolIndex ix) {
-  const int tid = threadIdx.x, nt = blockDim.x;
-  // rank sort: position i goes to slot #{j : (lab[j], j) < (lab[i], i)}
-  for (int i = tid; i < L; i += nt) {
-    const int li = lab[i];
-    int rank = 0;
-    for (int j = 0; j < L; ++j) {
-      const int lj = lab[j];
-      rank += (lj < li) || (lj == li && j < i);
-    }
-    ix.sorted[rank] = i;
-  }
-  __syncthreads();
-  if (tid == 0) {
-    int n = 0;
-    for (int k = 0; k < L; ++k) {
-      const int sym = lab[ix.sorted[k]];
-      if (k == 0 || sym != lab[ix.sorted[k - 1]]) {
-        ix.seg_start[n] = k;
-        ix.seg_sym[n] = sym;
-        ++n;
+// Ends with a __syncthreads().  Everything is data-parallel: a rank sort on packed (symbol, position)
+// keys (ix.seg_sym doubles as the key array until the segments are written), then the segment
+// boundaries by a ballot scan over the sorted order.
+__device__ __forceinline__ void build_symbol_index(const int* lab, int L, int V, SymbolIndex ix) {
+  const int tid = threadIdx.x, nt = blockDim.x, lane = tid & 31, warp = tid >> 5, n_warps = nt >> 5;
+  __shared__ int s_warp_tot[32];
+  __shared__ int s_base;
+  if ((long long)V * L < (1ll << 31)) {
+    // rank sort on one 32-bit key per label: position i goes to slot #{j : key[j] < key[i]}
+    int* key = ix.seg_sym;
+    for (int i = tid; i < L; i += nt) key[i] = lab[i] * L + i;
+    __syncthreads();
+    const int head = min(L, (int)((16u - ((unsigned)__cvta_generic_to_shared(key) & 15u)) & 15u) >> 2);
+    for (int i = tid; i < L; i += nt) {
+      const int ki = key[i];
+      int rank = 0, j = 0;
+      for (; j < head; ++j) rank += key[j] < ki;
+      for (; j + 4 <= L; j += 4) {
+        const int4 q = *reinterpret_cast<const int4*>(key + j);
+        rank += (q.x < ki) + (q.y < ki) + (q.z < ki) + (q.w < ki);
       }
+      for (; j < L; ++j) rank += key[j] < ki;
+      ix.sorted[rank] = i;
     }
-    ix.seg_start[n] = L;
-    *ix.n_seg = n;
+  } else {
+    for (int i = tid; i < L; i += nt) {
+      const int li = lab[i];
+      int rank = 0;
+      for (int j = 0; j < L; ++j) {
+        const int lj = lab[j];
+        rank += (lj < li) || (lj == li && j < i);
+      }
+      ix.sorted[rank] = i;
+    }
+  }
+  if (tid == 0) s_base = 0;
+  __syncthreads();
+  // segment starts in sorted order, numbered by a CTA-wide ballot scan, one tile of blockDim.x positions at a time
+  for (int k0 = 0; k0 < L; k0 += nt) {
+    const int k = k0 + tid;
+    int sym = 0;
+    bool start = false;
+    if (k < L) {
+      sym = lab[ix.sorted[k]];
+      start = k == 0 || sym != lab[ix.sorted[k - 1]];
+    }
+    const unsigned bal = __ballot_sync(0xffffffffu, start);
+    if (lane == 0) s_warp_tot[warp] = __popc(bal);
+    __syncthreads();
+    int off = s_base;
+    for (int i = 0; i < warp; ++i) off += s_warp_tot[i];
+    if (start) {
+      const int u = off + __popc(bal & ((1u << lane) - 1u));
+      ix.seg_start[u] = k;
+      ix.seg_sym[u] = sym;
+    }
+    __syncthreads();
+    if (tid == 0) {
+      int tot = s_base;
+      for (int i = 0; i < n_warps; ++i) tot += s_warp_tot[i];
+      s_base = tot;
+    }
+    __syncthreads();
+  }
+  if (tid == 0) {
+    ix.seg_start[s_base] = L;
+    *ix.n_seg = s_base;
   }
   __syncthreads();
 }

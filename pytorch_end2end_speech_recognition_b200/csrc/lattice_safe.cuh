@@ -65,7 +65,7 @@ __device__ void lattice_safe_utterance(const CallParams& p, int b, unsigned char
 
   for (int i = tid; i < L; i += nt) sm.lab[i] = p.labels[m.lab_off + i];
   __syncthreads();
-  build_symbol_index(sm.lab, L, sm.ix);
+  build_symbol_index(sm.lab, L, V, sm.ix);
 
   const float* acts_b = p.acts + (long long)b * p.as_b;
   double* alpha = reinterpret_cast<double*>(p.scratch + m.scratch_off * kGroupBytes);

@@ -61,6 +61,24 @@ def main():
         span = int(t[-1] - t[0])
         desc = ", ".join("%d->%d: %d x %.0f" % (k[0], k[1], v[1], v[0] / v[1]) for k, v in sorted(segs.items()) if v[0] > 0.01 * span)
         print("warp %2d  first %7d  span %7d  %s" % (w, int(t[0]) - t0, span, desc))
+    # lattice warps, per phase and per quarter of the phase: run / publish / barrier wait / import (cycles per chunk)
+    for w in range(63):
+        t, tag = t_all[w], tag_all[w]
+        if not len(t) or 2 not in tag:
+            continue
+        for phase, start_tag, done_tag in ((1, 2, 3), (2, 13, 14)):
+            idx = [i for i in range(len(t)) if tag[i] == start_tag]
+            rows = []
+            for a, i in enumerate(idx):
+                if i + 3 < len(t) and tag[i + 1] == done_tag and tag[i + 2] == 30 and tag[i + 3] == 31:
+                    nxt = int(t[i + 4] - t[i + 3]) if i + 4 < len(t) and tag[i + 4] == start_tag else 0
+                    rows.append((int(t[i + 1] - t[i]), int(t[i + 2] - t[i + 1]), int(t[i + 3] - t[i + 2]), nxt))
+            if not rows:
+                continue
+            r = np.array(rows, dtype=np.float64)
+            q = max(1, len(r) // 4)
+            parts = ["q%d run %4.0f pub %3.0f wait %4.0f imp %3.0f" % ((k,) + tuple(r[k * q:(k + 1) * q].mean(axis=0))) for k in range(4)]
+            print("warp %2d phase %d: %s" % (w, phase, " | ".join(parts)))
     if "--raw" in sys.argv:            # raw event sequences (tag@cycle) of every warp around the middle of phase 1 and of phase 2
         for lo_frac in (0.2, 0.7):
             lo = t0 + int((t1 - t0) * lo_frac)
