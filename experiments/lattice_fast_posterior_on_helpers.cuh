@@ -69,7 +69,6 @@ __device__ __forceinline__ void trace_event(int& cnt, int tag) {
 #ifndef B200CTC_ABLATE
 #define B200CTC_ABLATE 0   // developer timing experiments (tools/ablate_lattice.py); 0 = product
 #endif
-constexpr int kAbortExtremeRow = 2;  // abort word: K1 flagged the utterance (nothing was written yet); 1 = redo after a lost range
 constexpr int kEZero = -(1 << 28);  // exponent of an all-zero lane
 constexpr int kRowsRing = 4;        // emission-row chunks in the ring: the reducers' one, this chunk, the next one (landed), the one after (in flight)
 constexpr int kOthRing = 8;         // per-thread ring of the opposite side's records: two chunks of K = 4 frames
@@ -212,7 +211,8 @@ __host__ __device__ inline int post_rows_max(int L, int V) {
 struct FastSideSmem {
   float* rows;      // [kRowsRing][K][RWS]     staged emission rows (+ a zero slot at index RW)
   unsigned char* oth;   // [2][K] frame blocks   the opposite side's stored records, two chunks (+ one all-zero block)
-  float* post;      // [2][K][PS]              symbol-sorted label posteriors + blank partials + dump slot
+  unsigned char* fresh; // [2][K] frame blocks   this side's fresh phase-2 states, two chunks (+ one dump block)
+  float* post;      // [kReducers][PS]         symbol-sorted label posteriors of the frame a helper warp is reducing (+ dump slot)
   float4* halo_m;   // [2][NWMAX][HL][NS/4]    halo lanes
   int* halo_e;      // [2][NWMAX][HL]
   float* red_m;     // [NWMAX]
@@ -232,9 +232,10 @@ __host__ __device__ inline size_t fast_side_bytes(int L, int RW, int V) {
   constexpr int HL = 2 * K / NS;
   size_t b = 0;
   b += (size_t)(2 * K + 1) * frame_block_bytes<NS>(L);       // oth (+ the zero block)
+  b += (size_t)(2 * K + 1) * frame_block_bytes<NS>(L);       // fresh (+ the dump block)
   b += (size_t)2 * NWMAX * HL * (NS / 4) * 16;               // halo_m
   b += (size_t)kRowsRing * K * (size_t)(RW + 4) * 4;         // rows
-  b += 2 * (size_t)K * post_stride<NWMAX>(L, V) * 4;         // post
+  b += (size_t)kReducers * post_stride<NWMAX>(L, V) * 4;     // post
   b += (size_t)2 * NWMAX * HL * 4;                           // halo_e
   b += NWMAX * 8;                                            // red
   b += (size_t)kReducers * (post_rows_max(L, V) + 4) * 4;    // rowsum (one per reducer warp)
@@ -256,9 +257,10 @@ __device__ __forceinline__ FastSideSmem carve_fast_side(unsigned char* base, int
   FastSideSmem s;
   unsigned char* p = base;
   s.oth = p;                               p += (size_t)(2 * K + 1) * frame_block_bytes<NS>(L);
+  s.fresh = p;                             p += (size_t)(2 * K + 1) * frame_block_bytes<NS>(L);
   s.halo_m = reinterpret_cast<float4*>(p); p += (size_t)2 * NWMAX * HL * (NS / 4) * 16;
   s.rows = reinterpret_cast<float*>(p);    p += (size_t)kRowsRing * K * (size_t)(RW + 4) * 4;
-  s.post = reinterpret_cast<float*>(p);    p += 2 * (size_t)K * post_stride<NWMAX>(L, V) * 4;
+  s.post = reinterpret_cast<float*>(p);    p += (size_t)kReducers * post_stride<NWMAX>(L, V) * 4;
   s.halo_e = reinterpret_cast<int*>(p);    p += (size_t)2 * NWMAX * HL * 4;
   s.red_m = reinterpret_cast<float*>(p);   p += NWMAX * 4;
   s.red_e = reinterpret_cast<int*>(p);     p += NWMAX * 4;
@@ -293,8 +295,6 @@ struct LaneConst {
   int idxB[NS / 2]; // byte offset in the emission row of the label positions (zero slot if the position is a dummy)
   int idxB_blank;   // byte offset of the blank
   f2 Kf[NS / 4];    // skip-transition factors (1.0 allowed / 0.0 not) of the label pairs
-  int posB[NS / 2]; // byte offset of the label positions in the symbol-sorted posterior row (dump slot if dummy)
-  int blankB;       // byte offset of this thread's blank partial sum in the posterior row
   int recB, expB;   // byte offsets of this lane's group in a frame block: first mantissa plane, exponent
   bool owned;       // this lane's group belongs to the warp (not to the halo) and exists
   int group;        // global position group (pos0 / NS)
@@ -455,68 +455,111 @@ __device__ __forceinline__ void stage_row(const FastCtx<SIDE>& c, int slot, int 
   }
 }
 
-// Posterior of one frame for one lane: the fresh renormalised state times the stored record of the
-// opposite side, normalised by P:  post = a * o * 2^(e + oe - eP) / mP.  Scatters the label
-// posteriors and the blank partial sum.  Every lane of the warp runs it and stores: lanes that own no
-// group scatter into the dump slot, and a cost-only call points `post` at a dump row.
-// No band masks: for every state outside the reachable band at least one factor is exactly zero
-// (unreachable from this side's start: a == 0; unreachable from the other side's start: the stored
-// value is 0, or the record was never written and reads as zero -- prefetch_other).
-// The fresh state is normalised to [1,2) per lane, so the one scale factor cannot push a product
-// that matters out of the fp32 range.
-template <int SIDE, int NS>
-__device__ __forceinline__ void posterior_frame(SweepState<NS>& ss, const unsigned char* __restrict__ blk, int plane_bytes,
-                                                void* __restrict__ post) {
-  constexpr int NP = NS / 2, NH = NS / 4;
-  const LaneConst<NS>& lc = ss.lc;
-  const LaneState<NS>& st = ss.st;
-  f2 O[NP];
-#pragma unroll
-  for (int h = 0; h < NH; ++h) {
-    const float4 q = *reinterpret_cast<const float4*>(blk + lc.recB + h * plane_bytes);
-    O[2 * h] = f2_pack(q.x, q.y);
-    O[2 * h + 1] = f2_pack(q.z, q.w);
+// Which phase-1 records of position group `grp` (this side's group order) the OTHER side wrote: its warp
+// that owns the mirrored group was active in the chunk (K steps aligned at its step 0) that holds the
+// frame.  A reader at step n finds the record iff (unsigned)(rd_hi - n) < wr_len.
+template <int K, int SIDE, int NS>
+__device__ __forceinline__ void record_window(int grp, int JG, int P, int S, int T, int& rd_hi, int& wr_len) {
+  constexpr int HL = 2 * K / NS, WIN = 32 * NS, OWN = WIN - 2 * K, OWNG = OWN / NS;
+  const int G = JG - 1 - grp;                               // the writer's group index
+  const int wo = G < 32 ? 0 : (G - HL) / OWNG;              // its owner warp (the first HL lanes of warps > 0 are halo)
+  const int o_lo_pos = wo * OWN, o_hi_pos = min(wo * OWN + WIN - 1, P - 1);
+  const int os_lo = SIDE ? o_lo_pos : (P - 1 - o_hi_pos);   // the writer is the opposite side
+  const int os_hi = SIDE ? o_hi_pos : (P - 1 - o_lo_pos);
+  int t0, t1;
+  band_frames(os_lo, os_hi, S, T, t0, t1);
+  const int M_other = SIDE ? (T - T / 2) : (T / 2);         // frames the other side covers in phase 1
+  int na = SIDE ? t0 : T - 1 - t1;                          // in the writer's steps
+  int nb = min(SIDE ? t1 : T - 1 - t0, M_other - 1);
+  rd_hi = 0; wr_len = 0;
+  if (t0 <= t1 && na <= nb && grp < JG) {
+    na = na / K * K;
+    nb = nb / K * K + K - 1;
+    rd_hi = T - 1 - na;                                     // writer step n' = T-1-n for a reader at step n
+    wr_len = nb - na + 1;
   }
-  const int oe = *reinterpret_cast<const int*>(blk + lc.expB);
-  const int dexp = st.e + oe - ss.eP;
-  const float s = pow2_clamped(dexp) * ss.inv_mP;   // inv_mP in (0.5, 1]
-  const f2 s2 = f2_pack(s, s);
-  f2 PO[NP];
+}
+
+// What a helper warp keeps per position group it forms posteriors for (group g = lane + 32 i).
+template <int NS, int NG>
+struct HelperGroups {
+  int posB[NG][NS / 2];     // byte offsets of the group's label positions in the symbol-sorted posterior row (dump slot if dummy)
+  int rd_hi[NG], wr_len[NG];
+};
+
+// Posteriors of one phase-2 frame, formed by a helper warp from the two frame blocks in shared memory:
+// `fr` = the fresh renormalised states this side's lattice warps stored, `ot` = the stored records of
+// the opposite side:  post = a * o * 2^(e + oe - eP) / mP  for every position group (lane g, g+32, ..).
+// Label posteriors are scattered into the warp's symbol-sorted row `post`; the blank posteriors are
+// summed in registers (returned per lane).
+// No band masks: for every state outside the reachable band at least one factor is exactly zero
+// (unreachable from this side's start: a == 0 -- a lattice warp outside the band stores zero blocks;
+// unreachable from the other side's start: the stored value is 0, or the record was never written and the
+// all-zero block is read instead).  The fresh state is normalised to [1,2) per lane, so the one scale
+// factor cannot push a product that matters out of the fp32 range.
+// Range check.  A state that sits more than 2^-110 below its lane's largest value may have lost bits
+// (on either side).  Its posterior is bounded by
+//   2^-110 * max(own lane) * max(other lane) * 2^dexp / mP,   max(own lane) in [1,2);
+// if that bound is not negligible (> 2^-24) the block-exponent result cannot be trusted.  Evaluated on
+// the exponent fields (a zero maximum has field 0 and can only lower the bound), so it cannot overflow
+// or underflow; the caller tests the running maximum after every frame.
+template <int SIDE, int NS, int NG>
+__device__ __forceinline__ float posterior_groups(const HelperGroups<NS, NG>& hg, const unsigned char* __restrict__ fr,
+                                                  const unsigned char* __restrict__ ot, const unsigned char* __restrict__ zero_blk,
+                                                  int JG, int n, float inv_mP, int eP, void* __restrict__ post, bool scatter,
+                                                  int lane, int& maxbound) {
+  constexpr int NP = NS / 2, NH = NS / 4;
+  const int plane = JG * 16;
+  // Branch-free over the lane's groups, so that the loads of all of them are in flight together: a group
+  // index past the last one re-reads the last group with a zero scale, and its label slots are the dump slot.
+  f2 A[NG][NP], O[NG][NP];
+  int ex[NG];
 #pragma unroll
-  for (int j = 0; j < NP; ++j) PO[j] = f2_mul(f2_mul(st.A[j], O[j]), s2);
-  // Range check.  A state that sits more than 2^-110 below its lane's largest value may have lost
-  // bits (on either side).  Its posterior is bounded by
-  //   2^-110 * max(own lane) * max(other lane) * 2^dexp / mP,   max(own lane) in [1,2);
-  // if that bound is not negligible (> 2^-24) the block-exponent result cannot be trusted.  The own
-  // maximum runs over ALL states of the lane: dead states (too late to finish) share the exponent.
-  // Evaluated on the exponent fields (a zero maximum has field 0 and can only lower the bound), so
-  // it cannot overflow or underflow; the running maximum is tested at the chunk boundary.
-  const float omax = f2_max_all<NP>(O);
-  ss.maxbound = max(ss.maxbound, (__float_as_int(omax) >> 23) + dexp);
-  {
-    f2 bacc;
-    bool first = true;
+  for (int i = 0; i < NG; ++i) {
+    const int g = min(lane + 32 * i, JG - 1);
+    const bool wr = (unsigned)(hg.rd_hi[i] - n) < (unsigned)hg.wr_len[i];   // did the other side store this record?
+    const unsigned char* ob = wr ? ot : zero_blk;
+#pragma unroll
+    for (int h = 0; h < NH; ++h) {
+      const float4 a = *reinterpret_cast<const float4*>(fr + g * 16 + h * plane);
+      const float4 q = *reinterpret_cast<const float4*>(ob + g * 16 + h * plane);
+      A[i][2 * h] = f2_pack(a.x, a.y); A[i][2 * h + 1] = f2_pack(a.z, a.w);
+      O[i][2 * h] = f2_pack(q.x, q.y); O[i][2 * h + 1] = f2_pack(q.z, q.w);
+    }
+    ex[i] = *reinterpret_cast<const int*>(fr + NH * plane + g * 4) + *reinterpret_cast<const int*>(ob + NH * plane + g * 4);
+  }
+  f2 bacc = f2_pack(0.f, 0.f);
+#pragma unroll
+  for (int i = 0; i < NG; ++i) {
+    const int dexp = ex[i] - eP;
+    const float sc = (lane + 32 * i < JG) ? pow2_clamped(dexp) * inv_mP : 0.f;     // inv_mP in (0.5, 1]
+    const f2 s2 = f2_pack(sc, sc);
+    f2 PO[NP];
+#pragma unroll
+    for (int j = 0; j < NP; ++j) PO[j] = f2_mul(f2_mul(A[i][j], O[i][j]), s2);
+    const float omax = f2_max_all<NP>(O[i]);
+    maxbound = max(maxbound, (__float_as_int(omax) >> 23) + dexp);
 #pragma unroll
     for (int j = 0; j < NP; ++j) {
       const bool is_label = SIDE ? (j % 2 == 0) : (j % 2 == 1);
       if (is_label) {
-        const int u = j / 2;
-        sts_f32(post, lc.posB[u], el_j<SIDE>(PO[j]));
-        sts_f32(post, lc.posB[u + NP / 2], el_j4<SIDE>(PO[j]));
+        if (scatter) {
+          const int u = j / 2;
+          sts_f32(post, hg.posB[i][u], el_j<SIDE>(PO[j]));
+          sts_f32(post, hg.posB[i][u + NP / 2], el_j4<SIDE>(PO[j]));
+        }
       } else {
-        bacc = first ? PO[j] : f2_add(bacc, PO[j]);
-        first = false;
+        bacc = f2_add(bacc, PO[j]);
       }
     }
-    sts_f32(post, lc.blankB, f2_lo(bacc) + f2_hi(bacc));
   }
+  return f2_lo(bacc) + f2_hi(bacc);
 }
 
 // One chunk (kc <= K frames starting at step n0; emission rows in ring slot `rslot`).  A warp whose
 // window misses the reachable band in all frames of the chunk skips it (warp-uniform).
 template <int K, bool PH2, int SIDE, int NT, int NS>
-__device__ __forceinline__ void run_chunk(const FastCtx<SIDE>& c, SweepState<NS>& ss, int rslot, int pbuf, int obuf,
-                                          int n0, int kc, bool write_post) {
+__device__ __forceinline__ void run_chunk(const FastCtx<SIDE>& c, SweepState<NS>& ss, int rslot, int pbuf, int n0, int kc) {
   constexpr int NP = NS / 2, NH = NS / 4;
   const LaneConst<NS>& lc = ss.lc;
   const bool lane0 = c.lane == 0;
@@ -559,31 +602,33 @@ __device__ __forceinline__ void run_chunk(const FastCtx<SIDE>& c, SweepState<NS>
     if (dummy.e == 12345) ss.maxbound = 1 << 20;   // keep the duplicate chain alive
 #endif
   } else {
-    // cost-only calls (no gradient buffer) walk phase 2 for the range check: their posteriors land in one dump row
-    char* post = reinterpret_cast<char*>(c.sm.post + (size_t)pbuf * K * c.PS);
-    const int post_bytes = write_post ? c.PS * 4 : 0;
-    const bool store = write_post;
+    // phase 2: the same recursion; the fresh (post-emission, renormalised) state of every owned group goes
+    // to the shared-memory ring, where the helper warps form the posteriors one chunk later.  Lanes that own
+    // no group (halo, beyond the lattice) store into the dump block.
+    unsigned char* fp = c.sm.fresh + (lc.owned ? (size_t)pbuf * K * c.FB : (size_t)2 * K * c.FB) + lc.recB;
+    const int fstep = lc.owned ? c.FB : 0;
+    const int plane = c.JG * 16, eoff = lc.expB - lc.recB;
     if (active) {
-      const unsigned char* blk = c.sm.oth + (size_t)obuf * K * c.FB;
-      const unsigned char* zero_blk = c.sm.oth + (size_t)2 * K * c.FB;
-      const int plane = c.JG * 16;
 #pragma unroll 2
       for (int j = 0; j < kc; ++j) {
         f2 ACC[NP]; int E;
         lattice_frame<SIDE, NS>(ss.st, lc, row, lane0, ACC, E);
-        const bool wr = (unsigned)(ss.rd_hi - (n0 + j)) < (unsigned)ss.wr_len;   // did the other side store this record?
-        if (B200CTC_ABLATE != 5) posterior_frame<SIDE, NS>(ss, wr ? blk : zero_blk, plane, post);
+#pragma unroll
+        for (int h = 0; h < NH; ++h)
+          *reinterpret_cast<float4*>(fp + h * plane) =
+              make_float4(f2_lo(ss.st.A[2 * h]), f2_hi(ss.st.A[2 * h]), f2_lo(ss.st.A[2 * h + 1]), f2_hi(ss.st.A[2 * h + 1]));
+        *reinterpret_cast<int*>(fp + eoff) = ss.st.e;
         row += row_bytes;
-        post += post_bytes;
-        blk += c.FB;
+        fp += fstep;
       }
-    } else if (store) {
+    } else {
+      // outside the reachable band: every state is zero
 #pragma unroll 1
       for (int j = 0; j < kc; ++j) {
 #pragma unroll
-        for (int m = 0; m < NP; ++m) sts_f32(post, lc.posB[m], 0.f);
-        sts_f32(post, lc.blankB, 0.f);
-        post += post_bytes;
+        for (int h = 0; h < NH; ++h) *reinterpret_cast<float4*>(fp + h * plane) = make_float4(0.f, 0.f, 0.f, 0.f);
+        *reinterpret_cast<int*>(fp + eoff) = kEZero;
+        fp += fstep;
       }
     }
   }
@@ -605,7 +650,6 @@ __device__ __forceinline__ void chunk_boundary(const FastCtx<SIDE>& c, SweepStat
       c.sm.halo_m[slot * NH + h] = make_float4(f2_lo(st.A[2 * h]), f2_hi(st.A[2 * h]), f2_lo(st.A[2 * h + 1]), f2_hi(st.A[2 * h + 1]));
     c.sm.halo_e[slot] = st.e;
   }
-  if (ss.lc.owned && ss.maxbound > kLostBound) *abort_flag = 1;
   B200CTC_TRACE_EVENT(tc, 30);
 #if B200CTC_ABLATE == 7
   if ((cc & 7) == 7)
@@ -709,7 +753,6 @@ __device__ void fast_side_sweep(const CallParams& p, int b, const UttMeta& m, co
   lc.group = pos0 / NS;
   lc.owned = ((w == 0) || (lane >= HL)) && (lc.group < JG);
   lc.idxB_blank = 4 * (p.gathered ? 0 : p.blank);
-  lc.blankB = 4 * (lc.owned ? c.RC + c.tid_side : c.PS - 4);
   lc.recB = min(lc.group, JG - 1) * 16;
   lc.expB = NH * JG * 16 + min(lc.group, JG - 1) * 4;
   {
@@ -720,12 +763,10 @@ __device__ void fast_side_sweep(const CallParams& p, int b, const UttMeta& m, co
       const int s = SIDE ? (P - 1 - q) : q;
       const bool ok = (q < P) && (s >= 0) && (s < S);             // s is odd by construction
       lc.idxB[mslot] = 4 * c.RW;            // zero slot
-      lc.posB[mslot] = 4 * (c.PS - 4);      // dump slot
       kk[mslot] = 0.f;
       if (ok) {
         const int li = s >> 1;
         lc.idxB[mslot] = 4 * (p.gathered ? li + 1 : lab[li]);
-        if (lc.owned) lc.posB[mslot] = 4 * cm.slot_of_label[li];   // halo lanes scatter into the dump slot
         const bool sk = SIDE ? (s + 2 < S && lab[li] != lab[li + 1]) : (s >= 3 && lab[li] != lab[li - 1]);
         kk[mslot] = sk ? 1.f : 0.f;
       }
@@ -745,24 +786,8 @@ __device__ void fast_side_sweep(const CallParams& p, int b, const UttMeta& m, co
     if (t0 > t1) { a_lo = 1 << 30; a_hi = -1; }
     ss.act_lo = __shfl_sync(0xffffffffu, a_lo, 0);
     ss.act_hi = __shfl_sync(0xffffffffu, a_hi, 0);
-    // which phase-1 records of this lane's group the OTHER side wrote: its warp that owns the mirrored
-    // group was active in the chunk (K steps aligned at its step 0) that holds the frame
-    const int G = JG - 1 - lc.group;                          // the writer's group index
-    const int wo = G < 32 ? 0 : (G - HL) / OWNG;              // its owner warp (the first HL lanes of warps > 0 are halo)
-    const int o_lo_pos = wo * OWN, o_hi_pos = min(wo * OWN + WIN - 1, P - 1);
-    const int os_lo = SIDE ? o_lo_pos : (P - 1 - o_hi_pos);   // the writer is the opposite side
-    const int os_hi = SIDE ? o_hi_pos : (P - 1 - o_lo_pos);
-    band_frames(os_lo, os_hi, S, T, t0, t1);
-    const int M_other = SIDE ? (T - T / 2) : (T / 2);         // frames the other side covers in phase 1
-    int na = SIDE ? t0 : T - 1 - t1;                          // in the writer's steps
-    int nb = min(SIDE ? t1 : T - 1 - t0, M_other - 1);
-    ss.rd_hi = 0; ss.wr_len = 0;
-    if (t0 <= t1 && na <= nb && lc.group < JG) {
-      na = na / K * K;
-      nb = nb / K * K + K - 1;
-      ss.rd_hi = T - 1 - na;                                  // writer step n' = T-1-n for a reader at step n
-      ss.wr_len = nb - na + 1;
-    }
+    // which phase-1 records of this lane's group the other side wrote (the total probability reads one)
+    record_window<K, SIDE, NS>(lc.group, JG, P, S, T, ss.rd_hi, ss.wr_len);
   }
   // ---- initial state: delta on the first lattice state of this side's sweep ----
   {
@@ -812,7 +837,7 @@ __device__ void fast_side_sweep(const CallParams& p, int b, const UttMeta& m, co
   for (int n0 = 0; n0 < M_side; n0 += K, ++cc) {
     const int kc = min(K, M_side - n0);
     B200CTC_TRACE_EVENT(tc, 2);
-    run_chunk<K, false, SIDE, NT, NS>(c, ss, rs, 0, 0, n0, kc, false);
+    run_chunk<K, false, SIDE, NT, NS>(c, ss, rs, 0, n0, kc);
     B200CTC_TRACE_EVENT(tc, 3);
     chunk_boundary<K, NWMAX, SIDE, NS>(c, ss, cc, abort_flag, tc);
     rs = rs == kRowsRing - 1 ? 0 : rs + 1;
@@ -863,15 +888,12 @@ __device__ void fast_side_sweep(const CallParams& p, int b, const UttMeta& m, co
     }
     if (SIDE == 1 && c.tid_side == 0) p.costs[b] = (float)(-log2P * 0.69314718055994530942);
   }
-  // cost-only calls still walk phase 2 (for the range check) but neither store posteriors nor update rows
-  const bool write_post = p.grads != nullptr;
-
   // ================================ phase 2 ================================
   int k2 = 0;
   for (int n0 = M_side; n0 < T; n0 += K, ++k2, ++cc) {
     const int kc = min(K, T - n0), par = k2 & 1;
     B200CTC_TRACE_EVENT(tc, 13);
-    run_chunk<K, true, SIDE, NT, NS>(c, ss, rs, par, par, n0, kc, write_post);
+    run_chunk<K, true, SIDE, NT, NS>(c, ss, rs, par, n0, kc);
     B200CTC_TRACE_EVENT(tc, 14);
     chunk_boundary<K, NWMAX, SIDE, NS>(c, ss, cc, abort_flag, tc);
     rs = rs == kRowsRing - 1 ? 0 : rs + 1;
@@ -910,18 +932,13 @@ __device__ __forceinline__ float warp_sum_q30(float v) {
 
 // Per-symbol occupancy of one phase-2 frame (posterior row `post`, softmax row `yrow`) and the update
 // of its gradient row.
-template <int NWMAX>
+// `accb` is the lane's partial sum of the blank posteriors (posterior_groups).
 __device__ __forceinline__ void reduce_frame(const CallParams& p, const FastCommon& cm, const float* __restrict__ post,
                                              const float* __restrict__ yrow, float* __restrict__ grow, float* rowsum,
-                                             int RC, int NW, int C4, int R, int n_seg, bool one_row, int sym_first,
+                                             float accb, int C4, int R, int n_seg, bool one_row, int sym_first,
                                              int lane) {
   const float4* post4 = reinterpret_cast<const float4*>(post);
   const bool gathered = p.gathered != 0;
-  // blank: partial sums of the lattice threads
-  float accb = 0.f;
-#pragma unroll
-  for (int i = 0; i < NWMAX; ++i)
-    if (i < NW) accb += post[RC + i * 32 + lane];
   if (one_row && n_seg <= 32 && !gathered) {
     // the common small-vocabulary case, straight line: lane u owns symbol u's single row
     float tot = 0.f, y = 0.f;
@@ -967,18 +984,19 @@ __device__ __forceinline__ void reduce_frame(const CallParams& p, const FastComm
   }
 }
 
-// Helper warp hj of the side owns frame hj of every chunk: during chunk c it fetches what that frame
-// of chunk c+1 needs (emission row; in phase 2 the other side's records of all position groups) and,
-// in phase 2, reduces the posteriors the lattice warps produced for its frame of chunk c-1 into the
-// gradient row.  It meets the lattice warps at the one barrier per chunk.
+// Helper warp hj of the side owns frame hj of every chunk.  During chunk c of the lattice warps it stages
+// the emission row its frame of chunk c+2 needs and, in phase 2, (1) requests the other side's records of
+// its frame of chunk c (one TMA bulk copy), (2) forms the posteriors of its frame of chunk c-1 from the
+// fresh states the lattice warps left in shared memory and the records that landed a chunk ago, sums
+// them per symbol and updates the gradient row.  It meets the lattice warps at the one barrier per chunk.
 template <int K, int NWMAX, int SIDE, int NS>
 __device__ void fast_side_helper(const CallParams& p, int b, const UttMeta& m, const FastCommon& cm,
                                  unsigned char* side_smem, int hj, int lane) {
   static_assert(kReducers == K, "one helper warp per frame of a chunk");
-  constexpr int NT = NWMAX * 32;
+  constexpr int NG = (NWMAX * (32 * NS - 2 * K) + 2 * K) / NS / 32 + 1;   // position groups per lane (all windows)
   FastCtx<SIDE> c;
   fill_ctx<K, NWMAX, SIDE, NS>(c, p, b, m, side_smem, NWMAX + hj, lane);
-  const int T = c.T, NW = c.NW, V = p.V;
+  const int T = c.T, NW = c.NW, V = p.V, JG = c.JG;
   const SidePlan pl = side_plan<K, SIDE>(T);
   const int M_side = pl.M_side;
   const int nbar = (NW + kReducers) * 32;
@@ -1019,17 +1037,20 @@ __device__ void fast_side_helper(const CallParams& p, int b, const UttMeta& m, c
   // ================================ midpoint ================================
   named_bar_sync(kBarMidpoint, 2 * nbar);
   if (pl.nc2 == 0) return;
-  if (M_side + hj < T) {                             // records of the first phase-2 chunk
+  if (M_side + hj < T) {                             // records of the first phase-2 chunk (the total probability reads frame 0)
     prefetch_other<SIDE>(c, hj, M_side + hj, mbar);
     if (!mbar_wait(mbar, mphase) && lane == 0) *cm.abort_flag = 1;   // never observed; the safe lattice would redo the utterance
     mphase ^= 1;
   }
   named_bar_sync(bar_chunk(SIDE), nbar);
   named_bar_sync(bar_total(SIDE), nbar);
+  float inv_mP; int eP;
   {
-    float inv_mP; int eP; double log2P;
+    double log2P;
     if (!total_probability(c.sm, NW, inv_mP, eP, log2P)) return;
   }
+  // cost-only calls (no gradient buffer) still form the products for the range check, but neither
+  // scatter nor update rows
   const bool reduce = p.grads != nullptr && B200CTC_ABLATE != 9;   // ablation 9: helpers do not reduce (timing only)
 
   const int C4 = post_row_width(c.L, V) / 4;          // 16-byte chunks per row
@@ -1037,43 +1058,69 @@ __device__ void fast_side_helper(const CallParams& p, int b, const UttMeta& m, c
   const bool one_row = (R == n_seg);                  // every symbol fits one row: row index == segment index
   const int sym_first = lane < n_seg ? cm.ix.seg_sym[lane] : 0;
   float* rowsum = c.sm.rowsum + (size_t)hj * (post_rows_max(c.L, V) + 4);
+  float* post = c.sm.post + (size_t)hj * c.PS;        // this warp's posterior row
+  const unsigned char* zero_blk = c.sm.oth + (size_t)2 * K * c.FB;
+
+  // per position group of this lane: where its label posteriors go, which records exist
+  HelperGroups<NS, NG> hg;
+#pragma unroll
+  for (int i = 0; i < NG; ++i) {
+    const int g = lane + 32 * i;
+#pragma unroll
+    for (int mslot = 0; mslot < NS / 2; ++mslot) {
+      const int q = NS * g + (SIDE ? 2 * mslot : 2 * mslot + 1);    // label positions of the group
+      const int s = SIDE ? (c.P - 1 - q) : q;
+      const bool ok = (g < JG) && (q < c.P) && (s >= 0) && (s < c.S);   // s is odd by construction
+      hg.posB[i][mslot] = 4 * (ok ? cm.slot_of_label[s >> 1] : c.PS - 4);   // dump slot
+    }
+    record_window<K, SIDE, NS>(g, JG, c.P, c.S, T, hg.rd_hi[i], hg.wr_len[i]);
+  }
+  int maxbound = -(1 << 30);
+
+  // posteriors + reduce of frame hj of phase-2 chunk k (its records sit in buffer k & 1)
+  auto finish_frame = [&](int k) {
+    const int n = M_side + k * K + hj;
+    if (n >= T) return;
+    const float accb = posterior_groups<SIDE, NS, NG>(hg, c.sm.fresh + (size_t)((k & 1) * K + hj) * c.FB,
+                                                      c.sm.oth + (size_t)((k & 1) * K + hj) * c.FB, zero_blk, JG, n,
+                                                      inv_mP, eP, post, reduce, lane, maxbound);
+    if (maxbound > kLostBound) *cm.abort_flag = 1;
+    B200CTC_TRACE_EVENT(tc, 10);
+    if (reduce) {
+      __syncwarp();                                   // the warp's scattered posteriors are visible to its row sums
+      reduce_frame(p, cm, post, c.sm.rows + (size_t)(((nc1 + k) & (kRowsRing - 1)) * K + hj) * c.RWS,
+                   p.grads + ((long long)c.frame_of(n) * p.B + b) * V, rowsum, accb, C4, R, n_seg, one_row, sym_first, lane);
+      __syncwarp();                                   // ... and read before the next frame overwrites them
+    }
+  };
 
   // ================================ phase 2 ================================
   int k2 = 0;
+  bool copying = false;
   for (int n0 = M_side; n0 < T; n0 += K, ++k2, ++cc) {
-    const int par = k2 & 1;
     B200CTC_TRACE_EVENT(tc, 7);
-    bool copying = false;
     stage_chunk(cc + 2);
-    if (n0 + K + hj < T) {                            // the other side's records frame hj of the next chunk needs
-      prefetch_other<SIDE>(c, (par ^ 1) * K + hj, n0 + K + hj, mbar);
+    if (copying) {                                    // records of chunk k2-1 (requested during the previous chunk)
+      if (!mbar_wait(mbar, mphase) && lane == 0) *cm.abort_flag = 1;
+      mphase ^= 1;
+      copying = false;
+    }
+    if (k2 >= 1 && n0 + hj < T) {                     // records of this chunk: consumed during the next one
+      prefetch_other<SIDE>(c, (k2 & 1) * K + hj, n0 + hj, mbar);
       copying = true;
     }
     B200CTC_TRACE_EVENT(tc, 8);
-    if (reduce && k2 >= 1) {                          // frame hj of the previous chunk (it was a full chunk)
-      const int n = n0 - K + hj;
-      reduce_frame<NWMAX>(p, cm, c.sm.post + (size_t)((par ^ 1) * K + hj) * c.PS,
-                          c.sm.rows + (size_t)(((cc - 1) & (kRowsRing - 1)) * K + hj) * c.RWS,
-                          p.grads + ((long long)c.frame_of(n) * p.B + b) * V, rowsum, c.RC, NW, C4, R, n_seg,
-                          one_row, sym_first, lane);
-    }
+    if (k2 >= 1) finish_frame(k2 - 1);
     B200CTC_TRACE_EVENT(tc, 9);
     cp_async_wait<1>();
-    if (copying) {
-      if (!mbar_wait(mbar, mphase) && lane == 0) *cm.abort_flag = 1;
-      mphase ^= 1;
-    }
     named_bar_sync(bar_chunk(SIDE), nbar);
   }
   // the last chunk
-  if (reduce) {
-    const int n0 = M_side + (k2 - 1) * K, par = (k2 - 1) & 1;
-    if (n0 + hj < T)
-      reduce_frame<NWMAX>(p, cm, c.sm.post + (size_t)(par * K + hj) * c.PS,
-                          c.sm.rows + (size_t)(((cc - 1) & (kRowsRing - 1)) * K + hj) * c.RWS,
-                          p.grads + ((long long)c.frame_of(n0 + hj) * p.B + b) * V, rowsum, c.RC, NW, C4, R, n_seg,
-                          one_row, sym_first, lane);
+  if (copying) {
+    if (!mbar_wait(mbar, mphase) && lane == 0) *cm.abort_flag = 1;
+    mphase ^= 1;
   }
+  finish_frame(k2 - 1);
   cp_async_wait<0>();
 }
 
@@ -1122,7 +1169,7 @@ __device__ void lattice_fast_utterance(const CallParams& p, int b, unsigned char
     const int PS = post_stride<NWMAX>(L, p.V);
     for (int sd = 0; sd < 2; ++sd) {
       FastSideSmem s = carve_fast_side<K, NWMAX, NS>(smem + common + sd * side_bytes, L, RW, p.V);
-      for (int i = threadIdx.x; i < 2 * K * PS; i += blockDim.x) s.post[i] = 0.f;
+      for (int i = threadIdx.x; i < kReducers * PS; i += blockDim.x) s.post[i] = 0.f;
     }
   }
   __syncthreads();
@@ -1164,13 +1211,6 @@ __device__ void lattice_fast_utterance(const CallParams& p, int b, unsigned char
     g_trace_cnt[63] = 2;
   }
 #endif
-  // Everything above needed only the host-prepared tables.  From here on K1's output is read (softmax rows,
-  // gathered emissions, the extreme-row flag): wait for K1 (programmatic dependent launch, lattice.cu).
-  pdl_wait_primary();
-  if (p.flags[b] & FLAG_EXTREME_ROW) {      // some probability below 2^-100: the safe lattice takes the utterance
-    if (threadIdx.x == 0) *cm.abort_flag = kAbortExtremeRow;
-    return;
-  }
   if (w < NW) {
     if (side == 0) fast_side_sweep<K, NWMAX, 0, NS>(p, b, m, cm, smem + common, w, lane);
     else           fast_side_sweep<K, NWMAX, 1, NS>(p, b, m, cm, smem + common + side_bytes, w, lane);

@@ -19,6 +19,15 @@ constexpr int kGatherMinV = 129;  // V above this: the lattice reads gathered em
 
 inline size_t align_up(size_t x) { return (x + kAlign - 1) / kAlign * kAlign; }
 
+// K0: the call's host-prepared tables (utterance metadata, launch order, flags, labels) travel host -> device
+// by a KERNEL that reads the pinned staging slot through its mapped address, not by a DMA copy.  A small DMA
+// copy queues behind whatever large host-to-device transfer the application has in flight on the copy
+// engines (a data loader prefetching the next mini-batch of logits: +0.2 ms per call measured on B200,
+// tools/e2e_timeline.py); a kernel on the compute stream does not.
+__global__ void __launch_bounds__(256) fetch_tables_kernel(int4* __restrict__ dst, const int4* __restrict__ src, int n16) {
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n16; i += gridDim.x * blockDim.x) dst[i] = src[i];
+}
+
 struct WorkspaceLayout {
   size_t blob_bytes;   // meta + order + flags + labels
   size_t off_meta, off_order, off_flags, off_labels;
@@ -190,7 +199,7 @@ int b200ctc_loss_and_grad(b200ctc_handle* h, const float* acts, int64_t acts_str
     slot.host = nullptr;
     slot.capacity = 0;
     const size_t cap = std::max(lay.blob_bytes * 2, (size_t)1 << 16);
-    if (cudaHostAlloc(&slot.host, cap, cudaHostAllocDefault) != cudaSuccess) {
+    if (cudaHostAlloc(&slot.host, cap, cudaHostAllocMapped) != cudaSuccess) {
       cudaGetLastError();
       return B200CTC_STATUS_EXECUTION_FAILED;
     }
@@ -241,8 +250,15 @@ int b200ctc_loss_and_grad(b200ctc_handle* h, const float* acts, int64_t acts_str
     return wx > wy;
   });
 
-  if (cudaMemcpyAsync(ws, blob, lay.blob_bytes, cudaMemcpyHostToDevice, stream) != cudaSuccess ||
-      cudaEventRecord(slot.done, stream) != cudaSuccess) {
+  void* blob_dev = nullptr;                         // the staging slot as the device sees it
+  if (cudaHostGetDevicePointer(&blob_dev, blob, 0) != cudaSuccess) {
+    cudaGetLastError();
+    return B200CTC_STATUS_EXECUTION_FAILED;
+  }
+  const int n16 = (int)((lay.blob_bytes + 15) / 16);
+  fetch_tables_kernel<<<std::min(64, (n16 + 255) / 256), 256, 0, stream>>>(
+      reinterpret_cast<int4*>(ws), reinterpret_cast<const int4*>(blob_dev), n16);
+  if (cudaGetLastError() != cudaSuccess || cudaEventRecord(slot.done, stream) != cudaSuccess) {
     cudaGetLastError();
     return B200CTC_STATUS_EXECUTION_FAILED;
   }

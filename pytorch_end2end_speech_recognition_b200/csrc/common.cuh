@@ -43,6 +43,13 @@ struct CallParams {
   int gathered;           // 1: lattice reads emissions from `em`, 0: from the softmax rows in `grads`
 };
 
+// Programmatic dependent launch (sm_90+): K1 lets the lattice kernel start while it is still running; the
+// lattice kernel does everything that needs no K1 output (labels, symbol index) and then waits for K1's
+// completion and memory flush.  Both instructions are no-ops in a launch without the PDL attribute.
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait_primary() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
+
 enum UttFlags : int {
   FLAG_EXTREME_ROW = 1,   // some softmax probability of the utterance is below 2^-100: use the safe lattice
   FLAG_PRECISION_LOST = 2 // the block-exponent lattice saw a live state lose range: redo with the safe lattice

@@ -26,19 +26,23 @@ __global__ void __launch_bounds__(2 * (NWMAX + kReducers) * 32, 1) lattice_kerne
   } else if (m.T == 0) {  // empty utterance with an empty target: probability one
     if (threadIdx.x == 0) p.costs[b] = 0.f;
   } else {
-    bool use_safe = (p.flags[b] & FLAG_EXTREME_ROW) != 0 || fast_warps_needed<K, NS>(m.L) > NWMAX;
+    bool use_safe = fast_warps_needed<K, NS>(m.L) > NWMAX;
     bool dirty = false;
     if (!use_safe) {
+      // prologue (no K1 output needed), then wait for K1, then the sweeps -- unless K1 flagged an extreme row
       int* abort_word = nullptr;
       lattice_fast_utterance<K, NWMAX, NS>(p, b, smem, &abort_word);
       __syncthreads();
-      use_safe = *abort_word != 0;
-      if (use_safe) {
+      const int why = *abort_word;
+      use_safe = why != 0;
+      if (use_safe && why != kAbortExtremeRow) {
         dirty = p.grads != nullptr;  // part of the gradient rows may already have been rewritten
         if (threadIdx.x == 0) atomicOr(p.flags + b, FLAG_PRECISION_LOST);
         __threadfence();             // order this thread's row updates before the rows are rebuilt
         __syncthreads();
       }
+    } else {
+      pdl_wait_primary();
     }
     if (use_safe) lattice_safe_utterance(p, b, smem, dirty);
   }
@@ -89,8 +93,18 @@ cudaError_t launch_lattice_t(const CallParams& p, int max_L, cudaStream_t stream
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
   }
-  lattice_kernel<K, NWMAX, NS><<<p.B, 2 * (NWMAX + kReducers) * 32, smem, stream>>>(p);
-  return cudaGetLastError();
+  // programmatic dependent launch: this kernel may start while K1 (the previous kernel in the stream) runs
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)p.B);
+  cfg.blockDim = dim3(2 * (NWMAX + kReducers) * 32);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, lattice_kernel<K, NWMAX, NS>, p);
 }
 
 }  // namespace

@@ -38,6 +38,7 @@ __device__ __forceinline__ float group_sum(float v) {
 
 template <int LPR, int NV>
 __global__ void __launch_bounds__(256) softmax_rows_warp_kernel(CallParams p) {
+  pdl_launch_dependents();   // the lattice kernel may begin its prologue now
   constexpr int RPW = 32 / LPR;                       // rows per warp
   const int lane = threadIdx.x & 31;
   const int q = lane & (LPR - 1), sub = lane / LPR;
@@ -146,6 +147,7 @@ __device__ __forceinline__ float block_reduce_sum(float v, float* red) {
 }
 
 __global__ void __launch_bounds__(kRowThreads) softmax_rows_cta_kernel(CallParams p) {
+  pdl_launch_dependents();   // the lattice kernel may begin its prologue now
   extern __shared__ __align__(16) float srow[];  // V floats (+3 slack for the aligned window)
   __shared__ float red[kRowThreads / 32];
   const long long row = blockIdx.x;
