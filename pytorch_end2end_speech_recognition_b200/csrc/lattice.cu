@@ -21,6 +21,12 @@ __global__ void __launch_bounds__(2 * (NWMAX + kReducers) * 32, 1) lattice_kerne
   extern __shared__ __align__(16) unsigned char smem[];
   const int b = p.order[blockIdx.x];
   const UttMeta m = p.meta[b];
+#ifdef B200CTC_TRACE
+  if (threadIdx.x == 0 && blockIdx.x < 2048) {
+    unsigned long long t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    g_cta_time[blockIdx.x * 2] = (long long)t;
+  }
+#endif
   if (!m.feasible) {  // K1 already zero-filled its gradient rows
     if (threadIdx.x == 0) p.costs[b] = INFINITY;
   } else if (m.T == 0) {  // empty utterance with an empty target: probability one
@@ -47,6 +53,13 @@ __global__ void __launch_bounds__(2 * (NWMAX + kReducers) * 32, 1) lattice_kerne
     if (use_safe) lattice_safe_utterance(p, b, smem, dirty);
   }
 
+#ifdef B200CTC_TRACE
+  __syncthreads();
+  if (threadIdx.x == 0 && blockIdx.x < 2048) {
+    unsigned long long t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    g_cta_time[blockIdx.x * 2 + 1] = (long long)t;
+  }
+#endif
   // K3, fused: the CTA that finishes last sums the per-utterance costs in a fixed order (256 strided
   // partial sums in double, then a tree), so the returned loss is bit-reproducible run to run.
   if (p.loss_sum == nullptr) return;
@@ -131,6 +144,13 @@ cudaError_t launch_lattice(const CallParams& p, int max_L, cudaStream_t stream) 
 
 #ifdef B200CTC_TRACE
 // developer hook: copies the timeline of CTA 0 of the last lattice launch and clears it
+extern "C" __attribute__((visibility("default"))) int b200ctc_debug_set_trace_cta(int cta) {
+  return cudaMemcpyToSymbol(g_trace_cta, &cta, sizeof(int)) == cudaSuccess ? 0 : 2;
+}
+extern "C" __attribute__((visibility("default"))) int b200ctc_debug_read_cta_times(long long* host, int n) {
+  if (cudaDeviceSynchronize() != cudaSuccess) return 2;
+  return cudaMemcpyFromSymbol(host, g_cta_time, sizeof(long long) * 2 * n) == cudaSuccess ? 0 : 2;
+}
 extern "C" __attribute__((visibility("default"))) int b200ctc_debug_read_trace(long long* host, int* counts) {
   if (cudaDeviceSynchronize() != cudaSuccess) return 2;
   if (cudaMemcpyFromSymbol(host, g_trace, sizeof(long long) * 64 * kTraceCap) != cudaSuccess) return 2;

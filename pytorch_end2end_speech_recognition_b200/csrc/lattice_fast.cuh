@@ -52,8 +52,10 @@ namespace b200ctc {
 constexpr int kTraceCap = 4096;
 __device__ long long g_trace[64 * kTraceCap];
 __device__ int g_trace_cnt[64];
+__device__ int g_trace_cta = 0;               // which CTA (launch index) records its timeline
+__device__ long long g_cta_time[2 * 2048];   // %globaltimer at entry / exit of every CTA of the last lattice launch
 __device__ __forceinline__ void trace_event(int& cnt, int tag) {
-  if (blockIdx.x == 0 && (threadIdx.x & 31) == 0 && cnt < kTraceCap) {
+  if (blockIdx.x == g_trace_cta && (threadIdx.x & 31) == 0 && cnt < kTraceCap) {
     g_trace[(threadIdx.x >> 5) * kTraceCap + cnt] = ((long long)clock64() << 8) | tag;
     ++cnt;
     g_trace_cnt[threadIdx.x >> 5] = cnt;
@@ -183,10 +185,19 @@ __device__ __forceinline__ float f2_max(f2 a, f2 b) {  // max over the four floa
 // ---------------------------------------------------------------------------------------------
 // geometry shared by host (shared-memory sizing) and device.  NS = lattice states per lane (4 or 8).
 // ---------------------------------------------------------------------------------------------
+// Frames between two halo exchanges of neighbouring lattice windows.  Consecutive windows overlap by
+// 2*KX positions: dependencies only point downwards (s-1, s-2), so the garbage creeping up from a window's
+// bottom stays inside the overlap for KX frames.  K (frames per chunk) sets the granularity of the
+// shared-memory buffers and of the hand-off with the helper warps; phase 1 needs neither between two
+// exchanges and runs KX/K chunks back to back without a barrier -- every barrier costs the recursion's
+// dependent chain a pipeline drain and refill (~500 cycles against 140 per frame in steady state).
+template <int K, int NS>
+__host__ __device__ constexpr int exchange_frames() { return NS == 8 ? 4 * K : K; }
+
 template <int K, int NS>
 __host__ __device__ inline int fast_warps_needed(int L) {
   const int P = NS * ((2 * L + 1 + NS - 1) / NS);
-  const int win = 32 * NS, own = win - 2 * K;
+  const int win = 32 * NS, own = win - 2 * exchange_frames<K, NS>();
   return P <= win ? 1 : 1 + (P - win + own - 1) / own;
 }
 // One frame of stored records ("frame block"), the same layout in the HBM scratch and in shared memory:
@@ -197,11 +208,14 @@ __host__ __device__ inline int frame_block_bytes(int L) {
   const int JG = (2 * L + 1 + NS - 1) / NS;
   return (NS / 4) * JG * 16 + ((JG + 3) & ~3) * 4;
 }
-// Symbol-sorted posterior row: every symbol of the label sequence owns whole rows of C slots.
+// Symbol-sorted posterior row: every symbol of the label sequence owns whole rows of C slots.  C is chosen
+// so that a symbol occurring twice as often as the average still fits ONE row: the reducers' straight-line
+// path needs one row per symbol, and an utterance on the multi-row path takes ~10 % longer (in the C3
+// batch the utterances with 290..350 labels, a symbol count of 21..23 against C = 20, finished last).
 __host__ __device__ inline int post_row_width(int L, int V) {
   const int n_sym = L < V - 1 ? L : V - 1;
   const int avg = n_sym > 0 ? (L + n_sym - 1) / n_sym : 1;
-  const int want = avg + avg / 2 + 2;
+  const int want = 2 * avg + 2;
   return want <= 4 ? 4 : want <= 12 ? 12 : want <= 20 ? 20 : 28;  // odd number of 16-byte chunks: conflict-free LDS.128
 }
 __host__ __device__ inline int post_rows_max(int L, int V) {
@@ -210,7 +224,7 @@ __host__ __device__ inline int post_rows_max(int L, int V) {
 }
 
 struct FastSideSmem {
-  float* rows;      // [kRowsRing][K][RWS]     staged emission rows (+ a zero slot at index RW)
+  float* rows;      // [kRowsRing * KX/K][K][RWS]   staged emission rows (+ a zero slot at index RW)
   unsigned char* oth;   // [2][K] frame blocks   the opposite side's stored records, two chunks (+ one all-zero block)
   float* post;      // [2][K][PS]              symbol-sorted label posteriors + blank partials + dump slot
   float4* halo_m;   // [2][NWMAX][HL][NS/4]    halo lanes
@@ -229,11 +243,12 @@ __host__ __device__ inline int post_stride(int L, int V) {  // floats per frame 
 template <int K, int NWMAX, int NS>
 __host__ __device__ inline size_t fast_side_bytes(int L, int RW, int V) {
   const size_t NT = NWMAX * 32;
-  constexpr int HL = 2 * K / NS;
+  constexpr int HL = 2 * exchange_frames<K, NS>() / NS;
+  constexpr int RCH = kRowsRing * exchange_frames<K, NS>() / K;   // chunk slots of the emission-row ring
   size_t b = 0;
   b += (size_t)(2 * K + 1) * frame_block_bytes<NS>(L);       // oth (+ the zero block)
   b += (size_t)2 * NWMAX * HL * (NS / 4) * 16;               // halo_m
-  b += (size_t)kRowsRing * K * (size_t)(RW + 4) * 4;         // rows
+  b += (size_t)RCH * K * (size_t)(RW + 4) * 4;               // rows
   b += 2 * (size_t)K * post_stride<NWMAX>(L, V) * 4;         // post
   b += (size_t)2 * NWMAX * HL * 4;                           // halo_e
   b += NWMAX * 8;                                            // red
@@ -252,12 +267,13 @@ __host__ __device__ inline size_t fast_smem_bytes(int L, int RW, int V) {
 template <int K, int NWMAX, int NS>
 __device__ __forceinline__ FastSideSmem carve_fast_side(unsigned char* base, int L, int RW, int V) {
   const size_t NT = NWMAX * 32;
-  constexpr int HL = 2 * K / NS;
+  constexpr int HL = 2 * exchange_frames<K, NS>() / NS;
+  constexpr int RCH = kRowsRing * exchange_frames<K, NS>() / K;
   FastSideSmem s;
   unsigned char* p = base;
   s.oth = p;                               p += (size_t)(2 * K + 1) * frame_block_bytes<NS>(L);
   s.halo_m = reinterpret_cast<float4*>(p); p += (size_t)2 * NWMAX * HL * (NS / 4) * 16;
-  s.rows = reinterpret_cast<float*>(p);    p += (size_t)kRowsRing * K * (size_t)(RW + 4) * 4;
+  s.rows = reinterpret_cast<float*>(p);    p += (size_t)RCH * K * (size_t)(RW + 4) * 4;
   s.post = reinterpret_cast<float*>(p);    p += 2 * (size_t)K * post_stride<NWMAX>(L, V) * 4;
   s.halo_e = reinterpret_cast<int*>(p);    p += (size_t)2 * NWMAX * HL * 4;
   s.red_m = reinterpret_cast<float*>(p);   p += NWMAX * 4;
@@ -594,8 +610,8 @@ __device__ __forceinline__ void run_chunk(const FastCtx<SIDE>& c, SweepState<NS>
 // of the previous chunk is consumed), import the halo.
 template <int K, int NWMAX, int SIDE, int NS>
 __device__ __forceinline__ void chunk_boundary(const FastCtx<SIDE>& c, SweepState<NS>& ss, int cc, int* abort_flag, int& tc) {
-  constexpr int NH = NS / 4, HL = 2 * K / NS;
-  static_assert(HL * NS == 2 * K && HL >= 1, "the halo must be whole lanes");
+  constexpr int NH = NS / 4, HL = 2 * exchange_frames<K, NS>() / NS;
+  static_assert(HL * NS == 2 * exchange_frames<K, NS>() && HL >= 1, "the halo must be whole lanes");
   const int hb = cc & 1, NW = c.NW, w = c.w, lane = c.lane;
   LaneState<NS>& st = ss.st;
   if (w + 1 < NW && lane >= 32 - HL) {
@@ -689,7 +705,9 @@ template <int K, int NWMAX, int SIDE, int NS>
 __device__ void fast_side_sweep(const CallParams& p, int b, const UttMeta& m, const FastCommon& cm,
                                 unsigned char* side_smem, int w, int lane) {
   constexpr int NP = NS / 2, NH = NS / 4;
-  constexpr int H = 2 * K;          // halo positions
+  constexpr int KX = exchange_frames<K, NS>();
+  constexpr int H = 2 * KX;         // halo positions
+  constexpr int RCH = kRowsRing * KX / K;   // chunk slots of the emission-row ring
   constexpr int HL = H / NS;        // halo lanes
   constexpr int WIN = 32 * NS;      // positions per warp window
   constexpr int OWN = WIN - H;
@@ -796,7 +814,7 @@ __device__ void fast_side_sweep(const CallParams& p, int b, const UttMeta& m, co
   // the all-zero frame block (stands in for records the other side never wrote)
   for (int i = c.tid_side; i < c.FB / 4; i += NW * 32) reinterpret_cast<int*>(c.sm.oth + (size_t)2 * K * c.FB)[i] = (i >= NH * JG * 4) ? kEZero : 0;
   // zero slots of the row buffers (the helper warps stage the rows themselves)
-  for (int i = c.tid_side; i < kRowsRing * K; i += NW * 32) {
+  for (int i = c.tid_side; i < RCH * K; i += NW * 32) {
     float* z = c.sm.rows + (size_t)i * c.RWS + c.RW;
     z[0] = 0.f; z[1] = 0.f; z[2] = 0.f; z[3] = 0.f;
   }
@@ -808,14 +826,17 @@ __device__ void fast_side_sweep(const CallParams& p, int b, const UttMeta& m, co
   named_bar_sync(bar_chunk(SIDE), (NW + kReducers) * 32);       // rows of chunk 0 staged, wr_tab visible
 
   // ================================ phase 1 ================================
-  int cc = 0;
-  for (int n0 = 0; n0 < M_side; n0 += K, ++cc) {
-    const int kc = min(K, M_side - n0);
+  // KX/K chunks between two halo exchanges (one barrier with the helpers per exchange)
+  int cc = 0, xc = 0;
+  for (int n0 = 0; n0 < M_side; ++xc) {
     B200CTC_TRACE_EVENT(tc, 2);
-    run_chunk<K, false, SIDE, NT, NS>(c, ss, rs, 0, 0, n0, kc, false);
+#pragma unroll 1
+    for (int sub = 0; sub < KX / K && n0 < M_side; ++sub, n0 += K, ++cc) {
+      run_chunk<K, false, SIDE, NT, NS>(c, ss, rs, 0, 0, n0, min(K, M_side - n0), false);
+      rs = (rs + 1) & (RCH - 1);
+    }
     B200CTC_TRACE_EVENT(tc, 3);
-    chunk_boundary<K, NWMAX, SIDE, NS>(c, ss, cc, abort_flag, tc);
-    rs = rs == kRowsRing - 1 ? 0 : rs + 1;
+    chunk_boundary<K, NWMAX, SIDE, NS>(c, ss, xc, abort_flag, tc);
   }
 
   // ================================ midpoint ================================
@@ -873,8 +894,9 @@ __device__ void fast_side_sweep(const CallParams& p, int b, const UttMeta& m, co
     B200CTC_TRACE_EVENT(tc, 13);
     run_chunk<K, true, SIDE, NT, NS>(c, ss, rs, par, par, n0, kc, write_post);
     B200CTC_TRACE_EVENT(tc, 14);
-    chunk_boundary<K, NWMAX, SIDE, NS>(c, ss, cc, abort_flag, tc);
-    rs = rs == kRowsRing - 1 ? 0 : rs + 1;
+    chunk_boundary<K, NWMAX, SIDE, NS>(c, ss, xc, abort_flag, tc);
+    rs = (rs + 1) & (RCH - 1);
+    ++xc;
   }
   B200CTC_TRACE_EVENT(tc, 15);
 }
@@ -994,25 +1016,28 @@ __device__ void fast_side_helper(const CallParams& p, int b, const UttMeta& m, c
 
   // Emission rows are staged TWO chunks ahead (ring slot = chunk & 3), so that the global-memory latency
   // of a row never sits between the lattice warps and the chunk barrier.
+  constexpr int KX = exchange_frames<K, NS>(), M = KX / K, RCH = kRowsRing * M;
   const int nc1 = pl.nc1, n_chunks = pl.n_chunks;
   auto chunk_start = [&](int cc) { return cc < nc1 ? cc * K : M_side + (cc - nc1) * K; };
-  auto stage_chunk = [&](int cc) {
-    if (cc < n_chunks) {
-      const int n = chunk_start(cc) + hj;
-      if (n < T) stage_row<SIDE>(c, (cc & (kRowsRing - 1)) * K + hj, n);   // a row past a short chunk is harmless
+  int staged = 0;                                    // chunks [0, staged) have been requested
+  auto stage_upto = [&](int end) {                   // one cp.async group: this warp's row of chunks [staged, end)
+    for (; staged < min(end, n_chunks); ++staged) {
+      const int n = chunk_start(staged) + hj;
+      if (n < T) stage_row<SIDE>(c, (staged & (RCH - 1)) * K + hj, n);   // a row past a short chunk is harmless
     }
     cp_async_commit();
   };
-  stage_chunk(0);
-  stage_chunk(1);
+  stage_upto(M);
+  stage_upto(2 * M);
   cp_async_wait<1>();
   named_bar_sync(bar_chunk(SIDE), nbar);
 
   // ================================ phase 1 ================================
+  // one barrier per halo exchange of the lattice warps (M chunks); rows are staged two exchanges ahead
   int cc = 0;
-  for (; cc < nc1; ++cc) {
-    stage_chunk(cc + 2);
-    cp_async_wait<1>();                       // rows of chunk cc+1 have landed
+  for (int xc = 0; cc < nc1; ++xc, cc = min(cc + M, nc1)) {
+    stage_upto((xc + 3) * M);
+    cp_async_wait<1>();                       // rows up to chunk (xc+2)*M - 1 have landed
     named_bar_sync(bar_chunk(SIDE), nbar);
   }
 
@@ -1044,7 +1069,7 @@ __device__ void fast_side_helper(const CallParams& p, int b, const UttMeta& m, c
     const int par = k2 & 1;
     B200CTC_TRACE_EVENT(tc, 7);
     bool copying = false;
-    stage_chunk(cc + 2);
+    stage_upto(cc + 3);                               // chunk cc+2 (a no-op while phase 1's look-ahead lasts)
     if (n0 + K + hj < T) {                            // the other side's records frame hj of the next chunk needs
       prefetch_other<SIDE>(c, (par ^ 1) * K + hj, n0 + K + hj, mbar);
       copying = true;
@@ -1053,7 +1078,7 @@ __device__ void fast_side_helper(const CallParams& p, int b, const UttMeta& m, c
     if (reduce && k2 >= 1) {                          // frame hj of the previous chunk (it was a full chunk)
       const int n = n0 - K + hj;
       reduce_frame<NWMAX>(p, cm, c.sm.post + (size_t)((par ^ 1) * K + hj) * c.PS,
-                          c.sm.rows + (size_t)(((cc - 1) & (kRowsRing - 1)) * K + hj) * c.RWS,
+                          c.sm.rows + (size_t)(((cc - 1) & (RCH - 1)) * K + hj) * c.RWS,
                           p.grads + ((long long)c.frame_of(n) * p.B + b) * V, rowsum, c.RC, NW, C4, R, n_seg,
                           one_row, sym_first, lane);
     }
@@ -1070,7 +1095,7 @@ __device__ void fast_side_helper(const CallParams& p, int b, const UttMeta& m, c
     const int n0 = M_side + (k2 - 1) * K, par = (k2 - 1) & 1;
     if (n0 + hj < T)
       reduce_frame<NWMAX>(p, cm, c.sm.post + (size_t)(par * K + hj) * c.PS,
-                          c.sm.rows + (size_t)(((cc - 1) & (kRowsRing - 1)) * K + hj) * c.RWS,
+                          c.sm.rows + (size_t)(((cc - 1) & (RCH - 1)) * K + hj) * c.RWS,
                           p.grads + ((long long)c.frame_of(n0 + hj) * p.B + b) * V, rowsum, c.RC, NW, C4, R, n_seg,
                           one_row, sym_first, lane);
   }
@@ -1113,7 +1138,7 @@ __device__ void lattice_fast_utterance(const CallParams& p, int b, unsigned char
 
   // ---- prologue (all threads of the CTA) ----
 #ifdef B200CTC_TRACE
-  if (blockIdx.x == 0 && threadIdx.x == 0) g_trace[63 * kTraceCap] = ((long long)clock64() << 8) | 20;
+  if (blockIdx.x == g_trace_cta && threadIdx.x == 0) g_trace[63 * kTraceCap] = ((long long)clock64() << 8) | 20;
 #endif
   for (int i = threadIdx.x; i < L; i += blockDim.x) cm.lab[i] = p.labels[m.lab_off + i];
   if (threadIdx.x < 8) cm.abort_flag[threadIdx.x] = 0;
@@ -1159,7 +1184,7 @@ __device__ void lattice_fast_utterance(const CallParams& p, int b, unsigned char
     __syncthreads();
   }
 #ifdef B200CTC_TRACE
-  if (blockIdx.x == 0 && threadIdx.x == 0) {
+  if (blockIdx.x == g_trace_cta && threadIdx.x == 0) {
     g_trace[63 * kTraceCap + 1] = ((long long)clock64() << 8) | 21;
     g_trace_cnt[63] = 2;
   }

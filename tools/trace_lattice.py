@@ -36,6 +36,8 @@ def main():
     cap = 4096
     host = (ctypes.c_longlong * (64 * cap))()
     cnt = (ctypes.c_int * 64)()
+    cta = next((int(a[6:]) for a in sys.argv[1:] if a.startswith("--cta=")), 0)
+    assert lib.b200ctc_debug_set_trace_cta(cta) == 0
     for _ in range(3):
         eng.ctc_loss_and_grad(acts, wl.labels, wl.act_lens, wl.label_lens)
         torch.cuda.synchronize()
@@ -46,7 +48,7 @@ def main():
     tag_all = [ev[w, :counts[w]] & 0xff for w in range(64)]
     t0 = min(int(t[0]) for t in t_all if len(t))
     t1 = max(int(t[-1]) for t in t_all if len(t))
-    print("CTA 0 (utterance with L=%d, T=%d): %d cycles traced" % (wl.label_lens.max(), wl.T, t1 - t0))
+    print("CTA %d: %d cycles traced" % (cta, t1 - t0))
     for w in range(64):
         t, tag = t_all[w], tag_all[w]
         if not len(t):
@@ -79,6 +81,23 @@ def main():
             q = max(1, len(r) // 4)
             parts = ["q%d run %4.0f pub %3.0f wait %4.0f imp %3.0f" % ((k,) + tuple(r[k * q:(k + 1) * q].mean(axis=0))) for k in range(4)]
             print("warp %2d phase %d: %s" % (w, phase, " | ".join(parts)))
+    if "--ctas" in sys.argv:           # per-CTA wall time (ns, %globaltimer): who finishes last
+        nb = min(wl.B, 2048)
+        tt = (ctypes.c_longlong * (2 * nb))()
+        assert lib.b200ctc_debug_read_cta_times(tt, nb) == 0
+        tt = np.frombuffer(tt, dtype=np.int64).reshape(nb, 2)
+        order = np.argsort(-(wl.act_lens.astype(np.int64) * (2 * wl.label_lens + 1)), kind="stable")
+        t_first = tt[:, 0].min()
+        dur = tt[:, 1] - tt[:, 0]
+        print("kernel span %.1f us; CTA start spread %.1f us" % ((tt[:, 1].max() - t_first) / 1e3, (tt[:, 0].max() - t_first) / 1e3))
+        for i in np.argsort(-tt[:, 1])[:8]:
+            bb = order[i]
+            print("  CTA %3d (T=%d L=%d): start +%.1f us, runs %.1f us, ends +%.1f us" % (i, wl.act_lens[bb], wl.label_lens[bb], (tt[i, 0] - t_first) / 1e3, dur[i] / 1e3, (tt[i, 1] - t_first) / 1e3))
+        ls = wl.label_lens[order[:nb]]
+        for lo, hi in ((0, 128), (128, 240), (240, 252), (252, 352), (352, 376), (376, 464), (464, 2000)):
+            sel = (ls >= lo) & (ls < hi)
+            if sel.any():
+                print("  L in [%d,%d): %d CTAs, run time mean %.1f us max %.1f us" % (lo, hi, sel.sum(), dur[sel].mean() / 1e3, dur[sel].max() / 1e3))
     if "--raw" in sys.argv:            # raw event sequences (tag@cycle) of every warp around the middle of phase 1 and of phase 2
         for lo_frac in (0.2, 0.7):
             lo = t0 + int((t1 - t0) * lo_frac)
