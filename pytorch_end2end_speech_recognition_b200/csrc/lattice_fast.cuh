@@ -609,12 +609,13 @@ __device__ __forceinline__ void run_chunk(const FastCtx<SIDE>& c, SweepState<NS>
 // helper warps (after it the helpers' prefetch for the next chunk has landed and the posterior buffer
 // of the previous chunk is consumed), import the halo.
 template <int K, int NWMAX, int SIDE, int NS>
-__device__ __forceinline__ void chunk_boundary(const FastCtx<SIDE>& c, SweepState<NS>& ss, int cc, int* abort_flag, int& tc) {
+__device__ __forceinline__ void chunk_boundary(const FastCtx<SIDE>& c, SweepState<NS>& ss, int cc, int* abort_flag, int& tc,
+                                               bool exchange = true) {
   constexpr int NH = NS / 4, HL = 2 * exchange_frames<K, NS>() / NS;
   static_assert(HL * NS == 2 * exchange_frames<K, NS>() && HL >= 1, "the halo must be whole lanes");
   const int hb = cc & 1, NW = c.NW, w = c.w, lane = c.lane;
   LaneState<NS>& st = ss.st;
-  if (w + 1 < NW && lane >= 32 - HL) {
+  if (exchange && w + 1 < NW && lane >= 32 - HL) {
     const int slot = (hb * NWMAX + w) * HL + (lane - (32 - HL));
 #pragma unroll
     for (int h = 0; h < NH; ++h)
@@ -628,7 +629,7 @@ __device__ __forceinline__ void chunk_boundary(const FastCtx<SIDE>& c, SweepStat
 #endif
   named_bar_sync(bar_chunk(SIDE), (NW + kReducers) * 32);
   B200CTC_TRACE_EVENT(tc, 31);
-  if (w > 0 && lane < HL) {
+  if (exchange && w > 0 && lane < HL) {
     const int slot = (hb * NWMAX + (w - 1)) * HL + lane;
 #pragma unroll
     for (int h = 0; h < NH; ++h) {
@@ -894,9 +895,11 @@ __device__ void fast_side_sweep(const CallParams& p, int b, const UttMeta& m, co
     B200CTC_TRACE_EVENT(tc, 13);
     run_chunk<K, true, SIDE, NT, NS>(c, ss, rs, par, par, n0, kc, write_post);
     B200CTC_TRACE_EVENT(tc, 14);
-    chunk_boundary<K, NWMAX, SIDE, NS>(c, ss, xc, abort_flag, tc);
+    // the barrier with the helpers is per chunk; the halo is good for KX frames after an exchange
+    const bool exchange = (k2 + 1) % (KX / K) == 0;
+    chunk_boundary<K, NWMAX, SIDE, NS>(c, ss, xc, abort_flag, tc, exchange);
     rs = (rs + 1) & (RCH - 1);
-    ++xc;
+    xc += exchange ? 1 : 0;
   }
   B200CTC_TRACE_EVENT(tc, 15);
 }
