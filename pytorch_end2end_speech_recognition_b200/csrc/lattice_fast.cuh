@@ -21,7 +21,7 @@
 // of the two sides makes the stored values of one side load as ready-made pairs on the other.
 //
 // Schedule.  One CTA per utterance, 2*(NWMAX+K) warps.  Per side: NW lattice warps (forward: alpha,
-// t = 0,1,..; backward: beta on the reversed label sequence, t = T-1,T-2,..) and K reducer warps.
+// t = 0,1,..; backward: beta on the reversed label sequence, t = T-1,T-2,..) and K helper warps.
 // Phase 1: each side covers half of the frames and stores its pre-emission values to the scratch.
 // Phase 2 (after one CTA barrier): each side continues through the other half, multiplies its fresh
 // values with the stored ones of the opposite side -- posterior(t,s) = alpha_t(s) * beta'_t(s) / P --
@@ -33,13 +33,16 @@
 // Sequential depth is T frames instead of 2T, only half of alpha and beta ever goes through HBM, and
 // nothing but the recursion itself is on the critical path.
 //
-// Lattice layout.  Lane l of warp w holds positions base_w + 8l .. +7, base_w = w*(256-2K):
-// consecutive warp windows overlap by a halo of 2K positions (one lane for K = 4).  Dependencies only
-// point downwards (s-1, s-2), so a warp can run K frames without talking to its neighbour while the
-// garbage creeping up from its window bottom stays inside the halo; every K frames ("chunk") the
-// lattice warps of a side exchange halos through shared memory -- ONE named barrier per K frames.
-// Neighbour states inside a warp travel by __shfl_up.  The emission rows and the opposite side's
-// stored records of chunk c+1 are fetched with cp.async while chunk c computes.
+// Lattice layout.  Lane l of warp w holds positions base_w + 8l .. +7, base_w = w*(256-2*KX):
+// consecutive warp windows overlap by a halo of 2*KX positions (KX = 16 frames, four lanes).  Dependencies
+// only point downwards (s-1, s-2), so a warp can run KX frames without talking to its neighbour while
+// the garbage creeping up from its window bottom stays inside the halo; every KX frames the lattice
+// warps of a side exchange halo lanes through shared memory.  K = 4 frames ("chunk") is the granularity
+// of the shared-memory buffers: phase 1 runs KX/K chunks between two named barriers, phase 2 meets its
+// helper warps at one named barrier per chunk (posterior hand-off) and exchanges halos at every fourth.
+// Neighbour states inside a warp travel by __shfl_up.  The emission rows (cp.async, two exchanges ahead)
+// and the opposite side's stored records of chunk c+1 (TMA bulk copies) are fetched by the helper warps
+// while chunk c computes.
 #pragma once
 
 #include "lattice_common.cuh"
