@@ -211,19 +211,12 @@ __host__ __device__ inline int frame_block_bytes(int L) {
   const int JG = (2 * L + 1 + NS - 1) / NS;
   return (NS / 4) * JG * 16 + ((JG + 3) & ~3) * 4;
 }
-// Symbol-sorted posterior row: every symbol of the label sequence owns whole rows of C slots.  C is chosen
-// so that a symbol occurring twice as often as the average still fits ONE row: the reducers' straight-line
-// path needs one row per symbol, and an utterance on the multi-row path takes ~10 % longer (in the C3
-// batch the utterances with 290..350 labels, a symbol count of 21..23 against C = 20, finished last).
-__host__ __device__ inline int post_row_width(int L, int V) {
+// Symbol-sorted posterior row: the label posteriors of a frame grouped by symbol (label i sits at its rank
+// in (symbol, position) order), every symbol's group padded to a multiple of four slots so that the
+// reducers read it with LDS.128.  The padding slots are never written and stay zero.
+__host__ __device__ inline int post_label_slots(int L, int V) {
   const int n_sym = L < V - 1 ? L : V - 1;
-  const int avg = n_sym > 0 ? (L + n_sym - 1) / n_sym : 1;
-  const int want = 2 * avg + 2;
-  return want <= 4 ? 4 : want <= 12 ? 12 : want <= 20 ? 20 : 28;  // odd number of 16-byte chunks: conflict-free LDS.128
-}
-__host__ __device__ inline int post_rows_max(int L, int V) {
-  const int n_sym = L < V - 1 ? L : V - 1;
-  return L / post_row_width(L, V) + n_sym + 1;
+  return (L + 3 * n_sym + 3) & ~3;
 }
 
 struct FastSideSmem {
@@ -234,13 +227,12 @@ struct FastSideSmem {
   int* halo_e;      // [2][NWMAX][HL]
   float* red_m;     // [NWMAX]
   int* red_e;       // [NWMAX]
-  float* rowsum;    // [kReducers][Rmax+4]     reducer scratch (symbols spanning several rows)
   unsigned long long* mbar;   // [kReducers]   one mbarrier per helper warp (TMA bulk copies of the records)
 };
 
 template <int NWMAX>
 __host__ __device__ inline int post_stride(int L, int V) {  // floats per frame in the post buffer
-  return post_row_width(L, V) * post_rows_max(L, V) + NWMAX * 32 + 4;
+  return post_label_slots(L, V) + NWMAX * 32 + 4;
 }
 
 template <int K, int NWMAX, int NS>
@@ -255,13 +247,12 @@ __host__ __device__ inline size_t fast_side_bytes(int L, int RW, int V) {
   b += 2 * (size_t)K * post_stride<NWMAX>(L, V) * 4;         // post
   b += (size_t)2 * NWMAX * HL * 4;                           // halo_e
   b += NWMAX * 8;                                            // red
-  b += (size_t)kReducers * (post_rows_max(L, V) + 4) * 4;    // rowsum (one per reducer warp)
   b += (size_t)kReducers * 8 + 8;                            // mbar
   return (b + 15) / 16 * 16;
 }
 template <int K, int NWMAX, int NS>
 __host__ __device__ inline size_t fast_smem_bytes(int L, int RW, int V) {
-  // control words, lab, sorted, seg_start, seg_sym, slot_of_label, row_start
+  // control words, lab, sorted, seg_start, seg_sym, slot_of_label, seg_slot
   size_t common = (size_t)(16 + 6 * L + 16) * 4;
   common = (common + 15) / 16 * 16;
   return common + 2 * fast_side_bytes<K, NWMAX, NS>(L, RW, V) + 16;
@@ -281,7 +272,6 @@ __device__ __forceinline__ FastSideSmem carve_fast_side(unsigned char* base, int
   s.halo_e = reinterpret_cast<int*>(p);    p += (size_t)2 * NWMAX * HL * 4;
   s.red_m = reinterpret_cast<float*>(p);   p += NWMAX * 4;
   s.red_e = reinterpret_cast<int*>(p);     p += NWMAX * 4;
-  s.rowsum = reinterpret_cast<float*>(p);  p += (size_t)kReducers * (post_rows_max(L, V) + 4) * 4;
   p = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(p) + 7) / 8 * 8);
   s.mbar = reinterpret_cast<unsigned long long*>(p);
   return s;
@@ -293,8 +283,8 @@ struct FastCommon {
   int* lab;            // [L]
   SymbolIndex ix;      // sorted / seg_start / seg_sym / n_seg
   int* slot_of_label;  // [L]    slot of label i in the symbol-sorted posterior row
-  int* row_start;      // [n_seg+1] first row of every symbol segment
-  int* n_rows;         // total rows R
+  int* seg_slot;       // [n_seg+1] first slot of every symbol's group in the posterior row (a multiple of 4)
+  int* max_n4;         // the largest group, in 16-byte chunks
 };
 
 // named barrier ids (0 is __syncthreads)
@@ -910,23 +900,16 @@ __device__ void fast_side_sweep(const CallParams& p, int b, const UttMeta& m, co
 // ---------------------------------------------------------------------------------------------
 // helper warps of one side: prefetch for the lattice warps; per-symbol occupancy of every phase-2 frame, gradient rows
 // ---------------------------------------------------------------------------------------------
-template <int C4>
-__device__ __forceinline__ float post_row_sum(const float4* __restrict__ row4) {
-  float4 v[C4];
-#pragma unroll
-  for (int q = 0; q < C4; ++q) v[q] = row4[q];        // all loads in flight before the first add
+// Sum of one symbol's group of the posterior row: n4 16-byte chunks starting at row4.  Every lane of the
+// warp runs max_n4 (warp-uniform) iterations; chunks past the lane's own group read as zero.  Fixed order.
+__device__ __forceinline__ float post_group_sum(const float4* __restrict__ row4, int n4, int max_n4) {
   float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
-#pragma unroll
-  for (int q = 0; q < C4; ++q) { a0 += v[q].x; a1 += v[q].y; a2 += v[q].z; a3 += v[q].w; }
-  return (a0 + a1) + (a2 + a3);
-}
-__device__ __forceinline__ float post_row_sum_c4(const float4* __restrict__ row4, int C4) {   // C4 is warp-uniform
-  switch (C4) {
-    case 1: return post_row_sum<1>(row4);
-    case 3: return post_row_sum<3>(row4);
-    case 5: return post_row_sum<5>(row4);
-    default: return post_row_sum<7>(row4);
+#pragma unroll 4
+  for (int r = 0; r < max_n4; ++r) {
+    const float4 v = r < n4 ? row4[r] : make_float4(0.f, 0.f, 0.f, 0.f);
+    a0 += v.x; a1 += v.y; a2 += v.z; a3 += v.w;
   }
+  return (a0 + a1) + (a2 + a3);
 }
 
 // Sum over the warp of values in [0, 1] whose total is an occupancy (<= 1): one REDUX on Q30 fixed point
@@ -940,9 +923,9 @@ __device__ __forceinline__ float warp_sum_q30(float v) {
 // of its gradient row.
 template <int NWMAX>
 __device__ __forceinline__ void reduce_frame(const CallParams& p, const FastCommon& cm, const float* __restrict__ post,
-                                             const float* __restrict__ yrow, float* __restrict__ grow, float* rowsum,
-                                             int RC, int NW, int C4, int R, int n_seg, bool one_row, int sym_first,
-                                             int lane) {
+                                             const float* __restrict__ yrow, float* __restrict__ grow,
+                                             int RC, int NW, int n_seg, int max_n4, const int (&base4)[2], const int (&n4)[2],
+                                             const int (&sym)[2], int lane) {
   const float4* post4 = reinterpret_cast<const float4*>(post);
   const bool gathered = p.gathered != 0;
   // blank: partial sums of the lattice threads
@@ -950,43 +933,31 @@ __device__ __forceinline__ void reduce_frame(const CallParams& p, const FastComm
 #pragma unroll
   for (int i = 0; i < NWMAX; ++i)
     if (i < NW) accb += post[RC + i * 32 + lane];
-  if (one_row && n_seg <= 32 && !gathered) {
-    // the common small-vocabulary case, straight line: lane u owns symbol u's single row
-    float tot = 0.f, y = 0.f;
-    if (lane < n_seg) {
-      tot = post_row_sum_c4(post4 + (size_t)lane * C4, C4);
-      y = yrow[sym_first];
-    }
+  if (n_seg <= 64 && !gathered) {
+    // small vocabularies, straight line: lane u owns symbols u and u + 32 (their groups are in registers)
+    const float tot0 = post_group_sum(post4 + base4[0], n4[0], max_n4);
+    const float y0 = lane < n_seg ? yrow[sym[0]] : 0.f;
     const float yb = yrow[p.blank];
+    float tot1 = 0.f, y1 = 0.f;
+    if (n_seg > 32) {
+      tot1 = post_group_sum(post4 + base4[1], n4[1], max_n4);
+      y1 = lane + 32 < n_seg ? yrow[sym[1]] : 0.f;
+    }
     accb = warp_sum_q30(accb);
-    if (lane < n_seg) grow[sym_first] = y - tot;       // the touched symbols of a frame share one 128-byte row
+    if (lane < n_seg) grow[sym[0]] = y0 - tot0;        // the touched symbols of a frame share one or two 128-byte rows
+    if (lane + 32 < n_seg) grow[sym[1]] = y1 - tot1;
     if (lane == 0) grow[p.blank] = yb - accb;
     return;
   }
-  if (one_row) {
-    for (int u0 = 0; u0 < n_seg; u0 += 32) {
-      const int u = u0 + lane;
-      if (u < n_seg) {
-        const float tot = post_row_sum_c4(post4 + (size_t)u * C4, C4);
-        const int sym = u0 == 0 ? sym_first : cm.ix.seg_sym[u];
-        if (!gathered) grow[sym] = yrow[sym] - tot;      // the touched symbols of a frame share one 128-byte row
-        else atomicAdd(grow + sym, -tot);
-      }
+  for (int u0 = 0; u0 < n_seg; u0 += 32) {
+    const int u = u0 + lane;
+    const int s0 = u < n_seg ? cm.seg_slot[u] : 0, s1 = u < n_seg ? cm.seg_slot[u + 1] : 0;
+    const float tot = post_group_sum(post4 + (s0 >> 2), (s1 - s0) >> 2, max_n4);
+    if (u < n_seg) {
+      const int sy = cm.ix.seg_sym[u];
+      if (!gathered) grow[sy] = yrow[sy] - tot;
+      else atomicAdd(grow + sy, -tot);
     }
-  } else {
-    for (int r0 = 0; r0 < R; r0 += 32) {
-      const int r = r0 + lane;
-      if (r < R) rowsum[r] = post_row_sum_c4(post4 + (size_t)r * C4, C4);
-    }
-    __syncwarp();
-    for (int u = lane; u < n_seg; u += 32) {
-      float tot = 0.f;
-      for (int r = cm.row_start[u]; r < cm.row_start[u + 1]; ++r) tot += rowsum[r];
-      const int sym = cm.ix.seg_sym[u];
-      if (!gathered) grow[sym] = yrow[sym] - tot;
-      else atomicAdd(grow + sym, -tot);
-    }
-    __syncwarp();
   }
   accb = warp_sum_q30(accb);
   if (lane == 0) {
@@ -1063,11 +1034,15 @@ __device__ void fast_side_helper(const CallParams& p, int b, const UttMeta& m, c
   }
   const bool reduce = p.grads != nullptr && B200CTC_ABLATE != 9;   // ablation 9: helpers do not reduce (timing only)
 
-  const int C4 = post_row_width(c.L, V) / 4;          // 16-byte chunks per row
-  const int R = *cm.n_rows, n_seg = *cm.ix.n_seg;
-  const bool one_row = (R == n_seg);                  // every symbol fits one row: row index == segment index
-  const int sym_first = lane < n_seg ? cm.ix.seg_sym[lane] : 0;
-  float* rowsum = c.sm.rowsum + (size_t)hj * (post_rows_max(c.L, V) + 4);
+  const int n_seg = *cm.ix.n_seg, max_n4 = *cm.max_n4;
+  int sym[2], base4[2], n4[2];                        // this lane's symbol groups (u = lane, lane + 32)
+#pragma unroll
+  for (int i = 0; i < 2; ++i) {
+    const int u = lane + 32 * i;
+    sym[i] = u < n_seg ? cm.ix.seg_sym[u] : 0;
+    base4[i] = u < n_seg ? cm.seg_slot[u] >> 2 : 0;
+    n4[i] = u < n_seg ? (cm.seg_slot[u + 1] - cm.seg_slot[u]) >> 2 : 0;
+  }
 
   // ================================ phase 2 ================================
   int k2 = 0;
@@ -1085,8 +1060,7 @@ __device__ void fast_side_helper(const CallParams& p, int b, const UttMeta& m, c
       const int n = n0 - K + hj;
       reduce_frame<NWMAX>(p, cm, c.sm.post + (size_t)((par ^ 1) * K + hj) * c.PS,
                           c.sm.rows + (size_t)(((cc - 1) & (RCH - 1)) * K + hj) * c.RWS,
-                          p.grads + ((long long)c.frame_of(n) * p.B + b) * V, rowsum, c.RC, NW, C4, R, n_seg,
-                          one_row, sym_first, lane);
+                          p.grads + ((long long)c.frame_of(n) * p.B + b) * V, c.RC, NW, n_seg, max_n4, base4, n4, sym, lane);
     }
     B200CTC_TRACE_EVENT(tc, 9);
     cp_async_wait<1>();
@@ -1102,8 +1076,7 @@ __device__ void fast_side_helper(const CallParams& p, int b, const UttMeta& m, c
     if (n0 + hj < T)
       reduce_frame<NWMAX>(p, cm, c.sm.post + (size_t)(par * K + hj) * c.PS,
                           c.sm.rows + (size_t)(((cc - 1) & (RCH - 1)) * K + hj) * c.RWS,
-                          p.grads + ((long long)c.frame_of(n0 + hj) * p.B + b) * V, rowsum, c.RC, NW, C4, R, n_seg,
-                          one_row, sym_first, lane);
+                          p.grads + ((long long)c.frame_of(n0 + hj) * p.B + b) * V, c.RC, NW, n_seg, max_n4, base4, n4, sym, lane);
   }
   cp_async_wait<0>();
 }
@@ -1129,13 +1102,13 @@ __device__ void lattice_fast_utterance(const CallParams& p, int b, unsigned char
   int* ip = reinterpret_cast<int*>(smem);
   cm.abort_flag = ip;            ip += 8;
   cm.ix.n_seg = ip;              ip += 4;
-  cm.n_rows = ip;                ip += 4;
+  cm.max_n4 = ip;                ip += 4;
   cm.lab = ip;                   ip += L;
   cm.ix.sorted = ip;             ip += L;
   cm.ix.seg_start = ip;          ip += L + 1;
   cm.ix.seg_sym = ip;            ip += L + 1;
   cm.slot_of_label = ip;         ip += L;
-  cm.row_start = ip;             ip += L + 2;
+  cm.seg_slot = ip;              ip += L + 2;
   size_t common = (size_t)(reinterpret_cast<unsigned char*>(ip) - smem);
   common = (common + 15) / 16 * 16;
   const int RW = p.gathered ? m.W : (p.V + 3) / 4 * 4;
@@ -1158,25 +1131,28 @@ __device__ void lattice_fast_utterance(const CallParams& p, int b, unsigned char
   }
   __syncthreads();
   build_symbol_index(cm.lab, L, p.V, cm.ix);
-  // rows of the symbol-sorted posterior layout: segment u owns ceil(count_u / C) rows of C slots
+  // slots of the symbol-sorted posterior layout: the group of segment u starts at seg_slot[u] (padded to 4)
   {
-    const int C = post_row_width(L, p.V);
     const int n_seg = *cm.ix.n_seg;
     if (warp == 0) {
-      int base = 0;
+      int base = 0, mx = 0;
       for (int u0 = 0; u0 < n_seg; u0 += 32) {
         const int u = u0 + lane;
-        const int rows = (u < n_seg) ? (cm.ix.seg_start[u + 1] - cm.ix.seg_start[u] + C - 1) / C : 0;
-        int incl = rows;
+        const int cnt = (u < n_seg) ? cm.ix.seg_start[u + 1] - cm.ix.seg_start[u] : 0;
+        const int pad = (cnt + 3) & ~3;
+        mx = max(mx, cnt);
+        int incl = pad;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
           const int v = __shfl_up_sync(0xffffffffu, incl, o);
           if (lane >= o) incl += v;
         }
-        if (u < n_seg) cm.row_start[u] = base + incl - rows;
+        if (u < n_seg) cm.seg_slot[u] = base + incl - pad;
         base += __shfl_sync(0xffffffffu, incl, 31);
       }
-      if (lane == 0) { cm.row_start[n_seg] = base; *cm.n_rows = base; }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+      if (lane == 0) { cm.seg_slot[n_seg] = base; *cm.max_n4 = (mx + 3) >> 2; }
     }
     __syncthreads();
     for (int k = threadIdx.x; k < L; k += blockDim.x) {
@@ -1185,7 +1161,7 @@ __device__ void lattice_fast_utterance(const CallParams& p, int b, unsigned char
         const int mid = (lo + hi + 1) >> 1;
         if (cm.ix.seg_start[mid] <= k) lo = mid; else hi = mid - 1;
       }
-      cm.slot_of_label[cm.ix.sorted[k]] = cm.row_start[lo] * C + (k - cm.ix.seg_start[lo]);
+      cm.slot_of_label[cm.ix.sorted[k]] = cm.seg_slot[lo] + (k - cm.ix.seg_start[lo]);
     }
     __syncthreads();
   }
