@@ -821,15 +821,18 @@ __device__ void fast_side_sweep(const CallParams& p, int b, const UttMeta& m, co
 
   // ================================ phase 1 ================================
   // KX/K chunks between two halo exchanges (one barrier with the helpers per exchange)
+  // ... as ONE frame loop: the rows of the KX/K chunks are consecutive in the ring (an exchange interval
+  // starts at a multiple of KX/K chunk slots), and the band test applies to the whole interval (a warp that
+  // runs frames outside its band only writes records the reader never looks at, record_window).
   int cc = 0, xc = 0;
   for (int n0 = 0; n0 < M_side; ++xc) {
+    const int kc = min(KX, M_side - n0), nch = (kc + K - 1) / K;
     B200CTC_TRACE_EVENT(tc, 2);
-#pragma unroll 1
-    for (int sub = 0; sub < KX / K && n0 < M_side; ++sub, n0 += K, ++cc) {
-      run_chunk<K, false, SIDE, NT, NS>(c, ss, rs, 0, 0, n0, min(K, M_side - n0), false);
-      rs = (rs + 1) & (RCH - 1);
-    }
+    run_chunk<K, false, SIDE, NT, NS>(c, ss, rs, 0, 0, n0, kc, false);
     B200CTC_TRACE_EVENT(tc, 3);
+    rs = (rs + nch) & (RCH - 1);
+    n0 += kc;
+    cc += nch;
     chunk_boundary<K, NWMAX, SIDE, NS>(c, ss, xc, abort_flag, tc);
   }
 
