@@ -145,14 +145,10 @@ __device__ __forceinline__ f2 f2_pack(float lo, float hi) {
   return r;
 }
 __device__ __forceinline__ float f2_lo(f2 v) {
-  float a, b;
-  asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(v));
-  return a;
+  return __uint_as_float((unsigned)(v & 0xffffffffull));
 }
 __device__ __forceinline__ float f2_hi(f2 v) {
-  float a, b;
-  asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(v));
-  return b;
+  return __uint_as_float((unsigned)(v >> 32));
 }
 __device__ __forceinline__ f2 f2_add(f2 a, f2 b) {
   f2 r;
@@ -237,7 +233,6 @@ __host__ __device__ inline int post_stride(int L, int V) {  // floats per frame 
 
 template <int K, int NWMAX, int NS>
 __host__ __device__ inline size_t fast_side_bytes(int L, int RW, int V) {
-  const size_t NT = NWMAX * 32;
   constexpr int HL = 2 * exchange_frames<K, NS>() / NS;
   constexpr int RCH = kRowsRing * exchange_frames<K, NS>() / K;   // chunk slots of the emission-row ring
   size_t b = 0;
@@ -260,7 +255,6 @@ __host__ __device__ inline size_t fast_smem_bytes(int L, int RW, int V) {
 
 template <int K, int NWMAX, int NS>
 __device__ __forceinline__ FastSideSmem carve_fast_side(unsigned char* base, int L, int RW, int V) {
-  const size_t NT = NWMAX * 32;
   constexpr int HL = 2 * exchange_frames<K, NS>() / NS;
   constexpr int RCH = kRowsRing * exchange_frames<K, NS>() / K;
   FastSideSmem s;
@@ -802,7 +796,7 @@ __device__ void fast_side_sweep(const CallParams& p, int b, const UttMeta& m, co
   B200CTC_TRACE_EVENT(tc, 10);
 
   const SidePlan pl = side_plan<K, SIDE>(T);
-  const int M_side = pl.M_side, nc1 = pl.nc1, nc2 = pl.nc2;
+  const int M_side = pl.M_side, nc2 = pl.nc2;
   int* abort_flag = cm.abort_flag;
 
   // the all-zero frame block (stands in for records the other side never wrote)
@@ -977,7 +971,6 @@ template <int K, int NWMAX, int SIDE, int NS>
 __device__ void fast_side_helper(const CallParams& p, int b, const UttMeta& m, const FastCommon& cm,
                                  unsigned char* side_smem, int hj, int lane) {
   static_assert(kReducers == K, "one helper warp per frame of a chunk");
-  constexpr int NT = NWMAX * 32;
   FastCtx<SIDE> c;
   fill_ctx<K, NWMAX, SIDE, NS>(c, p, b, m, side_smem, NWMAX + hj, lane);
   const int T = c.T, NW = c.NW, V = p.V;

@@ -233,9 +233,11 @@ def test_every_short_length_and_chunk_tail():
             check(acts, np.concatenate([lab, lab]), [T, T], [len(lab), len(lab)])
 
 
-@pytest.mark.parametrize("L", [127, 128, 251, 252, 375, 376, 499])
+@pytest.mark.parametrize("L", [127, 128, 239, 240, 351, 352, 463, 464, 499])
 def test_lattice_window_boundaries(L):
-    """Label lengths at which the number of 256-state lattice windows per sweep changes (1..4 warps)."""
+    """Label lengths at which the number of 256-state lattice windows per sweep changes (1..4 warps; windows
+    overlap by 32 states, so a sweep of n windows holds 224 n + 32 states) and, from 464, the first lengths
+    that no longer fit four windows and take the safe lattice."""
     rng = np.random.RandomState(L)
     V = 30
     lab = _seq(rng, L, V)
@@ -243,6 +245,32 @@ def test_lattice_window_boundaries(L):
     acts = rng.randn(T, 2, V).astype(np.float32)
     lab2 = _seq(rng, L // 2, V)
     check(acts, np.concatenate([lab, lab2]), [T, T - 17], [L, len(lab2)], oracle="cpp")
+    assert ctc_mod.last_fallbacks() == (0, 0)
+
+
+@pytest.mark.parametrize("V,L", [(30, 200), (62, 75), (100, 180), (128, 120)])
+def test_symbol_group_reduce_paths(V, L):
+    """The reducers hold one or two symbol groups per lane (up to 32 / 64 distinct symbols) and loop beyond
+    that; V = 100 and 128 exercise the loop without the large-vocabulary gathered mode (V >= 129)."""
+    rng = np.random.RandomState(V * 1000 + L)
+    lab = rng.randint(1, V, size=L)
+    T = L + ctc_ref.count_repeats(lab) + 30
+    acts = rng.randn(T, 2, V).astype(np.float32)
+    lab2 = rng.randint(1, V, size=L // 3)
+    check(acts, np.concatenate([lab, lab2]), [T, T - 9], [L, len(lab2)], oracle="cpp")
+    assert ctc_mod.last_fallbacks() == (0, 0)
+
+
+def test_skewed_symbol_distribution():
+    """Real transcripts are skewed (space, 'e', 't'): one symbol carries 60 % of the labels, so its group in
+    the symbol-sorted posterior row is ~40 times the size of the others."""
+    rng = np.random.RandomState(77)
+    V, L = 30, 300
+    lab = np.where(rng.rand(L) < 0.6, 5, rng.randint(1, V, size=L)).astype(np.int64)
+    T = L + ctc_ref.count_repeats(lab) + 60
+    acts = rng.randn(T, 2, V).astype(np.float32)
+    lab2 = np.full(40, 7, dtype=np.int64)                     # a single symbol repeated: every label needs a blank
+    check(acts, np.concatenate([lab, lab2]), [T, T - 5], [L, len(lab2)], oracle="cpp")
     assert ctc_mod.last_fallbacks() == (0, 0)
 
 
