@@ -350,7 +350,12 @@ def main():
     # of the pinned logits and its own D2H read of the loss inside the timed loop.  The copy is split in two
     # halves on two copy streams: one stream moves a 12 MB pinned buffer at 17-28 GB/s on this box, two
     # concurrent copies at 53-55 GB/s (PCIe gen5 x16; tools/h2d_bandwidth.py).
-    pinned = [a.pin_memory() for a in acts_host]
+    # one pinned allocation for all rotating host buffers: separate pin_memory() calls gave one buffer out of
+    # fourteen that copies 2-6x slower than the others on this box (tools/pinned_probe.py)
+    pinned_all = torch.empty((len(acts_host),) + tuple(acts_host[0].shape), dtype=acts_host[0].dtype).pin_memory()
+    for i, a in enumerate(acts_host):
+        pinned_all[i].copy_(a)
+    pinned = [pinned_all[i] for i in range(len(acts_host))]
     stage = [torch.empty_like(a) for a in acts_dev[:2]]
     h2d = acts_bytes + wl.labels.nbytes + wl.act_lens.nbytes + wl.label_lens.nbytes
     e2e_loss = []
@@ -412,9 +417,9 @@ def main():
 
     for d in (0, 1):
         consumed[d].record(compute_stream)
-    e2e_run(3, 0)
+    e2e_run(n_rot + 2, 0)                     # warm-up: every rotating host buffer has been copied once
     torch.cuda.synchronize()
-    e2e_ms = timed(lambda i: e2e_run(args.steps, 4) if i == 0 else None, 1) / args.steps
+    e2e_ms = timed(lambda i: e2e_run(args.steps, n_rot + 2) if i == 0 else None, 1) / args.steps
     if e2e_debug is not None and rank == 0:
         print("e2e host us per step:", " ".join("%.0f" % x for x in e2e_debug), file=sys.stderr)
     e2e = {"value": frames * world / (e2e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": int(h2d),
@@ -429,7 +434,7 @@ def main():
                    "utterances_per_sec": wl.B * world / (ms_per_step * 1e-3),
                    "l2": "rotating %d acts/grads buffer sets (%.0f MB > L2)" % (n_rot, 2 * n_rot * acts_bytes / 1e6),
                    "parallelism": "utterance-sharded dp%d, scalar loss all-reduce" % world},
-        "roofline": roofline, "e2e": e2e, "gpu_launches": 3 * args.steps, "clocks": clocks,
+        "roofline": roofline, "e2e": e2e, "gpu_launches": 2 * args.steps, "clocks": clocks,
     }
     if rank == 0 and not args.no_cpu_baseline and world == 1:
         out["cpu_baseline"] = cpu_baseline(wl, acts_host[0].numpy())
