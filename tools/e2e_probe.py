@@ -39,10 +39,6 @@ def main():
             print("split %d  kernels concurrently: %-5s  slowest part %.3f ms (median)  wall per iteration %.3f ms"
                   % (nsplit, with_kernel, float(np.median(durs)), wall))
 
-if __name__ == "__main__":
-    main()
-
-
 def host_cost():
     """Host time of one ctc_loss_and_grad call (enqueue only; the GPU is idle when the call starts)."""
     dev = torch.device("cuda", 0)
@@ -59,5 +55,8 @@ def host_cost():
         print("%s: host time per call (enqueue) median %.1f us" % (key, 1e6 * float(np.median(ts))))
 
 
-if __name__ == "__main__" and "--host" in sys.argv:
-    host_cost()
+if __name__ == "__main__":
+    if "--host" in sys.argv:
+        host_cost()
+    else:
+        main()
