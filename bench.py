@@ -66,6 +66,7 @@ class ClockSampler(threading.Thread):
         self.index = index
         self.stop_flag = threading.Event()
         self.active = threading.Event()          # set while the timed region runs: only those samples count
+        self.ready = threading.Event()           # NVML is initialised and has answered once (its start-up is slow)
         self.sm, self.reasons, self.sm_max = [], set(), None
 
     def run(self):
@@ -80,6 +81,8 @@ class ClockSampler(threading.Thread):
                 getattr(pynvml, "nvmlClocksThrottleReasonSwThermalSlowdown", 0x20): "sw_thermal_slowdown",
                 getattr(pynvml, "nvmlClocksThrottleReasonSwPowerCap", 0x4): "sw_power_cap",
             }
+            pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM)
+            self.ready.set()
             while not self.stop_flag.is_set():
                 if self.active.is_set():
                     self.sm.append(pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM))
@@ -92,6 +95,7 @@ class ClockSampler(threading.Thread):
                         pass
                 time.sleep(0.001)
         except Exception:
+            self.ready.set()
             self._smi()
 
     def _smi(self):
@@ -294,13 +298,18 @@ def main():
             ms = float(t[0])
         return ms
 
-    for i in range(max(args.warmup, 3)):
-        step(i)
     sampler = ClockSampler(local_rank)
     sampler.start()
-    time.sleep(0.05)                          # NVML is initialised before the timed region starts
+    sampler.ready.wait(timeout=5.0)           # NVML start-up (slow, worse with eight ranks) stays out of the timed region
+    # warm-up: W steps as asked; with several ranks at least 20, so that the first NCCL launches and the rank
+    # skew after process start-up are behind us when the K timed steps begin
+    for i in range(max(args.warmup, 3 if world == 1 else 20)):
+        step(i)
+    drain()
     sampler.active.set()
+    t_host0 = time.perf_counter()
     ms = timed(step, args.steps)
+    host_ms_per_step = (time.perf_counter() - t_host0) * 1e3 / args.steps   # wall clock of the same loop (diagnostic)
     sampler.active.clear()
     n_in_region = len(sampler.sm)
     if n_in_region < 5:
@@ -435,12 +444,13 @@ def main():
 
     out = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
-        "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
+        "warmup": max(args.warmup, 3 if world == 1 else 20), "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": wl.name, "per_gpu_batch": wl.B, "frames_per_step_per_gpu": frames,
                    "utterances_per_sec": wl.B * world / (ms_per_step * 1e-3),
                    "l2": "rotating %d acts/grads buffer sets (%.0f MB > L2)" % (n_rot, 2 * n_rot * acts_bytes / 1e6),
                    "parallelism": "utterance-sharded dp%d, scalar loss all-reduce" % world},
+        "host": {"wall_ms_per_step": host_ms_per_step, "cpus": _host_threads()},
         "roofline": roofline, "e2e": e2e, "gpu_launches": 2 * args.steps, "clocks": clocks,
     }
     if rank == 0 and not args.no_cpu_baseline and world == 1:
