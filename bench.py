@@ -311,7 +311,18 @@ def main():
     ms = timed(step, args.steps)
     host_ms_per_step = (time.perf_counter() - t_host0) * 1e3 / args.steps   # wall clock of the same loop (diagnostic)
     sampler.active.clear()
+    def agree_min(n):
+        # every rank must take the same branch below: the extra steps contain collectives
+        if world == 1:
+            return n
+        t = torch.tensor([n], device=dev, dtype=torch.int32)
+        dist.all_reduce(t, op=dist.ReduceOp.MIN)
+        return int(t[0])
+
     n_in_region = len(sampler.sm)
+    if os.environ.get("B200CTC_TEST_CLOCK_SKEW") and rank == 0:
+        n_in_region = 0                       # test hook: one rank alone wants the fallback
+    n_in_region = agree_min(n_in_region)
     if n_in_region < 5:
         # The timed region lasts ~10 ms and the sampling thread rarely gets the interpreter while the main thread
         # enqueues: take the remaining samples from the main thread under the SAME load right after the timed
@@ -322,7 +333,7 @@ def main():
             sampler.sample_now()
         drain()
         torch.cuda.synchronize()
-    if not sampler.sm:
+    if agree_min(len(sampler.sm)) == 0:
         sampler.active.set()
         timed(step, max(args.steps, 200))
         sampler.active.clear()
