@@ -139,7 +139,7 @@ cudaError_t launch_lattice(const CallParams& p, int max_L, cudaStream_t stream) 
   const int nw = fast_warps_needed<kChunk, 8>(max_L);
   if (nw <= 1) return launch_lattice_t<kChunk, 1, 8>(p, max_L, stream);
   if (nw <= 2) return launch_lattice_t<kChunk, 2, 8>(p, max_L, stream);
-  return launch_lattice_t<kChunk, 4, 8>(p, max_L, stream);   // longer label sequences (L > 499) take the safe lattice
+  return launch_lattice_t<kChunk, 4, 8>(p, max_L, stream);   // longer label sequences (L > 463) take the safe lattice
 }
 
 #ifdef B200CTC_TRACE

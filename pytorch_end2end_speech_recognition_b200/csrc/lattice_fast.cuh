@@ -76,8 +76,7 @@ __device__ __forceinline__ void trace_event(int& cnt, int tag) {
 #endif
 constexpr int kAbortExtremeRow = 2;  // abort word: K1 flagged the utterance (nothing was written yet); 1 = redo after a lost range
 constexpr int kEZero = -(1 << 28);  // exponent of an all-zero lane
-constexpr int kRowsRing = 4;        // emission-row chunks in the ring: the reducers' one, this chunk, the next one (landed), the one after (in flight)
-constexpr int kOthRing = 8;         // per-thread ring of the opposite side's records: two chunks of K = 4 frames
+constexpr int kRowsRing = 4;        // emission-row ring, in halo-exchange intervals (KX/K chunks each): the reducers' one, the current one, the next (landed), the one after (in flight)
 constexpr int kReducers = 4;        // reducer warps per side: warp j takes frame j of every phase-2 chunk (== K)
 
 // ---------------------------------------------------------------------------------------------
@@ -987,8 +986,8 @@ __device__ void fast_side_helper(const CallParams& p, int b, const UttMeta& m, c
   }
   __syncwarp();
 
-  // Emission rows are staged TWO chunks ahead (ring slot = chunk & 3), so that the global-memory latency
-  // of a row never sits between the lattice warps and the chunk barrier.
+  // Emission rows are staged two barrier intervals ahead (ring slot = chunk & (RCH - 1)), so that the
+  // global-memory latency of a row never sits between the lattice warps and a barrier.
   constexpr int KX = exchange_frames<K, NS>(), M = KX / K, RCH = kRowsRing * M;
   const int nc1 = pl.nc1, n_chunks = pl.n_chunks;
   auto chunk_start = [&](int cc) { return cc < nc1 ? cc * K : M_side + (cc - nc1) * K; };
