@@ -123,3 +123,23 @@ def test_concatenate_labels_matches_the_reference_loop():
     assert b200.concatenate_labels(torch.tensor(ys), torch.tensor(y_lens)).tolist() == expect
     with pytest.raises(b200.B200CTCError):
         b200.concatenate_labels(ys, np.array([13, 0, 0, 0, 0, 0, 0]))
+
+
+def test_bench_roofline_inputs_are_readable():
+    """bench.py's roofline object reads the committed ncu traffic (profiles/r01_traffic.json) and the measured
+    peak; a format slip there would silently turn `roofline.traffic` into null."""
+    import importlib.util
+    import os
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    spec = importlib.util.spec_from_file_location("bench_module", os.path.join(root, "bench.py"))
+    bench = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bench)
+    traffic = bench.measured_traffic("C3")
+    assert isinstance(traffic, int) and 3e8 < traffic < 6e8        # DRAM bytes of one C3 lattice launch
+    assert bench.measured_traffic("C1") is None
+    peak, kind = bench.peaks()
+    assert 3000.0 < peak < 9000.0 and kind in ("measured", "fallback")
+    from pytorch_end2end_speech_recognition_b200 import workloads
+    wl = workloads.make_lengths_and_labels("C3")
+    total, strict, frames = workloads.algorithmic_bytes(wl)
+    assert frames == 102400 and strict < total < 7e8
