@@ -124,18 +124,7 @@ cudaError_t launch_lattice_t(const CallParams& p, int max_L, cudaStream_t stream
 
 cudaError_t launch_lattice(const CallParams& p, int max_L, cudaStream_t stream) {
   if (p.B == 0) return cudaSuccess;
-  // States per lane: eight (fewer instructions per lattice state); four states per lane with twice the
-  // lattice warps is kept as a tuning alternative (B200CTC_NS=4, label sequences up to 483).
-  int ns = 8;
-  if (const char* e = std::getenv("B200CTC_NS")) {
-    if (e[0] == '4' && fast_warps_needed<kChunk, 4>(max_L) <= 8) ns = 4;
-  }
-  if (ns == 4) {
-    const int nw = fast_warps_needed<kChunk, 4>(max_L);
-    if (nw <= 2) return launch_lattice_t<kChunk, 2, 4>(p, max_L, stream);
-    if (nw <= 4) return launch_lattice_t<kChunk, 4, 4>(p, max_L, stream);
-    return launch_lattice_t<kChunk, 8, 4>(p, max_L, stream);
-  }
+  // eight lattice states per lane; one, two or four 256-state windows per sweep
   const int nw = fast_warps_needed<kChunk, 8>(max_L);
   if (nw <= 1) return launch_lattice_t<kChunk, 1, 8>(p, max_L, stream);
   if (nw <= 2) return launch_lattice_t<kChunk, 2, 8>(p, max_L, stream);
