@@ -43,7 +43,7 @@
 extern "C" {
 #endif
 
-#define B200CTC_VERSION 100 /* 0.1.0 */
+#define B200CTC_VERSION 200 /* 0.2.0 */
 
 #if defined(__GNUC__)
 #define B200CTC_API __attribute__((visibility("default")))
@@ -80,6 +80,13 @@ B200CTC_API int b200ctc_get_workspace_size(const int* label_lens, const int* act
                                int T, int V, int B, size_t* bytes);
 
 /*
+ * Workspace bound from the shape alone (no length arrays): enough for any lengths with
+ * label_lens[b] <= max_label_len and act_lens[b] <= T.  This is the size the device-resident call
+ * b200ctc_loss_and_grad_dev needs; it is also valid for b200ctc_loss_and_grad.
+ */
+B200CTC_API int b200ctc_get_workspace_bound(int T, int V, int B, int max_label_len, size_t* bytes);
+
+/*
  * Replaces warp-ctc's compute_ctc_loss(activations, gradients, flat_labels,
  * label_lengths, input_lengths, alphabet_size, minibatch, costs, workspace,
  * options) as called by pytorch_binding's gpu_ctc
@@ -103,6 +110,11 @@ B200CTC_API int b200ctc_get_workspace_size(const int* label_lens, const int* act
  *   loss_sum    DEVICE fp32 [1] or NULL: sum_b costs[b] (ctc.py:50), fixed
  *               summation order.
  *   workspace   DEVICE, >= b200ctc_get_workspace_size bytes, 256-byte aligned.
+ *
+ * Limits: T * B rows, B * V * 4 < 2^31; label sequences of any length the fp64 safe lattice can hold in
+ * shared memory (about 4000 labels); longer ones return B200CTC_STATUS_UNSUPPORTED.
+ * A call whose lengths and labels equal those of the previous call on the same handle and stream reuses
+ * that call's plan (no planning, no host-to-device copy of the tables).
  */
 B200CTC_API int b200ctc_loss_and_grad(b200ctc_handle* handle,
                           const float* acts, int64_t acts_stride_t, int64_t acts_stride_b,
@@ -113,13 +125,38 @@ B200CTC_API int b200ctc_loss_and_grad(b200ctc_handle* handle,
                           void* workspace, size_t workspace_bytes, void* stream);
 
 /*
+ * The same evaluation with DEVICE-resident labels and lengths: the rewritten call site of
+ * models/pytorch_v3/ctc/ctc.py:294-326 keeps ys / x_lens / y_lens on the GPU, so
+ * nothing crosses PCIe and the host does no per-utterance work.  The call is kernel launches only
+ * (plan -> softmax rows -> lattice) and may be captured into a CUDA graph.
+ *
+ *   labels         DEVICE int32, utterance b's labels at labels[b*label_stride .. + label_lens[b])
+ *                  (a padded [B, Lmax] tensor with label_stride = Lmax, or a flat vector with equal strides)
+ *   label_lens     DEVICE int32 [B], 0 <= label_lens[b] <= max_label_len
+ *   act_lens       DEVICE int32 [B], 0 <= act_lens[b] <= T
+ *   max_label_len  host-side bound on label_lens (sizes shared memory and the workspace regions)
+ *   workspace      DEVICE, >= b200ctc_get_workspace_bound(T, V, B, max_label_len) bytes
+ *
+ * Inputs cannot be validated on the host: an utterance with a length out of range or a label outside
+ * [0,V) or equal to blank gets cost NaN and an all-zero gradient (b200ctc_get_last_fallbacks counts[2]).
+ * B <= 65536.
+ */
+B200CTC_API int b200ctc_loss_and_grad_dev(b200ctc_handle* handle,
+                              const float* acts, int64_t acts_stride_t, int64_t acts_stride_b,
+                              float* grads,
+                              const int* labels, int label_stride, const int* label_lens, const int* act_lens,
+                              int T, int V, int B, int max_label_len, int blank,
+                              float* costs, float* loss_sum,
+                              void* workspace, size_t workspace_bytes, void* stream);
+
+/*
  * Batched best-path decoder; replaces the numpy loops of
  * models/pytorch_v3/ctc/decoders/greedy_decoder.py:32-45 (per-frame argmax with
  * first-index tie break, collapse repeats, then drop blanks).
  *
  *   logits      DEVICE fp32, logical [B,T,V]; element (b,t,v) at
  *               logits[b*stride_b + t*stride_t + v].
- *   lens        DEVICE int32 [B] (x_lens), 0 <= lens[b] <= T.
+ *   lens        DEVICE int32 [B] (x_lens); values outside [0, T] are clamped to that range.
  *   out_tokens  DEVICE int32 [B,T]: hypothesis of utterance b in
  *               out_tokens[b*T .. b*T+out_lens[b]); the rest of the row is -1.
  *   out_lens    DEVICE int32 [B].
@@ -139,10 +176,13 @@ B200CTC_API int b200ctc_get_last_kernel_ms(b200ctc_handle* handle, float* ms3);
 /*
  * Diagnostics: number of utterances of the LAST call on this handle that were evaluated by the
  * fp64 safe lattice instead of the block-exponent fast lattice (counts[0]: flagged by the softmax
- * pass for extreme probabilities, counts[1]: the fast lattice lost range and was redone).
+ * pass for extreme probabilities, counts[1]: the fast lattice lost range and was redone), and
+ * counts[2]: utterances of a device-resident call with invalid lengths or labels.
  * Synchronises `stream`; the workspace of that call must still be alive.
  */
-B200CTC_API int b200ctc_get_last_fallbacks(b200ctc_handle* handle, int* counts2, void* stream);
+B200CTC_API int b200ctc_get_last_fallbacks(b200ctc_handle* handle, int* counts3, void* stream);
+/* Plan cache of b200ctc_loss_and_grad: calls that reused the previous call's plan / calls that planned. */
+B200CTC_API int b200ctc_get_plan_cache_stats(b200ctc_handle* handle, long long* hits, long long* misses);
 
 #ifdef __cplusplus
 }

@@ -16,7 +16,7 @@ CSRC = os.path.join(PKG_DIR, "csrc")
 LIB_DIR = os.path.join(PKG_DIR, "lib")
 LIB_PATH = os.environ.get("B200CTC_LIB") or os.path.join(LIB_DIR, "libb200ctc.so")   # B200CTC_LIB: developer variants
 
-SOURCES = ["api.cu", "softmax_rows.cu", "lattice.cu", "greedy.cu"]
+SOURCES = ["api.cu", "plan.cu", "softmax_rows.cu", "lattice.cu", "greedy.cu"]
 
 NVCC_FLAGS = [
     "-O3", "-std=c++17",
@@ -34,11 +34,26 @@ def _nvcc():
     return cand if os.path.exists(cand) else "nvcc"
 
 
-def _stale(target, deps):
+def _source_hash(deps, flags):
+    """Content hash of everything the library is built from (sources, header, flags): file times do not
+    survive the snapshot copy to the GPU box, contents do."""
+    import hashlib
+    h = hashlib.sha1(" ".join(flags).encode())
+    for d in sorted(deps):
+        h.update(os.path.basename(d).encode())
+        with open(d, "rb") as f:
+            h.update(f.read())
+    return h.hexdigest()
+
+
+def _stale(target, deps, flags=()):
     if not os.path.exists(target):
         return True
-    t = os.path.getmtime(target)
-    return any(os.path.getmtime(d) > t for d in deps)
+    try:
+        with open(target + ".srchash") as f:
+            return f.read().strip() != _source_hash(deps, flags)
+    except OSError:
+        return True
 
 
 def build_library(force=False, verbose=False, extra_flags=(), lib_path=None):
@@ -48,7 +63,7 @@ def build_library(force=False, verbose=False, extra_flags=(), lib_path=None):
     if lib_path is not None:
         return _build_variant(list(extra_flags), lib_path, verbose)
     deps = [os.path.join(CSRC, f) for f in os.listdir(CSRC)] + [os.path.join(REPO_DIR, "include", "b200ctc.h")]
-    if not force and not _stale(LIB_PATH, deps):
+    if not force and not _stale(LIB_PATH, deps, NVCC_FLAGS):
         return LIB_PATH
     objs = []
     for src in SOURCES:
@@ -62,6 +77,8 @@ def build_library(force=False, verbose=False, extra_flags=(), lib_path=None):
         objs.append(obj)
     cmd = [_nvcc(), "-shared", "-o", LIB_PATH] + objs + ["-Xcompiler", "-fPIC"]
     subprocess.run(cmd, check=True)
+    with open(LIB_PATH + ".srchash", "w") as f:
+        f.write(_source_hash(deps, NVCC_FLAGS))
     return LIB_PATH
 
 

@@ -28,7 +28,8 @@ struct UttMeta {
 struct CallParams {
   const float* acts;      // [T,B,V] logits, element (t,b,v) at acts[t*as_t + b*as_b + v]
   long long as_t, as_b;
-  float* grads;           // [T,B,V] contiguous or nullptr
+  float* grads;           // [T,B,V] contiguous or nullptr (cost only)
+  float* yrows;           // [T,B,V] where K1 leaves the softmax rows: == grads, or a workspace buffer in a cost-only call
   int T, B, V, blank;
   const UttMeta* meta;    // [B]
   const int* order;       // [B] utterances sorted by decreasing lattice work (longest first)
@@ -40,7 +41,13 @@ struct CallParams {
   unsigned char* scratch; // alpha/beta scratch
   float* costs;           // [B]
   float* loss_sum;        // [1] or nullptr
-  int gathered;           // 1: lattice reads emissions from `em`, 0: from the softmax rows in `grads`
+  int gathered;           // 1: lattice reads emissions from `em`, 0: from the softmax rows in `yrows`
+  int fast_l_cap;         // longest label sequence the block-exponent lattice takes (window count and shared-memory budget)
+  // device-resident call (b200ctc_loss_and_grad_dev): the tables above are produced by plan_kernel from these
+  const int* dev_label_lens;   // [B] or nullptr
+  const int* dev_act_lens;     // [B]
+  int label_stride;            // labels of utterance b start at labels + b * label_stride
+  int max_label_len;           // bound on label_lens (sizes the per-utterance workspace regions)
 };
 
 // Programmatic dependent launch (sm_90+): K1 lets the lattice kernel start while it is still running; the
@@ -51,15 +58,28 @@ __device__ __forceinline__ void pdl_wait_primary() { asm volatile("griddepcontro
 
 
 enum UttFlags : int {
-  FLAG_EXTREME_ROW = 1,   // some softmax probability of the utterance is below 2^-100: use the safe lattice
-  FLAG_PRECISION_LOST = 2 // the block-exponent lattice saw a live state lose range: redo with the safe lattice
+  FLAG_EXTREME_ROW = 1,    // some softmax probability of the utterance is below 2^-100: use the safe lattice
+  FLAG_PRECISION_LOST = 2, // the block-exponent lattice saw a live state lose range: redo with the safe lattice
+  FLAG_INVALID_INPUT = 4   // device-resident call: a label or a length of the utterance is out of range (cost NaN, zero gradient)
 };
 
 constexpr int kGroupBytes = 32;  // scratch bytes per (frame, group): the safe lattice stores 4 doubles
 
+// scratch units (32 bytes) per frame: the safe lattice stores 4 doubles per group of four states,
+// the fast lattice a little more than that for very short label sequences
+__host__ __device__ inline int groups_of(int L) {
+  const int j4 = (2 * L + 1 + 3) / 4, j8 = (2 * L + 1 + 7) / 8;
+  // fast lattice: 32 bytes of mantissas per group of eight states + an int32 exponent row padded to 4 groups
+  const int fast8 = (36 * j8 + 12 + 31) / 32;
+  return j4 > fast8 ? j4 : fast8;
+}
+__host__ __device__ inline int em_width_of(int L) { return (L + 1 + 3) / 4 * 4; }
+
 // host launchers (each in its own .cu)
 cudaError_t launch_softmax_rows(const CallParams& p, cudaStream_t stream);
+cudaError_t prepare_lattice(CallParams& p, int max_L);     // fills fast_l_cap; error when not even the safe lattice fits
 cudaError_t launch_lattice(const CallParams& p, int max_L, cudaStream_t stream);
+cudaError_t launch_plan(const CallParams& p, UttMeta* meta, int* order, int* flags, cudaStream_t stream);
 cudaError_t launch_greedy(const float* logits, long long stride_b, long long stride_t, const int* lens,
                           int T, int V, int B, int blank, int* out_tokens, int* out_lens,
                           cudaStream_t stream);

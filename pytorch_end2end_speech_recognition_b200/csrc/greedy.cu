@@ -46,7 +46,7 @@ __global__ void __launch_bounds__(256) frame_argmax_warp_kernel(
   const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (row >= (long long)B * T) return;
   const int b = (int)(row / T), t = (int)(row - (long long)b * T);
-  if (t >= lens[b]) return;
+  if (t >= min(lens[b], T)) return;
   const float* x = logits + b * stride_b + t * stride_t;
   unsigned long long best = 0ull;
   for (int v = lane; v < V; v += 32) best = umax64(best, argmax_key(__ldg(x + v), v));
@@ -61,7 +61,7 @@ __global__ void __launch_bounds__(256) frame_argmax_cta_kernel(
   __shared__ unsigned long long red[8];
   const long long row = blockIdx.x;
   const int b = (int)(row / T), t = (int)(row - (long long)b * T);
-  if (t >= lens[b]) return;
+  if (t >= min(lens[b], T)) return;
   const float* x = logits + b * stride_b + t * stride_t;
   const int tid = threadIdx.x;
   int head = (int)(((16 - ((uintptr_t)x & 15)) & 15) >> 2);
@@ -101,7 +101,7 @@ __global__ void __launch_bounds__(kCollapseThreads) collapse_kernel(
   __shared__ int base_s;
   const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   int* row = out_tokens + (long long)b * T;
-  const int n = lens[b];
+  const int n = min(max(lens[b], 0), T);   // a length outside [0, T] is clamped (the reference would raise IndexError)
   if (tid == 0) base_s = 0;
   __syncthreads();
   for (int t0 = 0; t0 < n; t0 += kCollapseThreads) {

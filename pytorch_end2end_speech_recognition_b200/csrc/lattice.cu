@@ -28,11 +28,11 @@ __global__ void __launch_bounds__(2 * (NWMAX + kReducers) * 32, 1) lattice_kerne
   }
 #endif
   if (!m.feasible) {  // K1 already zero-filled its gradient rows
-    if (threadIdx.x == 0) p.costs[b] = INFINITY;
+    if (threadIdx.x == 0) p.costs[b] = (p.flags[b] & FLAG_INVALID_INPUT) ? NAN : INFINITY;
   } else if (m.T == 0) {  // empty utterance with an empty target: probability one
     if (threadIdx.x == 0) p.costs[b] = 0.f;
   } else {
-    bool use_safe = fast_warps_needed<K, NS>(m.L) > NWMAX;
+    bool use_safe = m.L > p.fast_l_cap;   // too long for the lattice windows or for the shared-memory budget
     bool dirty = false;
     if (!use_safe) {
       // prologue (no K1 output needed), then wait for K1, then the sweeps -- unless K1 flagged an extreme row
@@ -86,21 +86,44 @@ __global__ void __launch_bounds__(2 * (NWMAX + kReducers) * 32, 1) lattice_kerne
   if (threadIdx.x == 0) *p.loss_sum = (float)part[0];
 }
 
-template <int K, int NWMAX, int NS>
-cudaError_t launch_lattice_t(const CallParams& p, int max_L, cudaStream_t stream) {
-  // longest label sequence the fast path's lattice window holds with NWMAX warps per side
+constexpr size_t kSmemBudget = 227 * 1024 - 6 * 1024;   // dynamic shared memory: 227 KB per CTA minus the kernel's static arrays (4.4 KB)
+
+// Launch geometry for a call whose longest feasible label sequence is max_L: the number of lattice windows
+// per sweep (template parameter NWMAX: 1, 2 or 4), the longest label sequence the block-exponent lattice
+// takes (l_cap: it must fit NWMAX windows AND the shared-memory budget -- in gathered mode the emission-row
+// ring grows with the label sequence, 256 * (L + 5) bytes per side), and the dynamic shared memory.
+// Longer utterances are evaluated by the fp64 safe lattice in the same launch.
+struct LatticeCfg {
+  int nwmax, l_cap;
+  size_t smem;
+};
+template <int NWMAX>
+size_t fast_bytes_at(const CallParams& p, int L) {
+  const int rw = p.gathered ? em_width_of(L) : (p.V + 3) / 4 * 4;
+  return fast_smem_bytes<kChunk, NWMAX, 8>(L, rw, p.V);
+}
+size_t fast_bytes(const CallParams& p, int nwmax, int L) {
+  return nwmax == 1 ? fast_bytes_at<1>(p, L) : (nwmax == 2 ? fast_bytes_at<2>(p, L) : fast_bytes_at<4>(p, L));
+}
+int round_nw(int nw) { return nw <= 1 ? 1 : (nw <= 2 ? 2 : 4); }
+
+cudaError_t lattice_cfg(const CallParams& p, int max_L, LatticeCfg* out) {
+  const size_t safe = safe_smem_bytes(max_L) > 256 * sizeof(double) ? safe_smem_bytes(max_L) : 256 * sizeof(double);
+  if (safe > kSmemBudget) return cudaErrorInvalidConfiguration;   // not even the safe lattice holds this label sequence
+  int nwmax = round_nw(fast_warps_needed<kChunk, 8>(max_L));
   int l_cap = max_L;
-  while (l_cap > 0 && fast_warps_needed<K, NS>(l_cap) > NWMAX) --l_cap;
-  const int rw = p.gathered ? (l_cap + 1 + 3) / 4 * 4 : (p.V + 3) / 4 * 4;
-  // the posterior row is not monotonic in L (its slot width steps): size for the worst L <= l_cap
-  size_t smem = 0;
-  for (int L = 0; L <= l_cap; ++L) {
-    const size_t s = fast_smem_bytes<K, NWMAX, NS>(L, rw, p.V);
-    smem = s > smem ? s : smem;
-  }
-  smem = smem > safe_smem_bytes(max_L) ? smem : safe_smem_bytes(max_L);
-  smem = smem > 256 * sizeof(double) ? smem : 256 * sizeof(double);   // the fused cost sum
-  if (smem > 227 * 1024) return cudaErrorInvalidConfiguration;
+  // shared memory is monotonic in L (and in the row width, which follows L in gathered mode)
+  while (l_cap > 0 && (fast_warps_needed<kChunk, 8>(l_cap) > nwmax || fast_bytes(p, nwmax, l_cap) > kSmemBudget)) --l_cap;
+  nwmax = round_nw(fast_warps_needed<kChunk, 8>(l_cap));
+  const size_t fast = fast_bytes(p, nwmax, l_cap);
+  out->nwmax = nwmax;
+  out->l_cap = fast <= kSmemBudget ? l_cap : -1;   // -1: every utterance takes the safe lattice
+  out->smem = (out->l_cap >= 0 && fast > safe) ? fast : safe;
+  return cudaSuccess;
+}
+
+template <int K, int NWMAX, int NS>
+cudaError_t launch_lattice_t(const CallParams& p, size_t smem, cudaStream_t stream) {
   if (smem > 48 * 1024) {
     cudaError_t e = cudaFuncSetAttribute(lattice_kernel<K, NWMAX, NS>,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -122,13 +145,22 @@ cudaError_t launch_lattice_t(const CallParams& p, int max_L, cudaStream_t stream
 
 }  // namespace
 
+cudaError_t prepare_lattice(CallParams& p, int max_L) {
+  LatticeCfg c;
+  cudaError_t e = lattice_cfg(p, max_L, &c);
+  if (e == cudaSuccess) p.fast_l_cap = c.l_cap;
+  return e;
+}
+
 cudaError_t launch_lattice(const CallParams& p, int max_L, cudaStream_t stream) {
   if (p.B == 0) return cudaSuccess;
+  LatticeCfg c;
+  cudaError_t e = lattice_cfg(p, max_L, &c);
+  if (e != cudaSuccess) return e;
   // eight lattice states per lane; one, two or four 256-state windows per sweep
-  const int nw = fast_warps_needed<kChunk, 8>(max_L);
-  if (nw <= 1) return launch_lattice_t<kChunk, 1, 8>(p, max_L, stream);
-  if (nw <= 2) return launch_lattice_t<kChunk, 2, 8>(p, max_L, stream);
-  return launch_lattice_t<kChunk, 4, 8>(p, max_L, stream);   // longer label sequences (L > 463) take the safe lattice
+  if (c.nwmax == 1) return launch_lattice_t<kChunk, 1, 8>(p, c.smem, stream);
+  if (c.nwmax == 2) return launch_lattice_t<kChunk, 2, 8>(p, c.smem, stream);
+  return launch_lattice_t<kChunk, 4, 8>(p, c.smem, stream);   // longer label sequences (L > 463) take the safe lattice
 }
 
 #ifdef B200CTC_TRACE

@@ -661,8 +661,8 @@ __device__ __forceinline__ void fill_ctx(FastCtx<SIDE>& c, const CallParams& p, 
   if (p.gathered) {
     row_src = p.em + m.em_off; row_stride = m.W; row_vec = 4; c.per_row = m.W / 4;
   } else {
-    row_src = p.grads + (long long)b * p.V; row_stride = (long long)p.B * p.V;
-    const uintptr_t a = reinterpret_cast<uintptr_t>(p.grads);
+    row_src = p.yrows + (long long)b * p.V; row_stride = (long long)p.B * p.V;
+    const uintptr_t a = reinterpret_cast<uintptr_t>(p.yrows);
     row_vec = (p.V % 4 == 0 && a % 16 == 0) ? 4 : ((p.V % 2 == 0 && a % 8 == 0) ? 2 : 1);
     c.per_row = p.V / row_vec;
   }

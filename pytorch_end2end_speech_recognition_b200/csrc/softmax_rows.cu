@@ -42,14 +42,15 @@ __global__ void __launch_bounds__(256) softmax_rows_warp_kernel(CallParams p) {
   constexpr int RPW = 32 / LPR;                       // rows per warp
   const int lane = threadIdx.x & 31;
   const int q = lane & (LPR - 1), sub = lane / LPR;
-  // grid: x over the mini-batch (RPW rows per warp, 8 warps per CTA), y = frame: no index division
-  const int t = blockIdx.y;
+  // grid: x over the mini-batch (RPW rows per warp, 8 warps per CTA), (y, z) = frame: no index division
+  const int t = blockIdx.y + blockIdx.z * 65535;
+  if (t >= p.T) return;
   int b = (blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * RPW + sub;
   const bool row_ok = b < p.B;
   if (!row_ok) b = p.B - 1;                           // keep the lane in the shuffles; it stores nothing
   const long long row = (long long)t * p.B + b;
   const int m_T = p.meta[b].T, m_feasible = p.meta[b].feasible;
-  float* grow = (p.grads && row_ok) ? p.grads + row * p.V : nullptr;
+  float* grow = (p.yrows && row_ok) ? p.yrows + row * p.V : nullptr;
   const bool live = t < m_T && m_feasible;
   const float* arow = p.acts + (long long)t * p.as_t + (long long)b * p.as_b;
   float x[NV];
@@ -156,7 +157,7 @@ __global__ void __launch_bounds__(kRowThreads) softmax_rows_cta_kernel(CallParam
   const UttMeta m = p.meta[b];
   const int V = p.V;
   const int tid = threadIdx.x;
-  float* grow = p.grads ? p.grads + row * V : nullptr;
+  float* grow = p.yrows ? p.yrows + row * V : nullptr;
 
   if (t >= m.T || !m.feasible) {
     if (grow) {
@@ -247,10 +248,10 @@ cudaError_t launch_softmax_rows(const CallParams& p, cudaStream_t stream) {
   if (n_rows == 0) return cudaSuccess;
   if (p.V <= 256) {
     const int warps = 8;
-    if (p.T > 65535) return cudaErrorInvalidConfiguration;
-    auto grid_for = [&](int rows_per_warp) {
+    auto grid_for = [&](int rows_per_warp) {     // frames on (y, z): T up to 65535^2
       const int per_cta = warps * rows_per_warp;
-      return dim3((unsigned)((p.B + per_cta - 1) / per_cta), (unsigned)p.T, 1);
+      const int ty = p.T < 65535 ? p.T : 65535;
+      return dim3((unsigned)((p.B + per_cta - 1) / per_cta), (unsigned)ty, (unsigned)((p.T + 65534) / 65535));
     };
     if (p.V <= 32) softmax_rows_warp_kernel<8, 4><<<grid_for(4), warps * 32, 0, stream>>>(p);
     else if (p.V <= 64) softmax_rows_warp_kernel<16, 4><<<grid_for(2), warps * 32, 0, stream>>>(p);

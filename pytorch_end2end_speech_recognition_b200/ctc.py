@@ -24,10 +24,11 @@ from . import _lib
 from ._lib import B200CTCError
 
 _HANDLES = {}
-_LAST_WORKSPACE = None
+_WORKSPACES = {}     # (device index, stream handle) -> growing uint8 workspace tensor
 
 
 def _handle(device_index):
+    """One library handle per device (the handle serialises its calls with a mutex, include/b200ctc.h)."""
     h = _HANDLES.get(device_index)
     if h is None:
         lib = _lib.load()
@@ -35,6 +36,24 @@ def _handle(device_index):
         _lib.check(lib.b200ctc_create(ctypes.byref(hp), int(device_index)), "b200ctc_create")
         h = _HANDLES[device_index] = hp
     return h
+
+
+def _workspace(dev_index, stream, nbytes):
+    """Workspace of the calls issued on one stream of one device: allocated once and grown on demand (no
+    caching-allocator round trip per call).  Calls on one stream are ordered, so they can share it; calls on
+    another stream get their own -- which is also what keeps the buffer alive and un-recycled while kernels
+    of that stream still use it (no record_stream needed)."""
+    key = (dev_index, stream)
+    ws = _WORKSPACES.get(key)
+    if ws is None or ws.numel() < nbytes:
+        ws = torch.empty(max(int(nbytes * 1.25), 1 << 20), dtype=torch.uint8, device=torch.device("cuda", dev_index))
+        _WORKSPACES[key] = ws
+    return ws
+
+
+def release_workspaces():
+    """Drop the cached workspaces (they are re-allocated on the next call)."""
+    _WORKSPACES.clear()
 
 
 def set_profiling(enable, device_index=None):
@@ -53,20 +72,33 @@ def last_kernel_ms(device_index=None):
     return tuple(float(x) for x in ms)
 
 
-def last_fallbacks(device_index=None):
-    """(extreme_rows, range_lost): utterances of the last call that took the fp64 safe lattice."""
+def last_fallbacks(device_index=None, with_invalid=False):
+    """(extreme_rows, range_lost): utterances of the last call that took the fp64 safe lattice;
+    with_invalid=True appends the number of utterances a device-resident call rejected (cost NaN)."""
     if device_index is None:
         device_index = torch.cuda.current_device()
-    c = (ctypes.c_int * 2)()
+    c = (ctypes.c_int * 3)()
     _lib.check(_lib.load().b200ctc_get_last_fallbacks(_handle(device_index), c,
                                                       torch.cuda.current_stream().cuda_stream),
                "b200ctc_get_last_fallbacks")
-    return int(c[0]), int(c[1])
+    return (int(c[0]), int(c[1]), int(c[2])) if with_invalid else (int(c[0]), int(c[1]))
+
+
+def plan_cache_stats(device_index=None):
+    """(hits, misses) of the host-label call's plan cache on this device's handle."""
+    if device_index is None:
+        device_index = torch.cuda.current_device()
+    h, m = ctypes.c_longlong(), ctypes.c_longlong()
+    _lib.check(_lib.load().b200ctc_get_plan_cache_stats(_handle(device_index), ctypes.byref(h), ctypes.byref(m)),
+               "b200ctc_get_plan_cache_stats")
+    return int(h.value), int(m.value)
 
 
 def _host_i32(x, name):
     """labels / lengths arrive as CPU int32 tensors in the reference (ctc.py:295-297,321);
     numpy arrays and lists are accepted too.  Returns a C-contiguous int32 numpy array."""
+    if isinstance(x, np.ndarray) and x.dtype == np.int32 and x.ndim == 1 and x.flags.c_contiguous:
+        return x
     if isinstance(x, torch.Tensor):
         if x.is_cuda:
             x = x.cpu()  # the warp-ctc contract keeps these on the host; tolerate device tensors
@@ -101,57 +133,112 @@ def workspace_bytes(label_lens, act_lens, T, V):
     return n.value
 
 
+def workspace_bound(T, V, B, max_label_len):
+    """Workspace size from the shape alone (what the device-resident call uses)."""
+    n = ctypes.c_size_t()
+    _lib.check(_lib.load().b200ctc_get_workspace_bound(int(T), int(V), int(B), int(max_label_len), ctypes.byref(n)),
+               "b200ctc_get_workspace_bound")
+    return n.value
+
+
+def _outputs(T, B, V, dev, grads, need_grad, costs, loss_sum):
+    if need_grad:
+        if grads is None:
+            grads = torch.empty((T, B, V), dtype=torch.float32, device=dev)
+        elif (not grads.is_cuda or grads.dtype != torch.float32 or tuple(grads.shape) != (T, B, V)
+              or not grads.is_contiguous()):
+            raise B200CTCError("grads must be a contiguous CUDA float32 tensor shaped like acts")
+    else:
+        grads = None
+    if costs is None:
+        costs = torch.empty(B, dtype=torch.float32, device=dev)
+    if loss_sum is None:
+        loss_sum = torch.empty(1, dtype=torch.float32, device=dev)
+    return grads, costs, loss_sum
+
+
+def _dev_i32(x, name, dev):
+    if not (isinstance(x, torch.Tensor) and x.is_cuda):
+        raise B200CTCError("%s must be a CUDA tensor when the labels are device-resident" % name)
+    if x.dtype != torch.int32 or not x.is_contiguous() or x.device != dev:
+        x = x.to(device=dev, dtype=torch.int32).contiguous()
+    return x
+
+
 def ctc_loss_and_grad(acts, labels, act_lens, label_lens, blank=0, grads=None, need_grad=True,
-                      costs=None, loss_sum=None):
+                      costs=None, loss_sum=None, max_label_len=None):
     """One fused cost-and-gradient evaluation on the current CUDA stream.
 
     acts [T,B,V] CUDA fp32 logits (any strides with a unit vocabulary stride, e.g. the
-    ``logits.transpose(0, 1)`` view the reference passes, ctc.py:319 -- no copy is made);
-    labels / act_lens / label_lens on the host.  Returns device tensors
-    ``(costs[B], loss_sum[1], grads[T,B,V] or None)``; nothing synchronises the host.
+    ``logits.transpose(0, 1)`` view the reference passes, ctc.py:319 -- no copy is made).
+    Two forms of labels / lengths:
+      * host-resident (the warp-ctc contract, ctc.py:295-297,321): flat int32 ``labels`` and ``act_lens`` /
+        ``label_lens`` as CPU tensors, numpy arrays or lists -- planned on the host, tables copied by the call;
+      * device-resident: ``labels`` a CUDA int32 tensor ``[B, Lmax]`` (padded; entries past ``label_lens[b]`` are
+        ignored) with CUDA int32 ``act_lens`` / ``label_lens`` -- planned by a kernel, the call is kernel
+        launches only and can be captured into a CUDA graph (``max_label_len`` defaults to ``Lmax``).
+    Returns device tensors ``(costs[B], loss_sum[1], grads[T,B,V] or None)``; nothing synchronises the host.
     """
     _require_cuda(acts)
     lib = _lib.load()
     if acts.stride(2) != 1 and acts.size(2) > 1:
         acts = acts.contiguous()
     T, B, V = acts.shape
-    labels = _host_i32(labels, "labels")
-    act_lens = _host_i32(act_lens, "act_lens")
-    label_lens = _host_i32(label_lens, "label_lens")
-    if len(act_lens) != B or len(label_lens) != B:
-        raise B200CTCError("act_lens and label_lens must have one entry per utterance (B=%d)" % B)
-    if int(label_lens.sum()) != len(labels):
-        raise B200CTCError("sum(label_lens)=%d does not match len(labels)=%d" % (int(label_lens.sum()), len(labels)))
     dev = acts.device
-    with torch.cuda.device(dev):
-        if need_grad:
-            if grads is None:
-                grads = torch.empty((T, B, V), dtype=torch.float32, device=dev)
-            elif (not grads.is_cuda or grads.dtype != torch.float32 or tuple(grads.shape) != (T, B, V)
-                  or not grads.is_contiguous()):
-                raise B200CTCError("grads must be a contiguous CUDA float32 tensor shaped like acts")
-        else:
-            grads = None
-        if costs is None:
-            costs = torch.empty(B, dtype=torch.float32, device=dev)
-        if loss_sum is None:
-            loss_sum = torch.empty(1, dtype=torch.float32, device=dev)
+    dev_index = dev.index if dev.index is not None else torch.cuda.current_device()
+    switch = torch.cuda.current_device() != dev_index
+    if switch:
+        prev_dev = torch.cuda.current_device()
+        torch.cuda.set_device(dev_index)
+    try:
+        grads, costs, loss_sum = _outputs(T, B, V, dev, grads, need_grad, costs, loss_sum)
+        stream = torch.cuda.current_stream(dev).cuda_stream
+        if isinstance(labels, torch.Tensor) and labels.is_cuda:
+            if labels.dim() != 2 or labels.size(0) != B:
+                raise B200CTCError("device-resident labels must be a padded [B, Lmax] tensor")
+            labels = labels if (labels.dtype == torch.int32 and labels.stride(1) == 1) else labels.to(torch.int32).contiguous()
+            act_lens_d = _dev_i32(act_lens, "act_lens", dev)
+            label_lens_d = _dev_i32(label_lens, "label_lens", dev)
+            if act_lens_d.numel() != B or label_lens_d.numel() != B:
+                raise B200CTCError("act_lens and label_lens must have one entry per utterance (B=%d)" % B)
+            Lmax = labels.size(1) if max_label_len is None else int(max_label_len)
+            if Lmax > labels.size(1):
+                raise B200CTCError("max_label_len exceeds the padded label width")
+            nbytes = ctypes.c_size_t()
+            _lib.check(lib.b200ctc_get_workspace_bound(T, V, B, Lmax, ctypes.byref(nbytes)), "b200ctc_get_workspace_bound")
+            workspace = _workspace(dev_index, stream, nbytes.value)
+            st = lib.b200ctc_loss_and_grad_dev(
+                _handle(dev_index), acts.data_ptr(), acts.stride(0), acts.stride(1),
+                grads.data_ptr() if grads is not None else None,
+                labels.data_ptr(), labels.stride(0) if B > 0 and labels.size(1) > 0 else Lmax,
+                label_lens_d.data_ptr(), act_lens_d.data_ptr(),
+                T, V, B, Lmax, int(blank), costs.data_ptr(), loss_sum.data_ptr(),
+                workspace.data_ptr(), workspace.numel(), stream)
+            _lib.check(st, "b200ctc_loss_and_grad_dev")
+            return costs, loss_sum, grads
+        labels = _host_i32(labels, "labels")
+        act_lens = _host_i32(act_lens, "act_lens")
+        label_lens = _host_i32(label_lens, "label_lens")
+        if len(act_lens) != B or len(label_lens) != B:
+            raise B200CTCError("act_lens and label_lens must have one entry per utterance (B=%d)" % B)
+        if int(label_lens.sum()) != len(labels):
+            raise B200CTCError("sum(label_lens)=%d does not match len(labels)=%d" % (int(label_lens.sum()), len(labels)))
         nbytes = ctypes.c_size_t()
         _lib.check(lib.b200ctc_get_workspace_size(_i32_ptr(label_lens), _i32_ptr(act_lens), T, V, B,
                                                   ctypes.byref(nbytes)), "b200ctc_get_workspace_size")
-        workspace = torch.empty(max(nbytes.value, 1), dtype=torch.uint8, device=dev)  # caching allocator
-        stream = torch.cuda.current_stream(dev).cuda_stream
+        workspace = _workspace(dev_index, stream, nbytes.value)
         st = lib.b200ctc_loss_and_grad(
-            _handle(dev.index if dev.index is not None else torch.cuda.current_device()),
+            _handle(dev_index),
             acts.data_ptr(), acts.stride(0), acts.stride(1),
             grads.data_ptr() if grads is not None else None,
             _i32_ptr(labels), _i32_ptr(label_lens), _i32_ptr(act_lens),
             T, V, B, int(blank),
             costs.data_ptr(), loss_sum.data_ptr(),
-            workspace.data_ptr(), nbytes.value, stream)
+            workspace.data_ptr(), workspace.numel(), stream)
         _lib.check(st, "b200ctc_loss_and_grad")
-        global _LAST_WORKSPACE
-        _LAST_WORKSPACE = workspace   # keeps the diagnostics (last_fallbacks) valid until the next call
+    finally:
+        if switch:
+            torch.cuda.set_device(prev_dev)
     return costs, loss_sum, grads
 
 

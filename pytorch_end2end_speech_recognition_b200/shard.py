@@ -69,8 +69,8 @@ def sharded_ctc_loss(acts, labels, act_lens, label_lens, blank=0, group=None, ra
     rank r evaluates its length-balanced shard, the scalar losses are all-reduced.
 
     Returns (global_loss[1] device tensor, local_index, local_costs, local_grads) where
-    local_grads is [T, B_local, V] for the utterances ``local_index`` (gradients never cross
-    GPUs)."""
+    local_grads is [T_local, B_local, V] for the utterances ``local_index`` (T_local = the longest
+    utterance of the shard; gradients never cross GPUs)."""
     import torch
     import torch.distributed as dist
     from .ctc import ctc_loss_and_grad
@@ -82,7 +82,8 @@ def sharded_ctc_loss(acts, labels, act_lens, label_lens, blank=0, group=None, ra
     index = balance_shards(act_lens, label_lens, V, world_size)[rank]
     flat, ll, al = shard_batch(labels, label_lens, act_lens, index)
     sel = torch.as_tensor(index, device=acts.device)
-    local_acts = acts.index_select(1, sel)
+    t_local = int(al.max()) if len(al) else 0
+    local_acts = acts[:t_local].index_select(1, sel)      # the shard's padded length, not the batch's
     costs, loss, grads = ctc_loss_and_grad(local_acts, flat, al, ll, blank=blank)
     loss = allreduce_loss(loss, group)
     return loss, index, costs, grads

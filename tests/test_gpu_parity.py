@@ -57,16 +57,26 @@ def test_golden_vectors(golden_dir):
 def test_reference_chainer_golden_vectors(golden_dir):
     """Costs/gradients produced by the reference's own in-tree CTC
     (models/chainer/ctc/ctc_loss_from_chainer.py, run by tests/golden/make_golden.py).  That code is a
-    float32 log-space recursion with -1e10 padding, so the fixture itself carries up to ~1.3e-4 of
-    rounding error against exact arithmetic at T=96 (measured against the fp64 oracle); the
-    gradient tolerance is 1e-4 up to T=64 and 5e-4 beyond for that reason."""
+    float32 log-space recursion with -1e10 padding, so the fixture itself carries rounding error against
+    exact arithmetic.  The test MEASURES that error (fixture against the fp64 oracle) and asserts
+      * our gradient is within GRAD_ATOL of the exact (fp64) gradient, always, and
+      * our gradient is within GRAD_ATOL + the fixture's own measured error of the fixture
+    instead of loosening the tolerance by a narrated amount."""
     z = np.load(os.path.join(golden_dir, "ctc_reference_golden.npz"))
+    worst_fixture_err = 0.0
     for i in range(int(z["n_cases"])):
         acts = z["acts_%d" % i]
-        c, _, g = run_gpu(acts, z["labels_%d" % i], z["act_lens_%d" % i], z["label_lens_%d" % i])
+        lab, al, ll = z["labels_%d" % i], z["act_lens_%d" % i], z["label_lens_%d" % i]
+        c, _, g = run_gpu(acts, lab, al, ll)
         assert np.allclose(c, z["costs_%d" % i], rtol=LOSS_RTOL), i
-        tol = GRAD_ATOL if acts.shape[0] <= 64 else 5e-4
-        assert np.max(np.abs(g - z["grads_%d" % i])) < tol, i
+        c64, g64 = ctc_ref.ctc_cost_and_grad(acts, lab, al, ll)
+        fixture_err = float(np.max(np.abs(z["grads_%d" % i] - g64)))
+        worst_fixture_err = max(worst_fixture_err, fixture_err)
+        assert np.max(np.abs(g - g64)) < GRAD_ATOL, i                       # against exact arithmetic
+        assert np.max(np.abs(g - z["grads_%d" % i])) < GRAD_ATOL + fixture_err, i
+        if acts.shape[0] <= 64:
+            assert fixture_err < GRAD_ATOL, (i, fixture_err)               # short cases: the fixture itself is within tolerance
+    assert worst_fixture_err < 5e-4       # the reference's fp32 log-space rounding stays below this on the fixture (T <= 96)
 
 
 def test_kats():
@@ -281,17 +291,6 @@ def test_label_sequence_beyond_the_fast_lattice_takes_the_safe_path():
     T = L + ctc_ref.count_repeats(lab) + 25
     acts = rng.randn(T, 1, V).astype(np.float32)
     check(acts, lab, [T], [L], oracle="cpp")
-
-
-def test_four_states_per_lane_variant_matches(monkeypatch):
-    """B200CTC_NS=4 selects the tuning variant with four lattice states per lane (twice the warps)."""
-    wl = workloads.make_lengths_and_labels(None, B=6, T=300, V=30, Lmax=140, kind="var", seed=14)
-    acts = workloads.make_acts(wl).numpy()
-    c8, _, g8 = run_gpu(acts, wl.labels, wl.act_lens, wl.label_lens)
-    monkeypatch.setenv("B200CTC_NS", "4")
-    c4, g4 = check(acts, wl.labels, wl.act_lens, wl.label_lens, oracle="cpp")
-    assert ctc_mod.last_fallbacks() == (0, 0)
-    assert np.allclose(c4, c8, rtol=1e-6) and np.max(np.abs(g4 - g8)) < 1e-5
 
 
 def test_results_are_bit_reproducible():

@@ -1,0 +1,230 @@
+"""GPU tests added in round 2: the device-resident call (plan kernel, CUDA-graph capture), the plan cache of
+the host call, cost-only calls at full size, label sequences beyond the shared-memory budget of the
+gathered mode, input clamping in the decoder, sharded evaluation of one batch."""
+import numpy as np
+import pytest
+import torch
+
+import pytorch_end2end_speech_recognition_b200 as b200
+from oracle import ctc_ref
+from oracle.ctc_cpu import ctc_cpu
+from pytorch_end2end_speech_recognition_b200 import ctc as ctc_mod
+from pytorch_end2end_speech_recognition_b200 import shard, workloads
+
+pytestmark = pytest.mark.gpu
+
+LOSS_RTOL = 1e-5
+GRAD_ATOL = 1e-4
+
+
+def padded(wl, width=None):
+    """[B, Lmax] int32 padded labels (pad value -7: must never be read) + CUDA length tensors."""
+    width = int(wl.label_lens.max(initial=0)) if width is None else width
+    ys = np.full((wl.B, max(width, 1)), -7, np.int32)
+    off = 0
+    for b, L in enumerate(wl.label_lens):
+        ys[b, :L] = wl.labels[off:off + L]
+        off += L
+    return (torch.from_numpy(ys).cuda(), torch.from_numpy(wl.act_lens.astype(np.int32)).cuda(),
+            torch.from_numpy(wl.label_lens.astype(np.int32)).cuda())
+
+
+def assert_parity(c, g, acts, wl):
+    c_ref, g_ref = ctc_cpu(acts, wl.labels, wl.act_lens, wl.label_lens, 0, precision="f64")
+    c = c.cpu().numpy()
+    assert np.max(np.abs(c - c_ref) / np.maximum(np.abs(c_ref), 1e-3)) < LOSS_RTOL
+    if g is not None:
+        assert np.max(np.abs(g.cpu().numpy() - g_ref)) < GRAD_ATOL
+
+
+@pytest.mark.parametrize("key", [None, "C1", "C3", "C5"])
+def test_device_resident_call_matches_host_call_and_oracle(key):
+    """Labels and lengths on the GPU (plan kernel) give bit-identical results to the host-planned call."""
+    wl = (workloads.make_lengths_and_labels(None, B=9, T=120, V=30, Lmax=40, kind="var", seed=31) if key is None
+          else workloads.make_lengths_and_labels(key))
+    acts_t = workloads.make_acts(wl)
+    acts = acts_t.cuda()
+    ys, al, ll = padded(wl, width=int(wl.label_lens.max()) + 3)
+    c_h, l_h, g_h = b200.ctc_loss_and_grad(acts, wl.labels, wl.act_lens, wl.label_lens)
+    c_d, l_d, g_d = b200.ctc_loss_and_grad(acts, ys, al, ll)
+    torch.cuda.synchronize()
+    assert ctc_mod.last_fallbacks(with_invalid=True) == (0, 0, 0)
+    assert torch.equal(c_h, c_d) and torch.equal(g_h, g_d) and torch.equal(l_h, l_d)
+    assert_parity(c_d, g_d, acts_t.numpy(), wl)
+
+
+def test_device_resident_call_rejects_bad_utterances_on_the_device():
+    wl = workloads.make_lengths_and_labels(None, B=5, T=40, V=12, Lmax=10, kind="var", seed=32)
+    acts = workloads.make_acts(wl).cuda()
+    ys, al, ll = padded(wl)
+    good = b200.ctc_loss_and_grad(acts, ys, al, ll)
+    ys2, al2, ll2 = ys.clone(), al.clone(), ll.clone()
+    ys2[1, 0] = 12            # label == V
+    ys2[2, 1] = 0             # label == blank
+    al2[3] = 41               # act_len > T
+    ll2[4] = ys.size(1) + 1   # label_len > padded width
+    c, loss, g = b200.ctc_loss_and_grad(acts, ys2, al2, ll2)
+    torch.cuda.synchronize()
+    assert ctc_mod.last_fallbacks(with_invalid=True)[2] == 4
+    c = c.cpu().numpy()
+    assert np.isnan(c[1:]).all() and c[0] == good[0][0].item()
+    g = g.cpu().numpy()
+    assert np.all(g[:, 1:] == 0) and np.array_equal(g[:, 0], good[2][:, 0].cpu().numpy())
+
+
+def test_device_resident_call_in_a_cuda_graph():
+    """The device-resident call is kernel launches only: captured once, replayed with new inputs."""
+    wl = workloads.make_lengths_and_labels(None, B=16, T=200, V=30, Lmax=60, kind="var", seed=33)
+    wl2 = workloads.make_lengths_and_labels(None, B=16, T=200, V=30, Lmax=60, kind="var", seed=34)
+    width = 60
+    acts = workloads.make_acts(wl).cuda()
+    ys, al, ll = padded(wl, width)
+    grads = torch.empty_like(acts)
+    costs = torch.empty(wl.B, device="cuda")
+    loss = torch.empty(1, device="cuda")
+    b200.ctc_loss_and_grad(acts, ys, al, ll, grads=grads, costs=costs, loss_sum=loss)    # warm-up (allocations)
+    torch.cuda.synchronize()
+    graph = torch.cuda.CUDAGraph()
+    s = torch.cuda.Stream()
+    s.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(s):
+        b200.ctc_loss_and_grad(acts, ys, al, ll, grads=grads, costs=costs, loss_sum=loss)
+        torch.cuda.synchronize()
+        with torch.cuda.graph(graph, stream=s):
+            b200.ctc_loss_and_grad(acts, ys, al, ll, grads=grads, costs=costs, loss_sum=loss)
+    torch.cuda.current_stream().wait_stream(s)
+    for w in (wl, wl2, wl):
+        a_new = workloads.make_acts(w, copy_index=3)
+        y_new, al_new, ll_new = padded(w, width)
+        acts.copy_(a_new.cuda()); ys.copy_(y_new); al.copy_(al_new); ll.copy_(ll_new)
+        grads.fill_(7.0)
+        graph.replay()
+        torch.cuda.synchronize()
+        assert_parity(costs, grads, a_new.numpy(), w)
+        c_ref, _ = ctc_cpu(a_new.numpy(), w.labels, w.act_lens, w.label_lens, 0, precision="f64")
+        assert abs(float(loss.cpu()[0]) - c_ref.sum()) < LOSS_RTOL * c_ref.sum()
+
+
+def test_plan_cache_reuses_the_previous_plan():
+    wl = workloads.make_lengths_and_labels(None, B=12, T=150, V=30, Lmax=50, kind="var", seed=35)
+    acts = workloads.make_acts(wl).cuda()
+    first = b200.ctc_loss_and_grad(acts, wl.labels, wl.act_lens, wl.label_lens)
+    h0, m0 = ctc_mod.plan_cache_stats()
+    again = b200.ctc_loss_and_grad(acts, wl.labels, wl.act_lens, wl.label_lens)
+    h1, m1 = ctc_mod.plan_cache_stats()
+    assert (h1, m1) == (h0 + 1, m0)
+    labels2 = wl.labels.copy()
+    labels2[5] = labels2[5] % (wl.V - 1) + 1                          # one label changed: must re-plan
+    changed = b200.ctc_loss_and_grad(acts, labels2, wl.act_lens, wl.label_lens)
+    h2, m2 = ctc_mod.plan_cache_stats()
+    assert (h2, m2) == (h1, m1 + 1)
+    torch.cuda.synchronize()
+    assert torch.equal(first[0], again[0]) and torch.equal(first[2], again[2])
+    c_ref, g_ref = ctc_ref.ctc_cost_and_grad(acts.cpu().numpy(), labels2, wl.act_lens, wl.label_lens)
+    assert np.allclose(changed[0].cpu().numpy(), c_ref, rtol=LOSS_RTOL)
+    assert np.max(np.abs(changed[2].cpu().numpy() - g_ref)) < GRAD_ATOL
+
+
+@pytest.mark.parametrize("key", ["C3", "C1"])
+def test_cost_only_call_at_full_size(key):
+    """Validation loss (no gradient buffer) on the headline shape: same lattice, same shared-memory footprint
+    as the training call (the softmax rows go to the workspace), no utterance on the safe path."""
+    wl = workloads.make_lengths_and_labels(key)
+    acts_t = workloads.make_acts(wl)
+    c, loss, g = b200.ctc_loss_and_grad(acts_t.cuda(), wl.labels, wl.act_lens, wl.label_lens, need_grad=False)
+    torch.cuda.synchronize()
+    assert g is None and ctc_mod.last_fallbacks() == (0, 0)
+    c_ref, _ = ctc_cpu(acts_t.numpy(), wl.labels, wl.act_lens, wl.label_lens, 0, precision="f64")
+    assert np.max(np.abs(c.cpu().numpy() - c_ref) / c_ref) < LOSS_RTOL
+    c2 = b200.ctc_loss_and_grad(acts_t.cuda(), wl.labels, wl.act_lens, wl.label_lens)[0]
+    assert torch.equal(c, c2)
+
+
+@pytest.mark.parametrize("V,L", [(300, 300), (1500, 260), (129, 400)])
+def test_large_vocabulary_long_labels_beyond_the_shared_memory_budget(V, L):
+    """Gathered mode (V >= 129): the emission-row ring grows with the label sequence, so the longest ones do
+    not fit 227 KB and are evaluated by the safe lattice in the same launch -- the call must not fail."""
+    rng = np.random.RandomState(V + L)
+    labs = [rng.randint(1, V, size=n) for n in (L, L // 2, 30)]
+    T = L + 40
+    acts = rng.randn(T, 3, V).astype(np.float32)
+    wl = workloads.Workload("x", T, 3, V, np.concatenate(labs).astype(np.int32), np.array([len(x) for x in labs], np.int32),
+                            np.array([T, T - 3, T - 11], np.int32), 0)
+    c, loss, g = b200.ctc_loss_and_grad(torch.from_numpy(acts).cuda(), wl.labels, wl.act_lens, wl.label_lens)
+    torch.cuda.synchronize()
+    assert_parity(c, g, acts, wl)
+    c2, _, g2 = b200.ctc_loss_and_grad(torch.from_numpy(acts).cuda(), wl.labels, wl.act_lens, wl.label_lens, need_grad=False)
+    assert g2 is None and np.allclose(c2.cpu().numpy(), c.cpu().numpy(), rtol=1e-6)
+
+
+def test_more_than_65535_frames():
+    """The softmax-rows grid carries the frame index on (y, z): T is not limited to 65535."""
+    rng = np.random.RandomState(41)
+    T, V = 66000, 5
+    acts = rng.randn(T, 1, V).astype(np.float32)
+    wl = workloads.Workload("x", T, 1, V, np.array([1, 2, 2, 3], np.int32), np.array([4], np.int32), np.array([T], np.int32), 0)
+    c, loss, g = b200.ctc_loss_and_grad(torch.from_numpy(acts).cuda(), wl.labels, wl.act_lens, wl.label_lens)
+    torch.cuda.synchronize()
+    assert_parity(c, g, acts, wl)
+
+
+def test_decoder_clamps_lengths_outside_the_tensor():
+    rng = np.random.RandomState(42)
+    logits = rng.randn(3, 20, 6).astype(np.float32)
+    tokens, lens = b200.greedy_decode(torch.from_numpy(logits).cuda(), np.array([25, -3, 20]))
+    ref = ctc_ref.greedy_decode(logits, np.array([20, 0, 20]))
+    tokens, lens = tokens.cpu().numpy(), lens.cpu().numpy()
+    for b in range(3):
+        assert np.array_equal(tokens[b, :lens[b]], ref[b])
+        assert np.all(tokens[b, lens[b]:] == -1)
+
+
+def test_handle_rejects_a_call_on_another_device_or_threads_share_it():
+    """Two host threads issuing calls on the same device share one handle (serialised by its mutex)."""
+    import threading
+    wl = workloads.make_lengths_and_labels(None, B=6, T=90, V=30, Lmax=25, kind="var", seed=43)
+    acts = workloads.make_acts(wl).cuda()
+    ref = b200.ctc_loss_and_grad(acts, wl.labels, wl.act_lens, wl.label_lens)
+    torch.cuda.synchronize()
+    out, err = [None] * 4, []
+
+    def work(i):
+        try:
+            s = torch.cuda.Stream()
+            with torch.cuda.stream(s):
+                for _ in range(20):
+                    r = b200.ctc_loss_and_grad(acts, wl.labels, wl.act_lens, wl.label_lens)
+                s.synchronize()
+            out[i] = r
+        except Exception as exc:          # pragma: no cover
+            err.append(exc)
+
+    threads = [threading.Thread(target=work, args=(i,)) for i in range(4)]
+    [t.start() for t in threads]
+    [t.join() for t in threads]
+    assert not err
+    for r in out:
+        assert torch.equal(r[0], ref[0]) and torch.equal(r[2], ref[2])
+
+
+def test_sharded_evaluation_of_one_batch_matches_the_whole_batch():
+    """utils/parallel.py replacement, emulated on one device: the C5-shaped batch is split into two
+    length-balanced shards (what ranks 0 and 1 of a 2-GPU job evaluate); shard losses add up to the loss of the
+    whole batch and every utterance's cost and gradient is the one the unsharded call produces."""
+    wl = workloads.make_lengths_and_labels(None, B=64, T=400, V=30, Lmax=100, kind="sweep", seed=44)
+    acts = workloads.make_acts(wl).cuda()
+    c_all, loss_all, g_all = b200.ctc_loss_and_grad(acts, wl.labels, wl.act_lens, wl.label_lens)
+    total = 0.0
+    seen = []
+    for rank in range(2):
+        loss, index, costs, grads = shard.sharded_ctc_loss(acts, wl.labels, wl.act_lens, wl.label_lens, rank=rank, world_size=2)
+        total += float(loss.cpu()[0])
+        seen.append(index)
+        idx = torch.as_tensor(index, device="cuda")
+        assert torch.equal(costs, c_all[idx])
+        T_loc = int(wl.act_lens[index].max())
+        assert tuple(grads.shape) == (T_loc, len(index), wl.V) and torch.equal(grads, g_all[:T_loc, idx])
+    assert sorted(np.concatenate(seen).tolist()) == list(range(wl.B))
+    assert abs(total - float(loss_all.cpu()[0])) < 1e-5 * float(loss_all.cpu()[0])
+    c_ref, _ = ctc_cpu(acts.cpu().numpy(), wl.labels, wl.act_lens, wl.label_lens, 0, precision="f64")
+    assert abs(total - c_ref.sum()) < LOSS_RTOL * c_ref.sum()

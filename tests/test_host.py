@@ -21,7 +21,7 @@ def test_library_exports_every_declared_symbol():
     assert declared == set(_lib.EXPORTED_SYMBOLS)
     for name in declared:
         assert hasattr(lib, name), name
-    assert lib.b200ctc_version() == 100
+    assert lib.b200ctc_version() == 200
     assert lib.b200ctc_status_string(0) == b"success"
     assert lib.b200ctc_status_string(1) == b"invalid value"
 
