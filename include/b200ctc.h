@@ -61,6 +61,29 @@ typedef enum {
 
 typedef struct b200ctc_handle b200ctc_handle;
 
+/*
+ * Arithmetic of the reference's loss call site fused into the kernels, for
+ * b200ctc_loss_and_grad_dev.  With z = logit_scale * acts and y = softmax(z):
+ *
+ *   loss_sum  = loss_scale * sum_b [ (1 - label_smoothing) * cost_b
+ *                                    + (label_smoothing / V) * sum_{t < act_lens[b]} sum_k -log y[t,b,k] ]
+ *   grads     = grad_scale * [ y - (1 - label_smoothing) * occupancy - label_smoothing / V ]     (t < act_lens[b])
+ *
+ * i.e. grads = grad_scale * d(loss_sum / loss_scale) / dz.  The reference computes exactly this with separate
+ * tensor passes: `logits /= logits_temperature` (models/pytorch_v3/ctc/ctc.py:306-307: logit_scale =
+ * 1/temperature), `/ len(xs)` (ctc.py:323: loss_scale = 1/B), and the label-smoothing cross entropy with a
+ * uniform distribution, a second log_softmax and a python loop over the mini-batch (ctc.py:329-337,
+ * models/pytorch_v3/criterion.py:51-80).  For the gradient with respect to the UNSCALED logits of a loss
+ * scaled by loss_scale pass grad_scale = loss_scale * logit_scale.
+ * A NULL options pointer means {1, 0, 1, 1}: results are bit-identical to b200ctc_loss_and_grad.
+ */
+typedef struct {
+  float logit_scale;      /* > 0 */
+  float label_smoothing;  /* in [0, 1) */
+  float loss_scale;
+  float grad_scale;
+} b200ctc_options;
+
 /* Replaces warp-ctc's get_warpctc_version(). */
 B200CTC_API int b200ctc_version(void);
 
@@ -135,6 +158,9 @@ B200CTC_API int b200ctc_loss_and_grad(b200ctc_handle* handle,
  *   label_lens     DEVICE int32 [B], 0 <= label_lens[b] <= max_label_len
  *   act_lens       DEVICE int32 [B], 0 <= act_lens[b] <= T
  *   max_label_len  host-side bound on label_lens (sizes shared memory and the workspace regions)
+ *   opts           fused call-site arithmetic (b200ctc_options above) or NULL
+ *   costs          DEVICE fp32 [B]: the plain CTC cost -log p(labels_b | z_b), whatever the options
+ *   ls_costs       DEVICE fp32 [B] or NULL: sum_{t<act_lens[b]} sum_k -log y[t,b,k] (written when label_smoothing > 0)
  *   workspace      DEVICE, >= b200ctc_get_workspace_bound(T, V, B, max_label_len) bytes
  *
  * Inputs cannot be validated on the host: an utterance with a length out of range or a label outside
@@ -146,7 +172,8 @@ B200CTC_API int b200ctc_loss_and_grad_dev(b200ctc_handle* handle,
                               float* grads,
                               const int* labels, int label_stride, const int* label_lens, const int* act_lens,
                               int T, int V, int B, int max_label_len, int blank,
-                              float* costs, float* loss_sum,
+                              const b200ctc_options* opts,
+                              float* costs, float* loss_sum, float* ls_costs,
                               void* workspace, size_t workspace_bytes, void* stream);
 
 /*

@@ -33,6 +33,12 @@ EXPORTED_SYMBOLS = (
 )
 
 
+class Options(ctypes.Structure):
+    """b200ctc_options (include/b200ctc.h): fused call-site arithmetic of the device-resident call."""
+    _fields_ = [("logit_scale", ctypes.c_float), ("label_smoothing", ctypes.c_float),
+                ("loss_scale", ctypes.c_float), ("grad_scale", ctypes.c_float)]
+
+
 class B200CTCError(RuntimeError):
     """Raised for every non-zero status of the C ABI (a RuntimeError, so the reference's
     skip-mini-batch guard, utils/training/training_loop.py:69-76, keeps working)."""
@@ -71,7 +77,8 @@ def _declare(lib):
         ctypes.c_void_p,                                   # grads
         ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p,   # labels, label_stride, label_lens, act_lens (device)
         ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int,  # T, V, B, max_label_len, blank
-        ctypes.c_void_p, ctypes.c_void_p,                  # costs, loss_sum (device)
+        ctypes.POINTER(Options),                           # opts (nullable)
+        ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, # costs, loss_sum, ls_costs (device)
         ctypes.c_void_p, ctypes.c_size_t, ctypes.c_void_p  # workspace, bytes, stream
     ]
     lib.b200ctc_get_plan_cache_stats.restype = ctypes.c_int

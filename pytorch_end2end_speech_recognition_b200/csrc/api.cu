@@ -31,7 +31,7 @@ inline size_t align_up(size_t x) { return (x + kAlign - 1) / kAlign * kAlign; }
 struct WorkspaceLayout {
   size_t blob_bytes;   // meta + order + flags + labels
   size_t off_meta, off_order, off_flags, off_labels;
-  size_t off_lse, off_em, off_scratch;
+  size_t off_lse, off_xe_rows, off_xe_costs, off_em, off_scratch;
   size_t total;
 };
 
@@ -76,6 +76,8 @@ WorkspaceLayout make_layout(const BatchTotals& t, int T, int B, int V) {
   w.off_labels = off; off += align_up((size_t)t.sum_labels * sizeof(int));
   w.blob_bytes = off;
   w.off_lse = off;    off += align_up((size_t)T * B * sizeof(float));
+  w.off_xe_rows = off; off += align_up((size_t)T * B * sizeof(float));   // label smoothing: per-row cross-entropy terms
+  w.off_xe_costs = off; off += align_up((size_t)B * sizeof(float));
   const size_t em_floats = V >= kGatherMinV ? (size_t)t.em_floats : (size_t)T * B * V;
   w.off_em = off;     off += align_up(em_floats * sizeof(float));
   w.off_scratch = off; off += align_up((size_t)t.scratch_units * kGroupBytes);
@@ -156,7 +158,21 @@ int run_kernels(b200ctc_handle* h, CallParams& p, int max_L, cudaStream_t stream
 }
 
 void fill_common(CallParams& p, const float* acts, int64_t as_t, int64_t as_b, float* grads, int T, int V, int B,
-                 int blank, float* costs, float* loss_sum, unsigned char* ws, const WorkspaceLayout& lay) {
+                 int blank, float* costs, float* loss_sum, unsigned char* ws, const WorkspaceLayout& lay,
+                 const b200ctc_options* o = nullptr, float* ls_costs = nullptr) {
+  // fused call-site arithmetic (include/b200ctc.h, b200ctc_options); the defaults leave every result bit-identical
+  const float logit_scale = o ? o->logit_scale : 1.f, lsp = o ? o->label_smoothing : 0.f;
+  const float grad_scale = o ? o->grad_scale : 1.f;
+  p.logit_scale = logit_scale;
+  p.s_y = grad_scale;
+  p.s_occ = grad_scale * (1.f - lsp);
+  p.c_ls = grad_scale * lsp / (float)V;
+  p.loss_scale = o ? o->loss_scale : 1.f;
+  p.ctc_w = 1.f - lsp;
+  p.ls_w = lsp / (float)V;
+  p.rescale = (p.s_y != 1.f || p.s_occ != 1.f || p.c_ls != 0.f) ? 1 : 0;
+  p.xe_rows = lsp != 0.f ? reinterpret_cast<float*>(ws + lay.off_xe_rows) : nullptr;
+  p.xe_costs = ls_costs ? ls_costs : reinterpret_cast<float*>(ws + lay.off_xe_costs);
   p.acts = acts;
   p.as_t = as_t;
   p.as_b = as_b;
@@ -404,9 +420,13 @@ int b200ctc_loss_and_grad(b200ctc_handle* h, const float* acts, int64_t acts_str
 int b200ctc_loss_and_grad_dev(b200ctc_handle* h, const float* acts, int64_t acts_stride_t,
                               int64_t acts_stride_b, float* grads, const int* labels, int label_stride,
                               const int* label_lens, const int* act_lens, int T, int V, int B,
-                              int max_label_len, int blank, float* costs, float* loss_sum,
-                              void* workspace, size_t workspace_bytes, void* stream_v) {
+                              int max_label_len, int blank, const b200ctc_options* opts, float* costs,
+                              float* loss_sum, float* ls_costs, void* workspace, size_t workspace_bytes,
+                              void* stream_v) {
   if (!h || T < 0 || V < 1 || B < 0 || blank < 0 || blank >= V || max_label_len < 0 || label_stride < max_label_len)
+    return B200CTC_STATUS_INVALID_VALUE;
+  if (opts && (!(opts->logit_scale > 0.f) || !(opts->label_smoothing >= 0.f) || !(opts->label_smoothing < 1.f) ||
+               opts->grad_scale != opts->grad_scale || opts->loss_scale != opts->loss_scale))
     return B200CTC_STATUS_INVALID_VALUE;
   std::lock_guard<std::mutex> lock(h->mu);
   int st = check_device(h);
@@ -428,7 +448,7 @@ int b200ctc_loss_and_grad_dev(b200ctc_handle* h, const float* acts, int64_t acts
   if (workspace_bytes < lay.total + lost) return B200CTC_STATUS_WORKSPACE_TOO_SMALL;
 
   CallParams p;
-  fill_common(p, acts, acts_stride_t, acts_stride_b, grads, T, V, B, blank, costs, loss_sum, ws, lay);
+  fill_common(p, acts, acts_stride_t, acts_stride_b, grads, T, V, B, blank, costs, loss_sum, ws, lay, opts, ls_costs);
   UttMeta* meta = reinterpret_cast<UttMeta*>(ws + lay.off_meta);
   int* order = reinterpret_cast<int*>(ws + lay.off_order);
   int* flags = reinterpret_cast<int*>(ws + lay.off_flags);

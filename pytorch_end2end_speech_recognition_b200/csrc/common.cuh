@@ -43,6 +43,13 @@ struct CallParams {
   float* loss_sum;        // [1] or nullptr
   int gathered;           // 1: lattice reads emissions from `em`, 0: from the softmax rows in `yrows`
   int fast_l_cap;         // longest label sequence the block-exponent lattice takes (window count and shared-memory budget)
+  // Fused call-site arithmetic (b200ctc_options; reference: models/pytorch_v3/ctc/ctc.py:306-307,323,329-337):
+  //   z = logit_scale * acts;  grads = s_y * softmax(z) - s_occ * occupancy - c_ls   (rows t < T_b)
+  //   loss_sum = loss_scale * sum_b [ ctc_w * cost_b + ls_w * sum_{t<T_b} (V * lse - sum_k z) ]
+  float logit_scale, s_y, s_occ, c_ls, loss_scale, ctc_w, ls_w;
+  int rescale;            // 1: s_y, s_occ, c_ls are not (1, 1, 0): every entry of a live gradient row is rewritten
+  float* xe_rows;         // [T*B] V*lse - sum_k z of every live row (label smoothing only) or nullptr
+  float* xe_costs;        // [B] their per-utterance sums (workspace, or the caller's ls_costs)
   // device-resident call (b200ctc_loss_and_grad_dev): the tables above are produced by plan_kernel from these
   const int* dev_label_lens;   // [B] or nullptr
   const int* dev_act_lens;     // [B]

@@ -60,6 +60,25 @@ __global__ void __launch_bounds__(2 * (NWMAX + kReducers) * 32, 1) lattice_kerne
     g_cta_time[blockIdx.x * 2 + 1] = (long long)t;
   }
 #endif
+  // Label smoothing (b200ctc_options): -sum_{t<T_b} sum_k log y[t,k] of this utterance from K1's per-row terms,
+  // strided partial sums in double, then a tree: fixed order.
+  double* part = reinterpret_cast<double*>(smem);
+  if (p.xe_rows != nullptr) {
+    pdl_wait_primary();
+    __syncthreads();               // the utterance's own use of the shared memory is over
+    if (threadIdx.x < 256) {
+      double acc = 0.0;
+      const int n_rows = m.feasible ? m.T : 0;     // K1 writes the term for live rows only
+      for (int t = threadIdx.x; t < n_rows; t += 256) acc += (double)__ldcg(p.xe_rows + (long long)t * p.B + b);
+      part[threadIdx.x] = acc;
+    }
+    __syncthreads();
+    for (int o = 128; o > 0; o >>= 1) {
+      if ((int)threadIdx.x < o) part[threadIdx.x] += part[threadIdx.x + o];
+      __syncthreads();
+    }
+    if (threadIdx.x == 0) p.xe_costs[b] = (float)part[0];
+  }
   // K3, fused: the CTA that finishes last sums the per-utterance costs in a fixed order (256 strided
   // partial sums in double, then a tree), so the returned loss is bit-reproducible run to run.
   if (p.loss_sum == nullptr) return;
@@ -72,10 +91,13 @@ __global__ void __launch_bounds__(2 * (NWMAX + kReducers) * 32, 1) lattice_kerne
   __syncthreads();
   if (!s_last) return;
   __threadfence();
-  double* part = reinterpret_cast<double*>(smem);
   if (threadIdx.x < 256) {
     double acc = 0.0;
-    for (int i = threadIdx.x; i < p.B; i += 256) acc += (double)__ldcg(p.costs + i);
+    for (int i = threadIdx.x; i < p.B; i += 256) {
+      double c = (double)__ldcg(p.costs + i) * (double)p.ctc_w;
+      if (p.xe_rows != nullptr) c += (double)__ldcg(p.xe_costs + i) * (double)p.ls_w;
+      acc += c;
+    }
     part[threadIdx.x] = acc;
   }
   __syncthreads();
@@ -83,7 +105,7 @@ __global__ void __launch_bounds__(2 * (NWMAX + kReducers) * 32, 1) lattice_kerne
     if ((int)threadIdx.x < o) part[threadIdx.x] += part[threadIdx.x + o];
     __syncthreads();
   }
-  if (threadIdx.x == 0) *p.loss_sum = (float)part[0];
+  if (threadIdx.x == 0) *p.loss_sum = (float)(part[0] * (double)p.loss_scale);
 }
 
 constexpr size_t kSmemBudget = 227 * 1024 - 6 * 1024;   // dynamic shared memory: 227 KB per CTA minus the kernel's static arrays (4.4 KB)

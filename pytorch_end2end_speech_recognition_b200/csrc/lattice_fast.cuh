@@ -244,10 +244,11 @@ __host__ __device__ inline size_t fast_side_bytes(int L, int RW, int V) {
   b += (size_t)kReducers * 8 + 8;                            // mbar
   return (b + 15) / 16 * 16;
 }
+constexpr int kUntouchedMaxV = 256;   // the small-vocabulary (non-gathered) lattice never sees a larger vocabulary
 template <int K, int NWMAX, int NS>
 __host__ __device__ inline size_t fast_smem_bytes(int L, int RW, int V) {
-  // control words, lab, sorted, seg_start, seg_sym, slot_of_label, seg_slot
-  size_t common = (size_t)(16 + 6 * L + 16) * 4;
+  // control words, lab, sorted, seg_start, seg_sym, slot_of_label, seg_slot, untouched
+  size_t common = (size_t)(16 + 6 * L + 16 + (V <= kUntouchedMaxV ? V : 0)) * 4;
   common = (common + 15) / 16 * 16;
   return common + 2 * fast_side_bytes<K, NWMAX, NS>(L, RW, V) + 16;
 }
@@ -278,6 +279,8 @@ struct FastCommon {
   int* slot_of_label;  // [L]    slot of label i in the symbol-sorted posterior row
   int* seg_slot;       // [n_seg+1] first slot of every symbol's group in the posterior row (a multiple of 4)
   int* max_n4;         // the largest group, in 16-byte chunks
+  int* untouched;      // [V] vocabulary entries that are neither the blank nor a label of the utterance (rescaled rows only)
+  int* n_untouched;
 };
 
 // named barrier ids (0 is __syncthreads)
@@ -929,6 +932,7 @@ __device__ __forceinline__ void reduce_frame(const CallParams& p, const FastComm
 #pragma unroll
   for (int i = 0; i < NWMAX; ++i)
     if (i < NW) accb += post[RC + i * 32 + lane];
+  const float sy = p.s_y, so = p.s_occ, cl = p.c_ls;   // (1, 1, 0) unless the call carries b200ctc_options
   if (n_seg <= 64 && !gathered) {
     // small vocabularies, straight line: lane u owns symbols u and u + 32 (their groups are in registers)
     const float tot0 = post_group_sum(post4 + base4[0], n4[0], max_n4);
@@ -940,25 +944,32 @@ __device__ __forceinline__ void reduce_frame(const CallParams& p, const FastComm
       y1 = lane + 32 < n_seg ? yrow[sym[1]] : 0.f;
     }
     accb = warp_sum_q30(accb);
-    if (lane < n_seg) grow[sym[0]] = y0 - tot0;        // the touched symbols of a frame share one or two 128-byte rows
-    if (lane + 32 < n_seg) grow[sym[1]] = y1 - tot1;
-    if (lane == 0) grow[p.blank] = yb - accb;
-    return;
-  }
-  for (int u0 = 0; u0 < n_seg; u0 += 32) {
-    const int u = u0 + lane;
-    const int s0 = u < n_seg ? cm.seg_slot[u] : 0, s1 = u < n_seg ? cm.seg_slot[u + 1] : 0;
-    const float tot = post_group_sum(post4 + (s0 >> 2), (s1 - s0) >> 2, max_n4);
-    if (u < n_seg) {
-      const int sy = cm.ix.seg_sym[u];
-      if (!gathered) grow[sy] = yrow[sy] - tot;
-      else atomicAdd(grow + sy, -tot);
+    if (lane < n_seg) grow[sym[0]] = fmaf(-so, tot0, fmaf(sy, y0, -cl));   // the touched symbols of a frame share one or two 128-byte rows
+    if (lane + 32 < n_seg) grow[sym[1]] = fmaf(-so, tot1, fmaf(sy, y1, -cl));
+    if (lane == 0) grow[p.blank] = fmaf(-so, accb, fmaf(sy, yb, -cl));
+  } else {
+    for (int u0 = 0; u0 < n_seg; u0 += 32) {
+      const int u = u0 + lane;
+      const int s0 = u < n_seg ? cm.seg_slot[u] : 0, s1 = u < n_seg ? cm.seg_slot[u + 1] : 0;
+      const float tot = post_group_sum(post4 + (s0 >> 2), (s1 - s0) >> 2, max_n4);
+      if (u < n_seg) {
+        const int sy_ = cm.ix.seg_sym[u];
+        if (!gathered) grow[sy_] = fmaf(-so, tot, fmaf(sy, yrow[sy_], -cl));
+        else atomicAdd(grow + sy_, -so * tot);          // K1 left s_y * y - c_ls in the row
+      }
+    }
+    accb = warp_sum_q30(accb);
+    if (lane == 0) {
+      if (!gathered) grow[p.blank] = fmaf(-so, accb, fmaf(sy, yrow[p.blank], -cl));
+      else atomicAdd(grow + p.blank, -so * accb);
     }
   }
-  accb = warp_sum_q30(accb);
-  if (lane == 0) {
-    if (!gathered) grow[p.blank] = yrow[p.blank] - accb;
-    else atomicAdd(grow + p.blank, -accb);
+  if (p.rescale && !gathered) {          // entries the utterance never touches: s_y * y - c_ls
+    const int n_un = *cm.n_untouched;
+    for (int j = lane; j < n_un; j += 32) {
+      const int k = cm.untouched[j];
+      grow[k] = fmaf(sy, yrow[k], -cl);
+    }
   }
 }
 
@@ -1104,6 +1115,8 @@ __device__ void lattice_fast_utterance(const CallParams& p, int b, unsigned char
   cm.ix.seg_sym = ip;            ip += L + 1;
   cm.slot_of_label = ip;         ip += L;
   cm.seg_slot = ip;              ip += L + 2;
+  cm.n_untouched = cm.abort_flag + 4;
+  cm.untouched = ip;             ip += (p.V <= kUntouchedMaxV ? p.V : 0);
   size_t common = (size_t)(reinterpret_cast<unsigned char*>(ip) - smem);
   common = (common + 15) / 16 * 16;
   const int RW = p.gathered ? m.W : (p.V + 3) / 4 * 4;
@@ -1159,6 +1172,29 @@ __device__ void lattice_fast_utterance(const CallParams& p, int b, unsigned char
       cm.slot_of_label[cm.ix.sorted[k]] = cm.seg_slot[lo] + (k - cm.ix.seg_start[lo]);
     }
     __syncthreads();
+    // rescaled rows (b200ctc_options): the reducers rewrite EVERY entry of a live row, so they also need the
+    // vocabulary entries the utterance never touches (neither the blank nor one of its labels)
+    if (p.rescale && !p.gathered && p.grads != nullptr) {
+      for (int k = threadIdx.x; k < p.V; k += blockDim.x) cm.untouched[k] = 1;
+      __syncthreads();
+      for (int u = threadIdx.x; u < n_seg; u += blockDim.x) cm.untouched[cm.ix.seg_sym[u]] = 0;
+      if (threadIdx.x == 0) cm.untouched[p.blank] = 0;
+      __syncthreads();
+      if (warp == 0) {                       // in-place compaction (reads of a tile precede its writes; the write index never overtakes)
+        int n = 0;
+        for (int k0 = 0; k0 < p.V; k0 += 32) {
+          const int k = k0 + lane;
+          const bool keep = k < p.V && cm.untouched[k] != 0;
+          const unsigned bal = __ballot_sync(0xffffffffu, keep);
+          __syncwarp();
+          if (keep) cm.untouched[n + __popc(bal & ((1u << lane) - 1u))] = k;
+          n += __popc(bal);
+          __syncwarp();
+        }
+        if (lane == 0) *cm.n_untouched = n;
+      }
+      __syncthreads();
+    }
   }
 #ifdef B200CTC_TRACE
   if (blockIdx.x == g_trace_cta && threadIdx.x == 0) {

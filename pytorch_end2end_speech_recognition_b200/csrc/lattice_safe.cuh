@@ -71,12 +71,16 @@ __device__ void lattice_safe_utterance(const CallParams& p, int b, unsigned char
   double* alpha = reinterpret_cast<double*>(p.scratch + m.scratch_off * kGroupBytes);
   const long long frame_stride = 4LL * m.J;  // doubles per frame in the scratch
 
-  if (rows_dirty && p.grads) {
+  // Gradient rows in their final form minus the occupancy (s_y * y - c_ls; the plain softmax without
+  // b200ctc_options): rebuilt when the fast path left them half-updated, and for rescaled small-vocabulary
+  // calls, whose rows K1 leaves as the plain softmax for the fast lattice to read.
+  const float ls = p.logit_scale;
+  if ((rows_dirty || (p.rescale && !p.gathered)) && p.grads) {
     for (int t = 0; t < T; ++t) {
       const float* arow = acts_b + (long long)t * p.as_t;
       float* grow = p.grads + ((long long)t * p.B + b) * V;
       const float lse = p.lse[(long long)t * p.B + b];
-      for (int v = tid; v < V; v += nt) grow[v] = expf(arow[v] - lse);
+      for (int v = tid; v < V; v += nt) grow[v] = fmaf(p.s_y, expf(arow[v] * ls - lse), -p.c_ls);
     }
     __threadfence();
     __syncthreads();
@@ -96,7 +100,7 @@ __device__ void lattice_safe_utterance(const CallParams& p, int b, unsigned char
       const double x0 = prev[s];
       const double x1 = (s >= 1) ? prev[s - 1] : -INFINITY;
       const double x2 = skip ? prev[s - 2] : -INFINITY;
-      const double v = log_sum_exp3(x0, x1, x2) + ((double)arow[sym] - lse);
+      const double v = log_sum_exp3(x0, x1, x2) + ((double)(arow[sym] * ls) - lse);
       cur[s] = v;
       alpha[t * frame_stride + s] = v;
     }
@@ -136,7 +140,7 @@ __device__ void lattice_safe_utterance(const CallParams& p, int b, unsigned char
       const double x0 = prev[s];
       const double x1 = (s + 1 < S) ? prev[s + 1] : -INFINITY;
       const double x2 = skip ? prev[s + 2] : -INFINITY;
-      const double lp = (double)arow[sym] - lse;
+      const double lp = (double)(arow[sym] * ls) - lse;
       const double v = log_sum_exp3(x0, x1, x2) + lp;
       cur[s] = v;
       const double q = alpha[t * frame_stride + s] + v - lp - ll;
@@ -150,7 +154,7 @@ __device__ void lattice_safe_utterance(const CallParams& p, int b, unsigned char
       float acc = 0.f;
       for (int s = 2 * lane; s < S; s += 64) acc += sm.post[s];
       acc = warp_sum(acc);
-      if (lane == 0) atomicAdd(grow + blank, -acc);
+      if (lane == 0) atomicAdd(grow + blank, -p.s_occ * acc);
     }
     // label symbols: one thread per symbol segment (warps 1.. when there are several warps)
     const int first = (n_warps > 1) ? 32 : 0;
@@ -158,7 +162,7 @@ __device__ void lattice_safe_utterance(const CallParams& p, int b, unsigned char
       float acc = 0.f;
       for (int k = sm.ix.seg_start[u]; k < sm.ix.seg_start[u + 1]; ++k)
         acc += sm.post[2 * sm.ix.sorted[k] + 1];
-      atomicAdd(grow + sm.ix.seg_sym[u], -acc);
+      atomicAdd(grow + sm.ix.seg_sym[u], -p.s_occ * acc);
     }
     __syncthreads();
     double* tmp = prev; prev = cur; cur = tmp;

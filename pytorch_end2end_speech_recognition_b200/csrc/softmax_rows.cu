@@ -58,7 +58,7 @@ __global__ void __launch_bounds__(256) softmax_rows_warp_kernel(CallParams p) {
 #pragma unroll
   for (int i = 0; i < NV; ++i) {
     const int v = q + LPR * i;
-    x[i] = (live && v < p.V) ? __ldg(arow + v) : -INFINITY;
+    x[i] = (live && v < p.V) ? __ldg(arow + v) * p.logit_scale : -INFINITY;
     mx = fmaxf(mx, x[i]);
   }
   mx = group_max<LPR>(mx);
@@ -78,6 +78,13 @@ __global__ void __launch_bounds__(256) softmax_rows_warp_kernel(CallParams p) {
 #pragma unroll
   for (int i = 0; i < NV; ++i) extreme |= (q + LPR * i < p.V) && (x[i] - lse < kExtremeLogProb);
   const unsigned ext = __ballot_sync(0xffffffffu, extreme && live && row_ok);
+  if (p.xe_rows) {                                    // label smoothing: -sum_k log y_k of the row = V * lse - sum_k z_k
+    float sx = 0.f;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) sx += (q + LPR * i < p.V && live) ? x[i] : 0.f;
+    sx = group_sum<LPR>(sx);
+    if (live && row_ok && q == 0) p.xe_rows[row] = (float)p.V * lse - sx;
+  }
   if (live && row_ok && q == 0) {
     p.lse[row] = lse;
     if ((ext >> (sub * LPR)) & ((LPR == 32) ? 0xffffffffu : ((1u << LPR) - 1u))) atomicOr(p.flags + b, FLAG_EXTREME_ROW);
@@ -86,7 +93,10 @@ __global__ void __launch_bounds__(256) softmax_rows_warp_kernel(CallParams p) {
 #pragma unroll
     for (int i = 0; i < NV; ++i) {
       const int v = q + LPR * i;
-      if (v < p.V) grow[v] = e[i] * inv;              // zero for rows t >= act_lens[b] and infeasible utterances
+      // zero for rows t >= act_lens[b] and infeasible utterances.  Small vocabularies: the plain softmax (the
+      // lattice reads it as its emissions and rewrites the row); gathered mode: the row in its final form
+      // minus the occupancy, which the lattice subtracts with one RED per (frame, symbol)
+      if (v < p.V) grow[v] = (p.gathered && live) ? fmaf(p.s_y, e[i] * inv, -p.c_ls) : e[i] * inv;
     }
   }
   if (p.gathered) {
@@ -181,8 +191,9 @@ __global__ void __launch_bounds__(kRowThreads) softmax_rows_cta_kernel(CallParam
   int head = (4 - phase) & 3;
   if (head > V) head = V;
   float mx = -INFINITY, mn = INFINITY;
+  const float ls = p.logit_scale;
   for (int v = tid; v < head; v += kRowThreads) {
-    float x = __ldg(arow + v);
+    float x = __ldg(arow + v) * ls;
     s[v] = x;
     mx = fmaxf(mx, x);
     mn = fminf(mn, x);
@@ -192,42 +203,49 @@ __global__ void __launch_bounds__(kRowThreads) softmax_rows_cta_kernel(CallParam
   float4* s4 = reinterpret_cast<float4*>(s + head);
   for (int v = tid; v < nvec; v += kRowThreads) {
     float4 x = __ldg(a4 + v);
+    x.x *= ls; x.y *= ls; x.z *= ls; x.w *= ls;
     s4[v] = x;
     mx = fmaxf(fmaxf(mx, fmaxf(x.x, x.y)), fmaxf(x.z, x.w));
     mn = fminf(fminf(mn, fminf(x.x, x.y)), fminf(x.z, x.w));
   }
   for (int v = head + (nvec << 2) + tid; v < V; v += kRowThreads) {
-    float x = __ldg(arow + v);
+    float x = __ldg(arow + v) * ls;
     s[v] = x;
     mx = fmaxf(mx, x);
     mn = fminf(mn, x);
   }
   mx = block_reduce_max(mx, red);  // barriers inside also publish the staged row
   mn = block_reduce_min(mn, red);
-  float sum = 0.f;
+  float sum = 0.f, sx = 0.f;
   for (int v = tid; v < V; v += kRowThreads) {
-    float e = __expf(s[v] - mx);
+    const float x = s[v];
+    float e = __expf(x - mx);
     s[v] = e;
     sum += e;
+    sx += x;
   }
   sum = block_reduce_sum(sum, red);
+  if (p.xe_rows) sx = block_reduce_sum(sx, red);
   const float inv = 1.0f / sum;
   const float lse = mx + logf(sum);
   if (tid == 0) {
     p.lse[row] = lse;
+    if (p.xe_rows) p.xe_rows[row] = (float)V * lse - sx;
     if (mn - lse < kExtremeLogProb) atomicOr(p.flags + b, FLAG_EXTREME_ROW);
   }
   if (grow) {
+    // this kernel only runs in gathered mode (V > 256): the row is written in its final form minus the occupancy
+    const float sy = p.gathered ? p.s_y * inv : inv, c = p.gathered ? p.c_ls : 0.f;
     int ghead = (int)(((16 - ((uintptr_t)grow & 15)) & 15) >> 2);
     if (ghead > V) ghead = V;
-    for (int v = tid; v < ghead; v += kRowThreads) grow[v] = s[v] * inv;
+    for (int v = tid; v < ghead; v += kRowThreads) grow[v] = fmaf(s[v], sy, -c);
     int gvec = (V - ghead) >> 2;
     float4* g4 = reinterpret_cast<float4*>(grow + ghead);
     for (int v = tid; v < gvec; v += kRowThreads) {
       int o = ghead + (v << 2);
-      g4[v] = make_float4(s[o] * inv, s[o + 1] * inv, s[o + 2] * inv, s[o + 3] * inv);
+      g4[v] = make_float4(fmaf(s[o], sy, -c), fmaf(s[o + 1], sy, -c), fmaf(s[o + 2], sy, -c), fmaf(s[o + 3], sy, -c));
     }
-    for (int v = ghead + (gvec << 2) + tid; v < V; v += kRowThreads) grow[v] = s[v] * inv;
+    for (int v = ghead + (gvec << 2) + tid; v < V; v += kRowThreads) grow[v] = fmaf(s[v], sy, -c);
   }
   if (p.gathered) {
     float* erow = p.em + m.em_off + (long long)t * m.W;

@@ -166,7 +166,8 @@ def _dev_i32(x, name, dev):
 
 
 def ctc_loss_and_grad(acts, labels, act_lens, label_lens, blank=0, grads=None, need_grad=True,
-                      costs=None, loss_sum=None, max_label_len=None):
+                      costs=None, loss_sum=None, max_label_len=None, logit_scale=1.0, label_smoothing=0.0,
+                      loss_scale=1.0, grad_scale=1.0, ls_costs=None):
     """One fused cost-and-gradient evaluation on the current CUDA stream.
 
     acts [T,B,V] CUDA fp32 logits (any strides with a unit vocabulary stride, e.g. the
@@ -177,6 +178,10 @@ def ctc_loss_and_grad(acts, labels, act_lens, label_lens, blank=0, grads=None, n
       * device-resident: ``labels`` a CUDA int32 tensor ``[B, Lmax]`` (padded; entries past ``label_lens[b]`` are
         ignored) with CUDA int32 ``act_lens`` / ``label_lens`` -- planned by a kernel, the call is kernel
         launches only and can be captured into a CUDA graph (``max_label_len`` defaults to ``Lmax``).
+    ``logit_scale`` / ``label_smoothing`` / ``loss_scale`` / ``grad_scale`` (device-resident form only) fuse the
+    arithmetic of the reference's call site into the kernels (b200ctc_options, include/b200ctc.h):
+    logits * logit_scale (1/temperature, ctc.py:306-307), loss_sum = loss_scale * sum_b[(1-ls) cost_b + ls/V * XE_b]
+    (ctc.py:323,329-337), grads = grad_scale * d(loss_sum/loss_scale)/d(scaled logits).
     Returns device tensors ``(costs[B], loss_sum[1], grads[T,B,V] or None)``; nothing synchronises the host.
     """
     _require_cuda(acts)
@@ -207,15 +212,23 @@ def ctc_loss_and_grad(acts, labels, act_lens, label_lens, blank=0, grads=None, n
             nbytes = ctypes.c_size_t()
             _lib.check(lib.b200ctc_get_workspace_bound(T, V, B, Lmax, ctypes.byref(nbytes)), "b200ctc_get_workspace_bound")
             workspace = _workspace(dev_index, stream, nbytes.value)
+            opts = None
+            if logit_scale != 1.0 or label_smoothing != 0.0 or loss_scale != 1.0 or grad_scale != 1.0:
+                opts = ctypes.byref(_lib.Options(float(logit_scale), float(label_smoothing), float(loss_scale),
+                                                 float(grad_scale)))
             st = lib.b200ctc_loss_and_grad_dev(
                 _handle(dev_index), acts.data_ptr(), acts.stride(0), acts.stride(1),
                 grads.data_ptr() if grads is not None else None,
                 labels.data_ptr(), labels.stride(0) if B > 0 and labels.size(1) > 0 else Lmax,
                 label_lens_d.data_ptr(), act_lens_d.data_ptr(),
-                T, V, B, Lmax, int(blank), costs.data_ptr(), loss_sum.data_ptr(),
+                T, V, B, Lmax, int(blank), opts, costs.data_ptr(), loss_sum.data_ptr(),
+                ls_costs.data_ptr() if ls_costs is not None else None,
                 workspace.data_ptr(), workspace.numel(), stream)
             _lib.check(st, "b200ctc_loss_and_grad_dev")
             return costs, loss_sum, grads
+        if logit_scale != 1.0 or label_smoothing != 0.0 or loss_scale != 1.0 or grad_scale != 1.0:
+            raise B200CTCError("logit_scale / label_smoothing / loss_scale / grad_scale need device-resident labels "
+                               "(the warp-ctc style call has no such arguments); see ctc_loss_from_padded")
         labels = _host_i32(labels, "labels")
         act_lens = _host_i32(act_lens, "act_lens")
         label_lens = _host_i32(label_lens, "label_lens")
@@ -369,21 +382,60 @@ def concatenate_labels(ys, y_lens):
     return np.ascontiguousarray(ys[mask], dtype=np.int32)
 
 
-def ctc_loss_from_padded(logits, ys, x_lens, y_lens, label_offset=1, logits_temperature=1.0, average=True):
-    """The loss computation of ``CTC.forward`` (reference: ctc.py:299-326) as one call, device resident.
+class _CTCFromPadded(torch.autograd.Function):
+    """The whole loss computation of ``CTC.forward`` as ONE device-resident call: temperature, ``/ len(xs)`` and
+    the label-smoothing cross entropy are evaluated inside the kernels (b200ctc_options)."""
+
+    @staticmethod
+    def forward(ctx, logits, ys, x_lens, y_lens, inv_temperature, label_smoothing, loss_scale):
+        need_grad = logits.requires_grad
+        _, loss, grads = ctc_loss_and_grad(
+            logits.transpose(0, 1), ys, x_lens, y_lens, blank=0, need_grad=need_grad,
+            logit_scale=inv_temperature, label_smoothing=label_smoothing, loss_scale=loss_scale,
+            grad_scale=loss_scale * inv_temperature)      # d loss / d (unscaled, batch-major) logits
+        ctx.grads = grads
+        return loss
+
+    @staticmethod
+    def backward(ctx, grad_output):
+        g = ctx.grads * grad_output.reshape(-1)[0]        # [T, B, V]
+        return g.transpose(0, 1), None, None, None, None, None, None
+
+
+def _dev_padded_labels(ys, y_lens, dev, label_offset):
+    """Padded ``ys[B, Lmax]`` (+ ``label_offset``) and ``y_lens[B]`` as CUDA int32 tensors (the reference keeps
+    them on the host, ctc.py:295-297: they are uploaded here, a few kilobytes)."""
+    ys = torch.as_tensor(ys) if not isinstance(ys, torch.Tensor) else ys
+    y_lens = torch.as_tensor(y_lens) if not isinstance(y_lens, torch.Tensor) else y_lens
+    if ys.dim() != 2 or ys.size(0) != y_lens.numel():
+        raise B200CTCError("ys must be [B, Lmax] with one length per row")
+    ys = ys.to(device=dev, dtype=torch.int32)
+    if label_offset:
+        ys = ys + int(label_offset)
+    return ys.contiguous(), y_lens.to(device=dev, dtype=torch.int32).contiguous()
+
+
+def ctc_loss_from_padded(logits, ys, x_lens, y_lens, label_offset=1, logits_temperature=1.0, average=True,
+                         label_smoothing=0.0):
+    """The loss computation of ``CTC.forward`` (reference: ctc.py:299-337) as one call, device resident.
 
     logits ``[B, T, V]`` CUDA (batch-major, as the encoder returns them; consumed through a strided view,
     no ``transpose().contiguous()`` copy), ys ``[B, Lmax]`` padded labels WITHOUT the blank offset
-    (``label_offset=1`` reproduces ``ys = ys + 1``, ctc.py:300: index 0 is the blank), x_lens / y_lens ``[B]``.
-    Returns a CUDA scalar tensor: ``sum_b cost_b / B`` (``average=True`` is the reference's ``/ len(xs)``,
-    ctc.py:323) that back-propagates into ``logits``.
+    (``label_offset=1`` reproduces ``ys = ys + 1``, ctc.py:300: index 0 is the blank), x_lens / y_lens ``[B]``
+    (host or device).  ``logits_temperature`` is the reference's "output smoothing" (ctc.py:306-307),
+    ``average=True`` its ``/ len(xs)`` (ctc.py:323), ``label_smoothing`` its ``ls_prob`` (ctc.py:329-337 with
+    models/pytorch_v3/criterion.py:51-80): all three are evaluated inside the kernels, not as tensor passes.
+    Returns a CUDA tensor ``[1]``:  ``(1-ls) * sum_b cost_b / B + ls/V * sum_b sum_{t<x_lens[b]} sum_k -lp[b,t,k] / B``
+    that back-propagates into ``logits``.
     """
     if logits.dim() != 3:
         raise B200CTCError("logits must be [B, T, V]")
-    if logits_temperature != 1:
-        logits = logits / logits_temperature              # "output smoothing", ctc.py:306-307
-    labels = concatenate_labels(ys, y_lens)
-    if label_offset:
-        labels = labels + np.int32(label_offset)
-    loss = ctc_loss(logits.transpose(0, 1), labels, x_lens, y_lens, blank=0, reduction="sum")
-    return loss / logits.size(0) if average else loss
+    _require_cuda(logits)
+    dev = logits.device
+    ys_d, y_lens_d = _dev_padded_labels(ys, y_lens, dev, label_offset)
+    x_lens_d = (x_lens if isinstance(x_lens, torch.Tensor) else torch.as_tensor(np.asarray(x_lens))).to(
+        device=dev, dtype=torch.int32).contiguous()
+    B = logits.size(0)
+    loss_scale = 1.0 / B if (average and B > 0) else 1.0
+    return _CTCFromPadded.apply(logits, ys_d, x_lens_d, y_lens_d, 1.0 / float(logits_temperature),
+                                float(label_smoothing), loss_scale)

@@ -228,3 +228,69 @@ def test_sharded_evaluation_of_one_batch_matches_the_whole_batch():
     assert abs(total - float(loss_all.cpu()[0])) < 1e-5 * float(loss_all.cpu()[0])
     c_ref, _ = ctc_cpu(acts.cpu().numpy(), wl.labels, wl.act_lens, wl.label_lens, 0, precision="f64")
     assert abs(total - c_ref.sum()) < LOSS_RTOL * c_ref.sum()
+
+
+def _call_site_case(rng, B, T, V, Lmax, full_lens=False):
+    logits = rng.randn(B, T, V).astype(np.float32)
+    y_lens = rng.randint(max(1, Lmax // 2), Lmax + 1, size=B).astype(np.int32)
+    ys = np.zeros((B, Lmax), dtype=np.int64)
+    for b in range(B):
+        ys[b, :y_lens[b]] = rng.randint(0, V - 1, size=y_lens[b])
+    x_lens = np.full(B, T, np.int32) if full_lens else np.sort(rng.randint(T - T // 4, T + 1, size=B))[::-1].astype(np.int32)
+    x_lens[0] = T
+    return logits, ys, x_lens, y_lens
+
+
+@pytest.mark.parametrize("B,T,V,Lmax", [(5, 60, 11, 9), (6, 500, 30, 220), (4, 200, 30, 6), (4, 160, 62, 70),
+                                        (3, 260, 100, 120), (3, 200, 300, 80), (2, 120, 1500, 50)])
+@pytest.mark.parametrize("temp,ls", [(1.0, 0.1), (2.0, 0.0), (1.3, 0.2)])
+def test_fused_call_site_temperature_average_label_smoothing(B, T, V, Lmax, temp, ls):
+    """ctc_loss_from_padded = ctc.py:299-337 in one device-resident call: logits / temperature, / len(xs) and the
+    label-smoothing cross entropy are evaluated inside the kernels.  Loss and d loss / d logits against the fp64
+    restatement of the reference's call site (every reducer path: one / two symbols per lane, the loop, the
+    untouched vocabulary entries, gathered mode with both softmax kernels)."""
+    rng = np.random.RandomState(B * 1000 + V + int(temp * 10) + int(ls * 100))
+    logits_np, ys, x_lens, y_lens = _call_site_case(rng, B, T, V, Lmax)
+    logits = torch.from_numpy(logits_np).cuda().requires_grad_(True)
+    loss = b200.ctc_loss_from_padded(logits, ys, x_lens, y_lens, logits_temperature=temp, label_smoothing=ls)
+    loss.backward()
+    torch.cuda.synchronize()
+    loss_ref, g_ref = ctc_ref.ctc_loss_call_site(logits_np, ys, x_lens, y_lens, temp, ls)
+    assert abs(float(loss.detach().cpu()[0]) - loss_ref) < LOSS_RTOL * abs(loss_ref)
+    g = logits.grad.cpu().numpy()
+    assert np.max(np.abs(g - g_ref)) < GRAD_ATOL / B             # the gradient carries the 1/B of the loss
+    for b in range(B):
+        assert np.all(g[b, x_lens[b]:] == 0)                     # padded frames: exactly zero
+    assert ctc_mod.last_fallbacks(with_invalid=True) == (0, 0, 0)
+
+
+def test_fused_options_defaults_are_bit_identical_and_safe_path_honours_them():
+    rng = np.random.RandomState(51)
+    logits_np, ys, x_lens, y_lens = _call_site_case(rng, 4, 80, 12, 10)
+    logits_np[1] *= 60.0                                          # utterance 1: extreme rows -> fp64 safe lattice
+    acts = torch.from_numpy(logits_np).cuda().transpose(0, 1)
+    ys_d = torch.from_numpy(ys + 1).to(torch.int32).cuda()
+    xl, yl = torch.from_numpy(x_lens).cuda(), torch.from_numpy(y_lens).cuda()
+    base = b200.ctc_loss_and_grad(acts, ys_d, xl, yl)
+    same = b200.ctc_loss_and_grad(acts, ys_d, xl, yl, logit_scale=1.0, label_smoothing=0.0, loss_scale=1.0, grad_scale=1.0)
+    assert torch.equal(base[0], same[0]) and torch.equal(base[2], same[2]) and torch.equal(base[1], same[1])
+    assert ctc_mod.last_fallbacks()[0] >= 1
+    logits = torch.from_numpy(logits_np).cuda().requires_grad_(True)
+    loss = b200.ctc_loss_from_padded(logits, ys, x_lens, y_lens, logits_temperature=1.5, label_smoothing=0.1)
+    loss.backward()
+    loss_ref, g_ref = ctc_ref.ctc_loss_call_site(logits_np, ys, x_lens, y_lens, 1.5, 0.1)
+    assert abs(float(loss.detach().cpu()[0]) - loss_ref) < LOSS_RTOL * abs(loss_ref)
+    assert np.max(np.abs(logits.grad.cpu().numpy() - g_ref)) < GRAD_ATOL / 4
+
+
+def test_fused_call_site_cost_only_and_upstream_gradient():
+    rng = np.random.RandomState(52)
+    logits_np, ys, x_lens, y_lens = _call_site_case(rng, 5, 90, 30, 25)
+    with torch.no_grad():
+        loss0 = b200.ctc_loss_from_padded(torch.from_numpy(logits_np).cuda(), ys, x_lens, y_lens,
+                                          logits_temperature=2.0, label_smoothing=0.15)
+    loss_ref, g_ref = ctc_ref.ctc_loss_call_site(logits_np, ys, x_lens, y_lens, 2.0, 0.15)
+    assert abs(float(loss0.cpu()[0]) - loss_ref) < LOSS_RTOL * abs(loss_ref)
+    logits = torch.from_numpy(logits_np).cuda().requires_grad_(True)
+    (3.0 * b200.ctc_loss_from_padded(logits, ys, x_lens, y_lens, logits_temperature=2.0, label_smoothing=0.15)).sum().backward()
+    assert np.max(np.abs(logits.grad.cpu().numpy() - 3.0 * g_ref)) < 3 * GRAD_ATOL / 5

@@ -210,3 +210,29 @@ def test_reductions():
     assert ctc_ref.reduce_costs(costs, [4, 4, 4]) == 9.0
     assert ctc_ref.reduce_costs(costs, [4, 4, 4], size_average=True) == 3.0
     assert ctc_ref.reduce_costs(costs, [4, 4, 4], length_average=True) == 0.75
+
+
+def test_call_site_restatement_matches_torch_autograd():
+    """oracle.ctc_ref.ctc_loss_call_site (ctc.py:299-337 + criterion.py:51-80 in fp64) against the same
+    computation written with torch ops on the CPU in fp64 (log_softmax, F.ctc_loss, the label-smoothing sum)."""
+    import torch
+    rng = np.random.RandomState(0)
+    B, T, V, Lmax = 4, 30, 9, 7
+    logits = rng.randn(B, T, V)
+    y_lens = rng.randint(1, Lmax + 1, size=B)
+    ys = np.zeros((B, Lmax), np.int64)
+    for b in range(B):
+        ys[b, :y_lens[b]] = rng.randint(0, V - 1, size=y_lens[b])
+    x_lens = np.array([30, 28, 22, 19])
+    for temp, ls in [(1.0, 0.0), (2.0, 0.0), (1.0, 0.1), (1.7, 0.2)]:
+        loss, g = ctc_ref.ctc_loss_call_site(logits, ys, x_lens, y_lens, temp, ls)
+        x = torch.tensor(logits, requires_grad=True)
+        lp = torch.log_softmax(x / temp, dim=2)
+        flat = torch.tensor(np.concatenate([ys[b, :y_lens[b]] + 1 for b in range(B)]))
+        ref = torch.nn.functional.ctc_loss(lp.transpose(0, 1), flat, torch.tensor(x_lens), torch.tensor(y_lens),
+                                           blank=0, reduction="sum") / B
+        if ls > 0:
+            ref = ref * (1 - ls) + sum([(-(ls / V) * lp[b, :x_lens[b]]).sum() for b in range(B)]) / B
+        ref.backward()
+        assert abs(float(ref.detach()) - loss) < 1e-12 * abs(loss)
+        assert np.max(np.abs(x.grad.numpy() - g)) < 1e-12
