@@ -193,6 +193,34 @@ B200CTC_API int b200ctc_greedy_decode(const float* logits, int64_t stride_b, int
                           int* out_tokens, int* out_lens, void* stream);
 
 /*
+ * Batched edit distance with error counts; replaces the python loops of compute_wer
+ * (utils/evaluation/edit_distance.py:53-126), which the metric code calls once per utterance
+ * (examples/timit/s5/exp/metrics/phone.py:93-101 and its twins).
+ *
+ *   refs / hyps   DEVICE int32 token ids, pair b at refs[b*ref_stride ..+ref_lens[b]) / hyps[b*hyp_stride ..+hyp_lens[b])
+ *   ref_lens / hyp_lens  DEVICE int32 [B]; values outside [0, max_ref] / [0, max_hyp] are clamped
+ *   out4          DEVICE int32 [B,4]: distance, substitutions, insertions, deletions, with the backtrace
+ *                 preference of the reference (:99-117): match, insertion, substitution, deletion.
+ *   workspace     DEVICE, >= b200ctc_edit_distance_workspace(B, max_ref, max_hyp) bytes
+ * max_ref <= 17000 (three anti-diagonals of the matrix live in shared memory).  The reference indexes its
+ * matrix with -1 at the borders and raises for some inputs (its callers swallow the exception and skip the
+ * utterance); here the first row / column always backtrace as insertions / deletions.
+ */
+B200CTC_API int b200ctc_edit_distance_workspace(int B, int max_ref, int max_hyp, size_t* bytes);
+B200CTC_API int b200ctc_edit_distance(const int* refs, int ref_stride, const int* ref_lens,
+                          const int* hyps, int hyp_stride, const int* hyp_lens,
+                          int B, int max_ref, int max_hyp, int* out4,
+                          void* workspace, size_t workspace_bytes, void* stream);
+
+/*
+ * probs[b,t,:] = softmax(logits[b,t,:] / temperature): the tensor work of CTC.posteriors
+ * (models/pytorch_v3/ctc/ctc.py:455-502) in one pass.  logits: DEVICE fp32, element (b,t,v) at
+ * logits[b*stride_b + t*stride_t + v]; probs: DEVICE fp32 [B,T,V] contiguous.
+ */
+B200CTC_API int b200ctc_softmax_temperature(const float* logits, int64_t stride_b, int64_t stride_t,
+                                int T, int V, int B, float temperature, float* probs, void* stream);
+
+/*
  * Measurement hooks (no counterpart in the reference; used by bench.py for the roofline line).
  * With profiling enabled every b200ctc_loss_and_grad call on this handle brackets each of its
  * kernels with CUDA events on `stream`; b200ctc_get_last_kernel_ms waits for the last call and

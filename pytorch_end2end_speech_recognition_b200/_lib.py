@@ -26,6 +26,9 @@ EXPORTED_SYMBOLS = (
     "b200ctc_loss_and_grad",
     "b200ctc_loss_and_grad_dev",
     "b200ctc_greedy_decode",
+    "b200ctc_edit_distance_workspace",
+    "b200ctc_edit_distance",
+    "b200ctc_softmax_temperature",
     "b200ctc_set_profiling",
     "b200ctc_get_last_kernel_ms",
     "b200ctc_get_last_fallbacks",
@@ -89,6 +92,16 @@ def _declare(lib):
         ctypes.c_void_p, ctypes.c_int64, ctypes.c_int64, ctypes.c_void_p,
         ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int,
         ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]
+    lib.b200ctc_edit_distance_workspace.restype = ctypes.c_int
+    lib.b200ctc_edit_distance_workspace.argtypes = [ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.POINTER(ctypes.c_size_t)]
+    lib.b200ctc_edit_distance.restype = ctypes.c_int
+    lib.b200ctc_edit_distance.argtypes = [
+        ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p,
+        ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_void_p]
+    lib.b200ctc_softmax_temperature.restype = ctypes.c_int
+    lib.b200ctc_softmax_temperature.argtypes = [
+        ctypes.c_void_p, ctypes.c_int64, ctypes.c_int64, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_float,
+        ctypes.c_void_p, ctypes.c_void_p]
     lib.b200ctc_set_profiling.restype = ctypes.c_int
     lib.b200ctc_set_profiling.argtypes = [ctypes.c_void_p, ctypes.c_int]
     lib.b200ctc_get_last_kernel_ms.restype = ctypes.c_int

@@ -517,6 +517,33 @@ int b200ctc_get_plan_cache_stats(b200ctc_handle* h, long long* hits, long long* 
   return B200CTC_STATUS_SUCCESS;
 }
 
+int b200ctc_edit_distance_workspace(int B, int max_ref, int max_hyp, size_t* bytes) {
+  if (!bytes || B < 0 || max_ref < 0 || max_hyp < 0) return B200CTC_STATUS_INVALID_VALUE;
+  *bytes = edit_distance_workspace_bytes(B, max_ref, max_hyp) + kAlign;
+  return B200CTC_STATUS_SUCCESS;
+}
+
+int b200ctc_edit_distance(const int* refs, int ref_stride, const int* ref_lens, const int* hyps, int hyp_stride,
+                          const int* hyp_lens, int B, int max_ref, int max_hyp, int* out4, void* workspace,
+                          size_t workspace_bytes, void* stream_v) {
+  if (B < 0 || max_ref < 0 || max_hyp < 0 || ref_stride < max_ref || hyp_stride < max_hyp) return B200CTC_STATUS_INVALID_VALUE;
+  if (B == 0) return B200CTC_STATUS_SUCCESS;
+  if (!ref_lens || !hyp_lens || !out4 || !workspace || (max_ref > 0 && !refs) || (max_hyp > 0 && !hyps))
+    return B200CTC_STATUS_INVALID_VALUE;
+  if (workspace_bytes < edit_distance_workspace_bytes(B, max_ref, max_hyp)) return B200CTC_STATUS_WORKSPACE_TOO_SMALL;
+  return status_of(launch_edit_distance(refs, ref_stride, ref_lens, hyps, hyp_stride, hyp_lens, B, max_ref, max_hyp, out4,
+                                        workspace, reinterpret_cast<cudaStream_t>(stream_v)));
+}
+
+int b200ctc_softmax_temperature(const float* logits, int64_t stride_b, int64_t stride_t, int T, int V, int B,
+                                float temperature, float* probs, void* stream_v) {
+  if (T < 0 || V < 1 || B < 0 || !(temperature > 0.f)) return B200CTC_STATUS_INVALID_VALUE;
+  if ((long long)B * T == 0) return B200CTC_STATUS_SUCCESS;
+  if (!logits || !probs) return B200CTC_STATUS_INVALID_VALUE;
+  return status_of(launch_softmax_temperature(logits, stride_b, stride_t, T, V, B, 1.0f / temperature, probs,
+                                              reinterpret_cast<cudaStream_t>(stream_v)));
+}
+
 int b200ctc_greedy_decode(const float* logits, int64_t stride_b, int64_t stride_t, const int* lens,
                           int T, int V, int B, int blank, int* out_tokens, int* out_lens,
                           void* stream_v) {

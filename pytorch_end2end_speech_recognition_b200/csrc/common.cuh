@@ -87,6 +87,12 @@ cudaError_t launch_softmax_rows(const CallParams& p, cudaStream_t stream);
 cudaError_t prepare_lattice(CallParams& p, int max_L);     // fills fast_l_cap; error when not even the safe lattice fits
 cudaError_t launch_lattice(const CallParams& p, int max_L, cudaStream_t stream);
 cudaError_t launch_plan(const CallParams& p, UttMeta* meta, int* order, int* flags, cudaStream_t stream);
+size_t edit_distance_workspace_bytes(int B, int max_ref, int max_hyp);
+cudaError_t launch_edit_distance(const int* refs, int ref_stride, const int* ref_lens, const int* hyps, int hyp_stride,
+                                 const int* hyp_lens, int B, int max_ref, int max_hyp, int* out4, void* workspace,
+                                 cudaStream_t stream);
+cudaError_t launch_softmax_temperature(const float* logits, long long stride_b, long long stride_t, int T, int V, int B,
+                                       float inv_temperature, float* probs, cudaStream_t stream);
 cudaError_t launch_greedy(const float* logits, long long stride_b, long long stride_t, const int* lens,
                           int T, int V, int B, int blank, int* out_tokens, int* out_lens,
                           cudaStream_t stream);

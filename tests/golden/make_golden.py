@@ -17,6 +17,13 @@
                       for those three names -- every line of CTC arithmetic that runs is the
                       reference's.  This is what pins oracle/ to the reference.
 
+  edit_distance_golden.npz : (distance, substitutions, insertions, deletions) returned by the REFERENCE's own
+                      ``compute_wer`` (utils/evaluation/edit_distance.py:53-126, imported from /root/reference;
+                      the module-level ``import Levenshtein`` -- a package that is not installed and that
+                      compute_wer never calls -- is satisfied by an empty stub) on seeded token lists.  Pairs on
+                      which the reference raises (its backtrace indexes the matrix with -1 at the borders; its
+                      callers swallow the exception, phone.py:92-103) are recorded with ``ok = 0``.
+
 Usage: python tests/golden/make_golden.py
 """
 import os
@@ -172,8 +179,55 @@ def reference_ctc_cases():
     np.savez_compressed(os.path.join(HERE, "ctc_reference_golden.npz"), **out)
 
 
+def edit_distance_cases():
+    import importlib.util
+    import types
+    sys.modules.setdefault("Levenshtein", types.ModuleType("Levenshtein"))      # never called by compute_wer
+    spec = importlib.util.spec_from_file_location("reference_edit_distance",
+                                                  "/root/reference/utils/evaluation/edit_distance.py")
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    rng = np.random.RandomState(53)
+    refs, hyps, outs, oks = [], [], [], []
+    for i in range(160):
+        V = int(rng.choice([2, 3, 5, 30, 62]))
+        R, H = int(rng.randint(0 if i % 9 == 0 else 1, 40)), int(rng.randint(0 if i % 7 == 0 else 1, 40))
+        ref = rng.randint(0, V, size=R)
+        if i % 3 == 0 and R > 0:                      # hypothesis = corrupted reference (the realistic case)
+            hyp = list(ref)
+            for _ in range(rng.randint(0, 6)):
+                op, pos = rng.randint(3), rng.randint(0, max(len(hyp), 1))
+                if op == 0 and hyp:
+                    hyp[min(pos, len(hyp) - 1)] = int(rng.randint(0, V))
+                elif op == 1:
+                    hyp.insert(pos, int(rng.randint(0, V)))
+                elif hyp:
+                    del hyp[min(pos, len(hyp) - 1)]
+            hyp = np.array(hyp, dtype=np.int64)
+        else:
+            hyp = rng.randint(0, V, size=H)
+        try:
+            with np.errstate(all="ignore"):
+                wer, sub, ins, dele = mod.compute_wer([int(x) for x in ref], [int(x) for x in hyp], normalize=False)
+            res, ok = (int(wer), int(sub), int(ins), int(dele)), 1
+        except Exception:
+            res, ok = (0, 0, 0, 0), 0
+        refs.append(ref); hyps.append(hyp); outs.append(res); oks.append(ok)
+    rmax, hmax = max(len(r) for r in refs), max(len(h) for h in hyps)
+    ref_pad = np.full((len(refs), rmax), -1, np.int32)
+    hyp_pad = np.full((len(hyps), hmax), -2, np.int32)
+    for b, (r, h) in enumerate(zip(refs, hyps)):
+        ref_pad[b, :len(r)] = r
+        hyp_pad[b, :len(h)] = h
+    np.savez_compressed(os.path.join(HERE, "edit_distance_golden.npz"), refs=ref_pad, hyps=hyp_pad,
+                        ref_lens=np.array([len(r) for r in refs], np.int32),
+                        hyp_lens=np.array([len(h) for h in hyps], np.int32),
+                        out=np.array(outs, np.int32), ok=np.array(oks, np.int32))
+
+
 if __name__ == "__main__":
     greedy_cases()
     ctc_cases()
     reference_ctc_cases()
+    edit_distance_cases()
     print("golden fixtures written to", HERE)

@@ -236,3 +236,19 @@ def test_call_site_restatement_matches_torch_autograd():
         ref.backward()
         assert abs(float(ref.detach()) - loss) < 1e-12 * abs(loss)
         assert np.max(np.abs(x.grad.numpy() - g)) < 1e-12
+
+
+def test_edit_distance_oracle_matches_the_reference_function(golden_dir):
+    """oracle/eval_ref.compute_wer against the outputs of the reference's own compute_wer
+    (tests/golden/edit_distance_golden.npz); where the reference raised (ok = 0) only the distance identity
+    sub + ins + del == distance and the length identity are checked."""
+    from oracle import eval_ref
+    z = np.load(os.path.join(golden_dir, "edit_distance_golden.npz"))
+    assert int(z["ok"].sum()) >= 100
+    for b in range(len(z["ok"])):
+        ref, hyp = z["refs"][b, :z["ref_lens"][b]], z["hyps"][b, :z["hyp_lens"][b]]
+        got = eval_ref.compute_wer(list(ref), list(hyp))
+        if z["ok"][b]:
+            assert got == tuple(int(x) for x in z["out"][b]), b
+        d, sub, ins, dele = got
+        assert d == sub + ins + dele and len(ref) - sub - dele == len(hyp) - sub - ins
