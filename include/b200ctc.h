@@ -193,6 +193,27 @@ B200CTC_API int b200ctc_greedy_decode(const float* logits, int64_t stride_b, int
                           int* out_tokens, int* out_lens, void* stream);
 
 /*
+ * Batched CTC prefix beam search without a language model; replaces the python loops of
+ * models/pytorch_v3/ctc/decoders/beam_search_decoder.py:33-124 (called with beam_width 10 for every published
+ * error rate and with beam_width 2 by every reference test).  One CTA per utterance; scores are accumulated in
+ * float64 with numpy's logaddexp formula on the float32 log-probabilities; the surviving prefixes and their
+ * order (ties included) are the reference's.
+ *
+ *   log_probs   DEVICE fp32 log-probabilities (log_softmax output, ctc.py:439-441), element (b,t,v) at
+ *               log_probs[b*stride_b + t*stride_t + v]
+ *   lens        DEVICE int32 [B]; clamped to [0, T]
+ *   beam_width  1..64
+ *   out_tokens  DEVICE int32 [B,T]: the best hypothesis of utterance b in out_tokens[b*T .. b*T+out_lens[b]), then -1
+ *   out_lens    DEVICE int32 [B];  out_scores  DEVICE fp32 [B] or NULL: log p of the best prefix
+ *   workspace   DEVICE, >= b200ctc_beam_search_workspace(B, T, V, beam_width) bytes
+ */
+B200CTC_API int b200ctc_beam_search_workspace(int B, int T, int V, int beam_width, size_t* bytes);
+B200CTC_API int b200ctc_beam_search(const float* log_probs, int64_t stride_b, int64_t stride_t,
+                        const int* lens, int T, int V, int B, int blank, int beam_width,
+                        int* out_tokens, int* out_lens, float* out_scores,
+                        void* workspace, size_t workspace_bytes, void* stream);
+
+/*
  * Batched edit distance with error counts; replaces the python loops of compute_wer
  * (utils/evaluation/edit_distance.py:53-126), which the metric code calls once per utterance
  * (examples/timit/s5/exp/metrics/phone.py:93-101 and its twins).

@@ -26,6 +26,8 @@ EXPORTED_SYMBOLS = (
     "b200ctc_loss_and_grad",
     "b200ctc_loss_and_grad_dev",
     "b200ctc_greedy_decode",
+    "b200ctc_beam_search_workspace",
+    "b200ctc_beam_search",
     "b200ctc_edit_distance_workspace",
     "b200ctc_edit_distance",
     "b200ctc_softmax_temperature",
@@ -92,6 +94,14 @@ def _declare(lib):
         ctypes.c_void_p, ctypes.c_int64, ctypes.c_int64, ctypes.c_void_p,
         ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int,
         ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]
+    lib.b200ctc_beam_search_workspace.restype = ctypes.c_int
+    lib.b200ctc_beam_search_workspace.argtypes = [ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int,
+                                                  ctypes.POINTER(ctypes.c_size_t)]
+    lib.b200ctc_beam_search.restype = ctypes.c_int
+    lib.b200ctc_beam_search.argtypes = [
+        ctypes.c_void_p, ctypes.c_int64, ctypes.c_int64, ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_int,
+        ctypes.c_int, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,
+        ctypes.c_size_t, ctypes.c_void_p]
     lib.b200ctc_edit_distance_workspace.restype = ctypes.c_int
     lib.b200ctc_edit_distance_workspace.argtypes = [ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.POINTER(ctypes.c_size_t)]
     lib.b200ctc_edit_distance.restype = ctypes.c_int

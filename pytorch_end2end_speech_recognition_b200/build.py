@@ -16,7 +16,7 @@ CSRC = os.path.join(PKG_DIR, "csrc")
 LIB_DIR = os.path.join(PKG_DIR, "lib")
 LIB_PATH = os.environ.get("B200CTC_LIB") or os.path.join(LIB_DIR, "libb200ctc.so")   # B200CTC_LIB: developer variants
 
-SOURCES = ["api.cu", "plan.cu", "softmax_rows.cu", "lattice.cu", "greedy.cu", "eval.cu"]
+SOURCES = ["api.cu", "plan.cu", "softmax_rows.cu", "lattice.cu", "greedy.cu", "beam.cu", "eval.cu"]
 
 NVCC_FLAGS = [
     "-O3", "-std=c++17",

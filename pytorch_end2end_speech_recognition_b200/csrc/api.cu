@@ -517,6 +517,24 @@ int b200ctc_get_plan_cache_stats(b200ctc_handle* h, long long* hits, long long* 
   return B200CTC_STATUS_SUCCESS;
 }
 
+int b200ctc_beam_search_workspace(int B, int T, int V, int beam_width, size_t* bytes) {
+  if (!bytes || B < 0 || T < 0 || V < 1 || beam_width < 1 || beam_width > 64) return B200CTC_STATUS_INVALID_VALUE;
+  *bytes = beam_search_workspace_bytes(B, T, V, beam_width) + kAlign;
+  return B200CTC_STATUS_SUCCESS;
+}
+
+int b200ctc_beam_search(const float* log_probs, int64_t stride_b, int64_t stride_t, const int* lens, int T, int V,
+                        int B, int blank, int beam_width, int* out_tokens, int* out_lens, float* out_scores,
+                        void* workspace, size_t workspace_bytes, void* stream_v) {
+  if (T < 0 || V < 1 || B < 0 || blank < 0 || blank >= V || beam_width < 1 || beam_width > 64)
+    return B200CTC_STATUS_INVALID_VALUE;
+  if (B == 0) return B200CTC_STATUS_SUCCESS;
+  if (!lens || !out_lens || !workspace || (T > 0 && (!log_probs || !out_tokens))) return B200CTC_STATUS_INVALID_VALUE;
+  if (workspace_bytes < beam_search_workspace_bytes(B, T, V, beam_width)) return B200CTC_STATUS_WORKSPACE_TOO_SMALL;
+  return status_of(launch_beam_search(log_probs, stride_b, stride_t, lens, T, V, B, blank, beam_width, out_tokens,
+                                      out_lens, out_scores, workspace, reinterpret_cast<cudaStream_t>(stream_v)));
+}
+
 int b200ctc_edit_distance_workspace(int B, int max_ref, int max_hyp, size_t* bytes) {
   if (!bytes || B < 0 || max_ref < 0 || max_hyp < 0) return B200CTC_STATUS_INVALID_VALUE;
   *bytes = edit_distance_workspace_bytes(B, max_ref, max_hyp) + kAlign;

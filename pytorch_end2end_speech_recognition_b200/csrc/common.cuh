@@ -93,6 +93,10 @@ cudaError_t launch_edit_distance(const int* refs, int ref_stride, const int* ref
                                  cudaStream_t stream);
 cudaError_t launch_softmax_temperature(const float* logits, long long stride_b, long long stride_t, int T, int V, int B,
                                        float inv_temperature, float* probs, cudaStream_t stream);
+size_t beam_search_workspace_bytes(int B, int T, int V, int beam_width);
+cudaError_t launch_beam_search(const float* log_probs, long long stride_b, long long stride_t, const int* lens, int T,
+                               int V, int B, int blank, int beam_width, int* out_tokens, int* out_lens,
+                               float* out_scores, void* workspace, cudaStream_t stream);
 cudaError_t launch_greedy(const float* logits, long long stride_b, long long stride_t, const int* lens,
                           int T, int V, int B, int blank, int* out_tokens, int* out_lens,
                           cudaStream_t stream);

@@ -16,7 +16,7 @@ import torch
 
 from . import _lib
 from ._lib import B200CTCError
-from .decode import greedy_decode
+from .decode import beam_search_decode, greedy_decode
 
 
 def _padded_i32(seqs, dev):
@@ -93,15 +93,19 @@ def posteriors(logits, temperature=1.0):
     return out
 
 
-def evaluate_batch(logits, x_lens, ys, y_lens, blank=0, label_offset=1):
-    """Greedy decode + edit distance for a whole mini-batch, device resident.
+def evaluate_batch(logits, x_lens, ys, y_lens, blank=0, label_offset=1, beam_width=1):
+    """Decode (greedy for ``beam_width == 1``, else prefix beam search on ``log_softmax(logits)``, the choice
+    ``CTC.decode`` makes, ctc.py:435-441) + edit distance for a whole mini-batch, device resident.
 
     logits ``[B, T, V]`` CUDA; ys ``[B, Lmax]`` reference labels WITHOUT the blank offset (as the dataset
     stores them), y_lens ``[B]``.  The hypotheses are shifted by ``-label_offset`` exactly as ``CTC.decode`` does
     (``best_hyps -= 1``, ctc.py:444).  Returns ``(errors[B,4] int32 CUDA, hyp_tokens[B,T], hyp_lens[B])`` with
     errors = (distance, sub, ins, del) per utterance; ``errors.sum(0)`` over a data set divided by
     ``y_lens.sum()`` gives PER / CER and its breakdown (phone.py:119-126)."""
-    tokens, hyp_lens = greedy_decode(logits, x_lens, blank)
+    if int(beam_width) == 1:
+        tokens, hyp_lens = greedy_decode(logits, x_lens, blank)
+    else:
+        tokens, hyp_lens = beam_search_decode(torch.log_softmax(logits, dim=-1), x_lens, beam_width, blank)
     hyps = tokens - int(label_offset)                       # padding (-1) becomes more negative: never read
     dev = logits.device
     refs = torch.as_tensor(ys).to(device=dev, dtype=torch.int32)

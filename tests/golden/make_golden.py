@@ -24,6 +24,14 @@
                       which the reference raises (its backtrace indexes the matrix with -1 at the borders; its
                       callers swallow the exception, phone.py:92-103) are recorded with ``ok = 0``.
 
+  beam_golden.npz   : hypotheses of the REFERENCE's own BeamSearchDecoder
+                      (models/pytorch_v3/ctc/decoders/beam_search_decoder.py), imported from /root/reference and
+                      called per utterance, beam widths 1 / 2 / 10 / 20, fed float32 log-softmax outputs upcast to
+                      float64 -- the arithmetic the reference performs under the numpy it was written for (python
+                      float + float32 scalar = float64 before NEP 50).  The hypotheses it returns for the float32
+                      array itself under this container's numpy 2 (float32 arithmetic) are stored next to them
+                      (``hyp32_*``) and are identical on every case.
+
 Usage: python tests/golden/make_golden.py
 """
 import os
@@ -225,9 +233,51 @@ def edit_distance_cases():
                         out=np.array(outs, np.int32), ok=np.array(oks, np.int32))
 
 
+def beam_cases():
+    sys.path.insert(0, "/root/reference")
+    from models.pytorch_v3.ctc.decoders.beam_search_decoder import BeamSearchDecoder  # the reference itself
+    dec = BeamSearchDecoder(blank_index=0)
+    rng = np.random.RandomState(77)
+    out = {}
+    shapes = [(3, 30, 6, 2), (2, 40, 30, 10), (2, 50, 30, 20), (2, 35, 62, 10), (3, 25, 5, 1), (2, 20, 30, 2),
+              (2, 28, 3, 10), (1, 60, 30, 10)]
+    n_same = 0
+    for i, (B, T, V, W) in enumerate(shapes):
+        scale = [1.0, 2.0, 3.0, 1.5, 1.0, 4.0, 1.0, 2.5][i]
+        logits = (rng.randn(B, T, V) * scale).astype(np.float32)
+        if i in (1, 7):
+            logits[:, :, 0] += 2.0                    # blank-dominated, as a trained CTC model's output
+        if i == 4:
+            logits[0, :, :] = 0.0                     # exact ties everywhere: the tie order of the sort decides
+        lp = torch.log_softmax(torch.from_numpy(logits), dim=-1).numpy()           # float32, as ctc.py:439-441 feeds it
+        x_lens = rng.randint(T // 2, T + 1, size=B)
+        x_lens[0] = T
+        if i == 6:
+            x_lens[1] = 0
+        hyps, hyps32 = [], []
+        for b in range(B):
+            with np.errstate(all="ignore"):
+                h = dec(lp[b:b + 1].astype(np.float64), x_lens[b:b + 1], beam_width=W)
+                h32 = dec(lp[b:b + 1], x_lens[b:b + 1], beam_width=W)
+            hyps.append(np.asarray(h[0], dtype=np.int64).reshape(-1))
+            hyps32.append(np.asarray(h32[0], dtype=np.int64).reshape(-1))
+            n_same += int(np.array_equal(hyps[-1], hyps32[-1]))
+        out["log_probs_%d" % i] = lp
+        out["x_lens_%d" % i] = x_lens.astype(np.int32)
+        out["beam_%d" % i] = np.array(W)
+        out["hyp_lens_%d" % i] = np.array([len(h) for h in hyps], dtype=np.int32)
+        out["hyp_flat_%d" % i] = np.concatenate(hyps) if hyps else np.zeros(0, np.int64)
+        out["hyp32_lens_%d" % i] = np.array([len(h) for h in hyps32], dtype=np.int32)
+        out["hyp32_flat_%d" % i] = np.concatenate(hyps32) if hyps32 else np.zeros(0, np.int64)
+    out["n_cases"] = np.array(len(shapes))
+    print("beam: float64 and float32 runs of the reference agree on %d of %d utterances" % (n_same, sum(s[0] for s in shapes)))
+    np.savez_compressed(os.path.join(HERE, "beam_golden.npz"), **out)
+
+
 if __name__ == "__main__":
     greedy_cases()
     ctc_cases()
     reference_ctc_cases()
     edit_distance_cases()
+    beam_cases()
     print("golden fixtures written to", HERE)

@@ -252,3 +252,18 @@ def test_edit_distance_oracle_matches_the_reference_function(golden_dir):
             assert got == tuple(int(x) for x in z["out"][b]), b
         d, sub, ins, dele = got
         assert d == sub + ins + dele and len(ref) - sub - dele == len(hyp) - sub - ins
+
+
+def test_beam_search_oracle_matches_the_reference_decoder(golden_dir):
+    from oracle import beam_ref
+    z = np.load(os.path.join(golden_dir, "beam_golden.npz"))
+    for i in range(int(z["n_cases"])):
+        lp, x_lens, W = z["log_probs_%d" % i], z["x_lens_%d" % i], int(z["beam_%d" % i])
+        offs = np.concatenate([[0], np.cumsum(z["hyp_lens_%d" % i])])
+        assert np.array_equal(z["hyp_lens_%d" % i], z["hyp32_lens_%d" % i])          # fp32 run of the reference: same result
+        assert np.array_equal(z["hyp_flat_%d" % i], z["hyp32_flat_%d" % i])
+        for b in range(lp.shape[0]):
+            if lp.shape[1] * lp.shape[2] * W > 20000:
+                continue                                                            # keep the CPU suite short
+            hyp, _ = beam_ref.beam_search(lp[b], x_lens[b], W)
+            assert hyp == list(z["hyp_flat_%d" % i][offs[b]:offs[b + 1]]), (i, b)
