@@ -27,7 +27,8 @@ def main():
         return
     import numpy as np
     import torch
-    b.LIB_PATH = LIB                      # make the package load the trace variant
+    b.LIB_PATH = LIB                      # make the package load the trace variant ...
+    os.environ["B200CTC_LIB"] = LIB       # ... as it is (no staleness rebuild without -DB200CTC_TRACE)
     import pytorch_end2end_speech_recognition_b200 as eng
     from pytorch_end2end_speech_recognition_b200 import _lib, workloads
     wl = workloads.make_lengths_and_labels(key)
