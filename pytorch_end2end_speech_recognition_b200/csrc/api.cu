@@ -31,7 +31,7 @@ inline size_t align_up(size_t x) { return (x + kAlign - 1) / kAlign * kAlign; }
 struct WorkspaceLayout {
   size_t blob_bytes;   // meta + order + flags + labels
   size_t off_meta, off_order, off_flags, off_labels;
-  size_t off_lse, off_xe_rows, off_xe_costs, off_em, off_scratch;
+  size_t off_lse, off_xe_rows, off_xe_costs, off_symtab, off_nseg, off_em, off_scratch;
   size_t total;
 };
 
@@ -67,7 +67,7 @@ BatchTotals totals_from_bound(int T, int B, int max_label_len) {
 // them); the host call keeps them, with the labels, in the handle's staging slots.
 // Small vocabularies never run the lattice in gathered mode: the `em` region then holds the softmax rows of a
 // cost-only call (no gradient buffer to leave them in).
-WorkspaceLayout make_layout(const BatchTotals& t, int T, int B, int V) {
+WorkspaceLayout make_layout(const BatchTotals& t, int T, int B, int V, long long symtab_ints) {
   WorkspaceLayout w;
   size_t off = 0;
   w.off_meta = off;   off += align_up((size_t)B * sizeof(UttMeta));
@@ -78,6 +78,8 @@ WorkspaceLayout make_layout(const BatchTotals& t, int T, int B, int V) {
   w.off_lse = off;    off += align_up((size_t)T * B * sizeof(float));
   w.off_xe_rows = off; off += align_up((size_t)T * B * sizeof(float));   // label smoothing: per-row cross-entropy terms
   w.off_xe_costs = off; off += align_up((size_t)B * sizeof(float));
+  w.off_symtab = off; off += align_up((size_t)(V >= kGatherMinV ? symtab_ints : 0) * sizeof(int));
+  w.off_nseg = off;   off += align_up((size_t)B * sizeof(int));
   const size_t em_floats = V >= kGatherMinV ? (size_t)t.em_floats : (size_t)T * B * V;
   w.off_em = off;     off += align_up(em_floats * sizeof(float));
   w.off_scratch = off; off += align_up((size_t)t.scratch_units * kGroupBytes);
@@ -149,8 +151,9 @@ int run_kernels(b200ctc_handle* h, CallParams& p, int max_L, cudaStream_t stream
   e = launch_softmax_rows(p, stream);
   if (prof) cudaEventRecord(h->prof[1], stream);
   if (e == cudaSuccess) e = launch_lattice(p, max_L, stream);
+  if (prof) cudaEventRecord(h->prof[2], stream);
+  if (e == cudaSuccess && p.gathered && p.grads) e = launch_apply_occupancy(p, stream);
   if (prof) {
-    cudaEventRecord(h->prof[2], stream);
     cudaEventRecord(h->prof[3], stream);
     h->prof_valid = true;
   }
@@ -173,6 +176,8 @@ void fill_common(CallParams& p, const float* acts, int64_t as_t, int64_t as_b, f
   p.rescale = (p.s_y != 1.f || p.s_occ != 1.f || p.c_ls != 0.f) ? 1 : 0;
   p.xe_rows = lsp != 0.f ? reinterpret_cast<float*>(ws + lay.off_xe_rows) : nullptr;
   p.xe_costs = ls_costs ? ls_costs : reinterpret_cast<float*>(ws + lay.off_xe_costs);
+  p.sym_tab = reinterpret_cast<int*>(ws + lay.off_symtab);
+  p.nseg = reinterpret_cast<int*>(ws + lay.off_nseg);
   p.acts = acts;
   p.as_t = as_t;
   p.as_b = as_b;
@@ -248,13 +253,13 @@ int b200ctc_get_workspace_size(const int* label_lens, const int* act_lens, int T
   BatchTotals t;
   int st = totals_from_lens(label_lens, act_lens, T, B, &t);
   if (st != B200CTC_STATUS_SUCCESS) return st;
-  *bytes = make_layout(t, T, B, V).total + kAlign;
+  *bytes = make_layout(t, T, B, V, t.sum_labels).total + kAlign;
   return B200CTC_STATUS_SUCCESS;
 }
 
 int b200ctc_get_workspace_bound(int T, int V, int B, int max_label_len, size_t* bytes) {
   if (!bytes || T < 0 || V < 1 || B < 0 || max_label_len < 0) return B200CTC_STATUS_INVALID_VALUE;
-  *bytes = make_layout(totals_from_bound(T, B, max_label_len), T, B, V).total + kAlign;
+  *bytes = make_layout(totals_from_bound(T, B, max_label_len), T, B, V, (long long)B * max_label_len).total + kAlign;
   return B200CTC_STATUS_SUCCESS;
 }
 
@@ -283,7 +288,7 @@ int b200ctc_loss_and_grad(b200ctc_handle* h, const float* acts, int64_t acts_str
   if (tot.sum_labels > 0 && !flat_labels) return B200CTC_STATUS_INVALID_VALUE;
   if (tot.sum_labels > 0x7fffffffLL) return B200CTC_STATUS_UNSUPPORTED;
   if ((long long)B * V * 4 > 0x7fffffffLL) return B200CTC_STATUS_UNSUPPORTED;   // frame stride of the gradient rows in bytes (int32 in the lattice)
-  const WorkspaceLayout lay = make_layout(tot, T, B, V);
+  const WorkspaceLayout lay = make_layout(tot, T, B, V, tot.sum_labels);
   unsigned char* ws = reinterpret_cast<unsigned char*>(
       (reinterpret_cast<uintptr_t>(workspace) + kAlign - 1) / kAlign * kAlign);
   const size_t lost = (size_t)(ws - reinterpret_cast<unsigned char*>(workspace));
@@ -371,6 +376,8 @@ int b200ctc_loss_and_grad(b200ctc_handle* h, const float* acts, int64_t acts_str
       m.W = em_width_of(L);
       m.scratch_off = scratch_off;
       m.em_off = em_off;
+      m.sym_off = (int)lab_off;
+      m.pad_ = 0;
       lab_off += L;
       em_off += (long long)Tb * m.W;
       scratch_off += (long long)(Tb + 1) * m.J;
@@ -441,7 +448,7 @@ int b200ctc_loss_and_grad_dev(b200ctc_handle* h, const float* acts, int64_t acts
     return B200CTC_STATUS_INVALID_VALUE;
   if ((long long)B * V * 4 > 0x7fffffffLL || (long long)B * label_stride > 0x7fffffffLL || B > 65536)
     return B200CTC_STATUS_UNSUPPORTED;
-  const WorkspaceLayout lay = make_layout(totals_from_bound(T, B, max_label_len), T, B, V);
+  const WorkspaceLayout lay = make_layout(totals_from_bound(T, B, max_label_len), T, B, V, (long long)B * max_label_len);
   unsigned char* ws = reinterpret_cast<unsigned char*>(
       (reinterpret_cast<uintptr_t>(workspace) + kAlign - 1) / kAlign * kAlign);
   const size_t lost = (size_t)(ws - reinterpret_cast<unsigned char*>(workspace));

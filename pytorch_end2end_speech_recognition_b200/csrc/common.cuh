@@ -22,6 +22,8 @@ struct UttMeta {
   int W;            // emission-row width in gathered mode: round_up(L+1, 4)
   long long scratch_off;  // offset of its alpha/beta scratch, in 32-byte units (one unit per group per frame)
   long long em_off;       // offset of its gathered emission rows, in floats (gathered mode only)
+  int sym_off;            // offset of its distinct-symbol list in CallParams::sym_tab (gathered mode only)
+  int pad_;
 };
 
 // Device views of one call, shared by all kernels.
@@ -42,6 +44,11 @@ struct CallParams {
   float* costs;           // [B]
   float* loss_sum;        // [1] or nullptr
   int gathered;           // 1: lattice reads emissions from `em`, 0: from the softmax rows in `yrows`
+  // Gathered mode leaves the per-symbol occupancy of frame t in the emission row em[t] it no longer needs
+  // ([0] blank, [1 + u] distinct symbol u) instead of one RED per (frame, symbol) into gradient rows that have
+  // long left the L2; apply_occupancy_kernel subtracts them afterwards, all frames in parallel.
+  int* sym_tab;           // distinct symbols of every utterance (at meta[b].sym_off), written by the lattice prologue
+  int* nseg;              // [B] their number
   int fast_l_cap;         // longest label sequence the block-exponent lattice takes (window count and shared-memory budget)
   // Fused call-site arithmetic (b200ctc_options; reference: models/pytorch_v3/ctc/ctc.py:306-307,323,329-337):
   //   z = logit_scale * acts;  grads = s_y * softmax(z) - s_occ * occupancy - c_ls   (rows t < T_b)
@@ -67,7 +74,8 @@ __device__ __forceinline__ void pdl_wait_primary() { asm volatile("griddepcontro
 enum UttFlags : int {
   FLAG_EXTREME_ROW = 1,    // some softmax probability of the utterance is below 2^-100: use the safe lattice
   FLAG_PRECISION_LOST = 2, // the block-exponent lattice saw a live state lose range: redo with the safe lattice
-  FLAG_INVALID_INPUT = 4   // device-resident call: a label or a length of the utterance is out of range (cost NaN, zero gradient)
+  FLAG_INVALID_INPUT = 4,  // device-resident call: a label or a length of the utterance is out of range (cost NaN, zero gradient)
+  FLAG_OCC_ROWS = 8        // gathered mode: the fast lattice left the utterance's occupancy in its emission rows
 };
 
 constexpr int kGroupBytes = 32;  // scratch bytes per (frame, group): the safe lattice stores 4 doubles
@@ -86,6 +94,7 @@ __host__ __device__ inline int em_width_of(int L) { return (L + 1 + 3) / 4 * 4; 
 cudaError_t launch_softmax_rows(const CallParams& p, cudaStream_t stream);
 cudaError_t prepare_lattice(CallParams& p, int max_L);     // fills fast_l_cap; error when not even the safe lattice fits
 cudaError_t launch_lattice(const CallParams& p, int max_L, cudaStream_t stream);
+cudaError_t launch_apply_occupancy(const CallParams& p, cudaStream_t stream);
 cudaError_t launch_plan(const CallParams& p, UttMeta* meta, int* order, int* flags, cudaStream_t stream);
 size_t edit_distance_workspace_bytes(int B, int max_ref, int max_hyp);
 cudaError_t launch_edit_distance(const int* refs, int ref_stride, const int* ref_lens, const int* hyps, int hyp_stride,

@@ -41,6 +41,8 @@ __global__ void __launch_bounds__(2 * (NWMAX + kReducers) * 32, 1) lattice_kerne
       __syncthreads();
       const int why = *abort_word;
       use_safe = why != 0;
+      if (!use_safe && p.gathered && p.grads != nullptr && threadIdx.x == 0)
+        atomicOr(p.flags + b, FLAG_OCC_ROWS);        // the occupancy of every frame sits in the emission rows
       if (use_safe && why != kAbortExtremeRow) {
         dirty = p.grads != nullptr;  // part of the gradient rows may already have been rewritten
         if (threadIdx.x == 0) atomicOr(p.flags + b, FLAG_PRECISION_LOST);
@@ -165,6 +167,36 @@ cudaError_t launch_lattice_t(const CallParams& p, size_t smem, cudaStream_t stre
   return cudaLaunchKernelEx(&cfg, lattice_kernel<K, NWMAX, NS>, p);
 }
 
+// Gathered mode, after the lattice: grads[t,b,symbol] -= s_occ * occupancy for the blank and every distinct symbol
+// of the utterance, one warp per frame row.  Each (frame, symbol) entry is touched once: plain read-modify-write.
+__global__ void __launch_bounds__(256) apply_occupancy_kernel(CallParams p) {
+  const int lane = threadIdx.x & 31;
+  const long long row = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (row >= (long long)p.T * p.B) return;
+  const int t = (int)(row / p.B), b = (int)(row - (long long)t * p.B);
+  const UttMeta m = p.meta[b];
+  if (t >= m.T || !(p.flags[b] & FLAG_OCC_ROWS)) return;
+  const float* occ = p.em + m.em_off + (long long)t * m.W;
+  float* g = p.grads + row * p.V;
+  const int* syms = p.sym_tab + m.sym_off;
+  const int n = p.nseg[b];
+  for (int u = lane; u < n; u += 32) {
+    const int k = __ldg(syms + u);
+    g[k] = fmaf(-p.s_occ, __ldcg(occ + 1 + u), g[k]);
+  }
+  if (lane == 0) g[p.blank] = fmaf(-p.s_occ, __ldcg(occ), g[p.blank]);
+}
+
+}  // namespace
+
+cudaError_t launch_apply_occupancy(const CallParams& p, cudaStream_t stream) {
+  const long long rows = (long long)p.T * p.B;
+  if (rows == 0) return cudaSuccess;
+  apply_occupancy_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, stream>>>(p);
+  return cudaGetLastError();
+}
+
+namespace {
 }  // namespace
 
 cudaError_t prepare_lattice(CallParams& p, int max_L) {

@@ -955,13 +955,13 @@ __device__ __forceinline__ void reduce_frame(const CallParams& p, const FastComm
       if (u < n_seg) {
         const int sy_ = cm.ix.seg_sym[u];
         if (!gathered) grow[sy_] = fmaf(-so, tot, fmaf(sy, yrow[sy_], -cl));
-        else atomicAdd(grow + sy_, -so * tot);          // K1 left s_y * y - c_ls in the row
+        else grow[1 + u] = tot;                         // gathered: `grow` is the frame's emission row, now its occupancy row
       }
     }
     accb = warp_sum_q30(accb);
     if (lane == 0) {
       if (!gathered) grow[p.blank] = fmaf(-so, accb, fmaf(sy, yrow[p.blank], -cl));
-      else atomicAdd(grow + p.blank, -so * accb);
+      else grow[0] = accb;
     }
   }
   if (p.rescale && !gathered) {          // entries the utterance never touches: s_y * y - c_ls
@@ -1039,6 +1039,11 @@ __device__ void fast_side_helper(const CallParams& p, int b, const UttMeta& m, c
     if (!total_probability(c.sm, NW, inv_mP, eP, log2P)) return;
   }
   const bool reduce = p.grads != nullptr && B200CTC_ABLATE != 9;   // ablation 9: helpers do not reduce (timing only)
+  // the row reduce_frame updates: the gradient row of the frame, or (gathered mode) the frame's emission row in the
+  // workspace, which nobody reads any more once its posteriors exist and which becomes its occupancy row
+  auto out_row = [&](int frame) -> float* {
+    return p.gathered ? p.em + m.em_off + (long long)frame * m.W : p.grads + ((long long)frame * p.B + b) * V;
+  };
 
   const int n_seg = *cm.ix.n_seg, max_n4 = *cm.max_n4;
   int sym[2], base4[2], n4[2];                        // this lane's symbol groups (u = lane, lane + 32)
@@ -1066,7 +1071,7 @@ __device__ void fast_side_helper(const CallParams& p, int b, const UttMeta& m, c
       const int n = n0 - K + hj;
       reduce_frame<NWMAX>(p, cm, c.sm.post + (size_t)((par ^ 1) * K + hj) * c.PS,
                           c.sm.rows + (size_t)(((cc - 1) & (RCH - 1)) * K + hj) * c.RWS,
-                          p.grads + ((long long)c.frame_of(n) * p.B + b) * V, c.RC, NW, n_seg, max_n4, base4, n4, sym, lane);
+                          out_row(c.frame_of(n)), c.RC, NW, n_seg, max_n4, base4, n4, sym, lane);
     }
     B200CTC_TRACE_EVENT(tc, 9);
     cp_async_wait<1>();
@@ -1082,7 +1087,7 @@ __device__ void fast_side_helper(const CallParams& p, int b, const UttMeta& m, c
     if (n0 + hj < T)
       reduce_frame<NWMAX>(p, cm, c.sm.post + (size_t)(par * K + hj) * c.PS,
                           c.sm.rows + (size_t)(((cc - 1) & (RCH - 1)) * K + hj) * c.RWS,
-                          p.grads + ((long long)c.frame_of(n0 + hj) * p.B + b) * V, c.RC, NW, n_seg, max_n4, base4, n4, sym, lane);
+                          out_row(c.frame_of(n0 + hj)), c.RC, NW, n_seg, max_n4, base4, n4, sym, lane);
   }
   cp_async_wait<0>();
 }
@@ -1172,6 +1177,10 @@ __device__ void lattice_fast_utterance(const CallParams& p, int b, unsigned char
       cm.slot_of_label[cm.ix.sorted[k]] = cm.seg_slot[lo] + (k - cm.ix.seg_start[lo]);
     }
     __syncthreads();
+    if (p.gathered && p.grads != nullptr) {      // apply_occupancy_kernel needs the distinct symbols in global memory
+      for (int u = threadIdx.x; u < n_seg; u += blockDim.x) p.sym_tab[m.sym_off + u] = cm.ix.seg_sym[u];
+      if (threadIdx.x == 0) p.nseg[b] = n_seg;
+    }
     // rescaled rows (b200ctc_options): the reducers rewrite EVERY entry of a live row, so they also need the
     // vocabulary entries the utterance never touches (neither the blank nor one of its labels)
     if (p.rescale && !p.gathered && p.grads != nullptr) {

@@ -50,6 +50,8 @@ __global__ void __launch_bounds__(kPlanThreads) plan_kernel(CallParams p, UttMet
       m.W = em_width_of(L);
       m.scratch_off = (long long)b * (p.T + 1) * J_max;     // worst-case regions: no prefix sum over the mini-batch
       m.em_off = (long long)b * p.T * W_max;
+      m.sym_off = b * p.max_label_len;
+      m.pad_ = 0;
       meta[b] = m;
       flags[b] = (bad_len || bad_lab) ? FLAG_INVALID_INPUT : 0;
       if (b < kPlanSmemKeys) s_key[b] = work_key(m);
