@@ -31,7 +31,7 @@ if ROOT not in sys.path:
 METRIC = "ctc_fwd_bwd_frames_per_sec"
 UNIT = "frames/s"
 N_ROTATE = 16          # distinct acts/grads buffer sets cycled through the timed loop (> L2 in total)
-GROUP = 4              # steps per CUDA graph (and per all-reduce message at N > 1)
+GROUP = 8              # steps per CUDA graph (and per all-reduce message at N > 1); 4 per graph measured 3 % slower on C3
 MIN_REGION_MS = 50.0   # N > 1: a timed region shorter than this is repeated until it adds up to it
 
 

@@ -19,6 +19,7 @@ constexpr int kChunk = 4;  // frames between halo exchanges (K)
 template <int K, int NWMAX, int NS>
 __global__ void __launch_bounds__(2 * (NWMAX + kReducers) * 32, 1) lattice_kernel(CallParams p) {
   extern __shared__ __align__(16) unsigned char smem[];
+  pdl_launch_dependents();   // the plan kernel of the next device-resident call may run underneath this kernel (plan.cu)
   const int b = p.order[blockIdx.x];
   const UttMeta m = p.meta[b];
 #ifdef B200CTC_TRACE
@@ -62,6 +63,9 @@ __global__ void __launch_bounds__(2 * (NWMAX + kReducers) * 32, 1) lattice_kerne
     g_cta_time[blockIdx.x * 2 + 1] = (long long)t;
   }
 #endif
+  // A CTA that never needed K1's output (infeasible or empty utterance) still must not let this kernel complete
+  // before K1 does: whatever follows in the stream is ordered behind THIS kernel.  A no-op for everybody else.
+  pdl_wait_primary();
   // Label smoothing (b200ctc_options): -sum_{t<T_b} sum_k log y[t,k] of this utterance from K1's per-row terms,
   // strided partial sums in double, then a tree: fixed order.
   double* part = reinterpret_cast<double*>(smem);

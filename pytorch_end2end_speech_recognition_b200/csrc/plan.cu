@@ -10,65 +10,99 @@ namespace b200ctc {
 
 namespace {
 
-constexpr int kPlanThreads = 1024;
-constexpr int kPlanSmemKeys = 6144;   // work keys of up to this many utterances are ranked from shared memory
+constexpr int kPlanThreads = 256;    // few registers and threads: the CTA fits next to a lattice CTA of the previous call
+constexpr int kPlanSmemUtts = 768;   // up to this many utterances are planned in shared memory, underneath the previous call
 
 __device__ __forceinline__ long long work_key(const UttMeta& m) {
   return (long long)m.T * (2 * m.L + 1) * m.feasible;
 }
 
-// One CTA.  Phase 1: one warp per utterance (labels checked and repeats counted 32 at a time).
-// Phase 2: rank sort of the utterances by decreasing lattice work, ties by index (stable).
+// Metadata of utterance b, computed by one warp (labels checked and repeats counted 32 at a time).
+__device__ __forceinline__ UttMeta plan_utterance(const CallParams& p, int b, int lane, int J_max, int W_max, int* flag) {
+  int L = p.dev_label_lens[b], T = p.dev_act_lens[b];
+  const bool bad_len = L < 0 || L > p.max_label_len || T < 0 || T > p.T;
+  if (bad_len) { L = 0; T = 0; }
+  const int* lab = p.labels + (long long)b * p.label_stride;
+  int repeats = 0;
+  bool bad_lab = false;
+  for (int i = lane; i < L; i += 32) {
+    const int s = lab[i];
+    bad_lab |= s < 0 || s >= p.V || s == p.blank;
+    repeats += (i > 0 && s == lab[i - 1]) ? 1 : 0;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) repeats += __shfl_xor_sync(0xffffffffu, repeats, o);
+  bad_lab = __any_sync(0xffffffffu, bad_lab);
+  UttMeta m;
+  m.T = T;
+  m.L = L;
+  m.lab_off = b * p.label_stride;
+  m.feasible = (!bad_len && !bad_lab && L + repeats <= T) ? 1 : 0;
+  m.J = groups_of(L);
+  m.W = em_width_of(L);
+  m.scratch_off = (long long)b * (p.T + 1) * J_max;     // worst-case regions: no prefix sum over the mini-batch
+  m.em_off = (long long)b * p.T * W_max;
+  m.sym_off = b * p.max_label_len;
+  m.pad_ = 0;
+  *flag = (bad_len || bad_lab) ? FLAG_INVALID_INPUT : 0;
+  return m;
+}
+
+// One CTA, launched PROGRAMMATICALLY behind the previous call's lattice kernel (which signals its dependents at
+// its start): everything that only reads the caller's labels and lengths -- the per-utterance scan and the rank
+// sort by decreasing lattice work, ties by index -- happens in shared memory while that kernel still runs; the
+// tables in the workspace, which the previous call may still be reading, are written after griddepcontrol.wait.
+// The wait also keeps this kernel from COMPLETING before the previous call: the softmax-rows kernel that
+// follows (a normal launch) is ordered behind this kernel only, and it overwrites the shared workspace.
 __global__ void __launch_bounds__(kPlanThreads) plan_kernel(CallParams p, UttMeta* __restrict__ meta,
                                                             int* __restrict__ order, int* __restrict__ flags) {
-  extern __shared__ long long s_key[];
+  extern __shared__ __align__(16) unsigned char s_raw[];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, n_warps = blockDim.x >> 5;
   const int B = p.B;
   const int J_max = groups_of(p.max_label_len), W_max = em_width_of(p.max_label_len);
-  for (int b = warp; b < B; b += n_warps) {
-    int L = p.dev_label_lens[b], T = p.dev_act_lens[b];
-    const bool bad_len = L < 0 || L > p.max_label_len || T < 0 || T > p.T;
-    if (bad_len) { L = 0; T = 0; }
-    const int* lab = p.labels + (long long)b * p.label_stride;
-    int repeats = 0;
-    bool bad_lab = false;
-    for (int i = lane; i < L; i += 32) {
-      const int s = lab[i];
-      bad_lab |= s < 0 || s >= p.V || s == p.blank;
-      repeats += (i > 0 && s == lab[i - 1]) ? 1 : 0;
+  if (B <= kPlanSmemUtts) {
+    UttMeta* s_meta = reinterpret_cast<UttMeta*>(s_raw);
+    int* s_flag = reinterpret_cast<int*>(s_meta + B);
+    int* s_order = s_flag + B;
+    for (int b = warp; b < B; b += n_warps) {
+      int f;
+      const UttMeta m = plan_utterance(p, b, lane, J_max, W_max, &f);
+      if (lane == 0) { s_meta[b] = m; s_flag[b] = f; }
     }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) repeats += __shfl_xor_sync(0xffffffffu, repeats, o);
-    bad_lab = __any_sync(0xffffffffu, bad_lab);
-    if (lane == 0) {
-      UttMeta m;
-      m.T = T;
-      m.L = L;
-      m.lab_off = b * p.label_stride;
-      m.feasible = (!bad_len && !bad_lab && L + repeats <= T) ? 1 : 0;
-      m.J = groups_of(L);
-      m.W = em_width_of(L);
-      m.scratch_off = (long long)b * (p.T + 1) * J_max;     // worst-case regions: no prefix sum over the mini-batch
-      m.em_off = (long long)b * p.T * W_max;
-      m.sym_off = b * p.max_label_len;
-      m.pad_ = 0;
-      meta[b] = m;
-      flags[b] = (bad_len || bad_lab) ? FLAG_INVALID_INPUT : 0;
-      if (b < kPlanSmemKeys) s_key[b] = work_key(m);
+    __syncthreads();
+    for (int b = tid; b < B; b += blockDim.x) {
+      const long long kb = work_key(s_meta[b]);
+      int rank = 0;
+      for (int j = 0; j < B; ++j) {
+        const long long kj = work_key(s_meta[j]);
+        rank += (kj > kb || (kj == kb && j < b)) ? 1 : 0;
+      }
+      s_order[rank] = b;
     }
+    __syncthreads();
+    pdl_wait_primary();                                   // the previous call no longer reads the tables
+    for (int b = tid; b < B; b += blockDim.x) {
+      meta[b] = s_meta[b];
+      flags[b] = s_flag[b];
+      order[b] = s_order[b];
+    }
+    if (tid == 0) flags[B] = 0;                           // finished-utterance counter of the lattice kernel
+    return;
   }
-  if (tid == 0) flags[B] = 0;   // finished-utterance counter of the lattice kernel
+  // large mini-batches: planned in place, after the previous call
+  pdl_wait_primary();
+  for (int b = warp; b < B; b += n_warps) {
+    int f;
+    const UttMeta m = plan_utterance(p, b, lane, J_max, W_max, &f);
+    if (lane == 0) { meta[b] = m; flags[b] = f; }
+  }
+  if (tid == 0) flags[B] = 0;
   __threadfence_block();
   __syncthreads();
   for (int b = tid; b < B; b += blockDim.x) {
-    const long long kb = b < kPlanSmemKeys ? s_key[b] : work_key(meta[b]);
+    const long long kb = work_key(meta[b]);
     int rank = 0;
-    const int ns = B < kPlanSmemKeys ? B : kPlanSmemKeys;
-    for (int j = 0; j < ns; ++j) {
-      const long long kj = s_key[j];
-      rank += (kj > kb || (kj == kb && j < b)) ? 1 : 0;
-    }
-    for (int j = ns; j < B; ++j) {
+    for (int j = 0; j < B; ++j) {
       const long long kj = work_key(meta[j]);
       rank += (kj > kb || (kj == kb && j < b)) ? 1 : 0;
     }
@@ -79,14 +113,20 @@ __global__ void __launch_bounds__(kPlanThreads) plan_kernel(CallParams p, UttMet
 }  // namespace
 
 cudaError_t launch_plan(const CallParams& p, UttMeta* meta, int* order, int* flags, cudaStream_t stream) {
-  const int n_keys = p.B < kPlanSmemKeys ? p.B : kPlanSmemKeys;
-  const size_t smem = (size_t)n_keys * sizeof(long long);
-  if (smem > 48 * 1024) {
-    cudaError_t e = cudaFuncSetAttribute(plan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return e;
-  }
-  plan_kernel<<<1, kPlanThreads, smem, stream>>>(p, meta, order, flags);
-  return cudaGetLastError();
+  const size_t smem = p.B <= kPlanSmemUtts ? (size_t)p.B * (sizeof(UttMeta) + 2 * sizeof(int)) : 0;   // <= 43 KB
+  // Programmatic dependent launch: the lattice kernel of the PREVIOUS call on this stream signals its
+  // dependents at its start, so this kernel runs underneath it instead of after it (see plan_kernel).
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(1);
+  cfg.blockDim = dim3(kPlanThreads);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, plan_kernel, p, meta, order, flags);
 }
 
 }  // namespace b200ctc

@@ -294,3 +294,43 @@ def test_fused_call_site_cost_only_and_upstream_gradient():
     logits = torch.from_numpy(logits_np).cuda().requires_grad_(True)
     (3.0 * b200.ctc_loss_from_padded(logits, ys, x_lens, y_lens, logits_temperature=2.0, label_smoothing=0.15)).sum().backward()
     assert np.max(np.abs(logits.grad.cpu().numpy() - 3.0 * g_ref)) < 3 * GRAD_ATOL / 5
+
+
+def test_back_to_back_device_resident_calls_and_single_call_graph_replays_do_not_race():
+    """The plan kernel of a call runs underneath the lattice kernel of the previous call (programmatic dependent
+    launch) and writes the shared tables only after that kernel has completed: consecutive calls with DIFFERENT
+    lengths on one stream, and back-to-back replays of a graph that holds a single call, must each give the
+    result of an isolated call."""
+    wls = [workloads.make_lengths_and_labels(None, B=48, T=300, V=30, Lmax=120, kind="var", seed=70 + i) for i in range(3)]
+    acts = [workloads.make_acts(w, copy_index=i).cuda() for i, w in enumerate(wls)]
+    pads = [padded(w, 120) for w in wls]
+    ref = []
+    for a, (ys, al, ll) in zip(acts, pads):
+        r = b200.ctc_loss_and_grad(a, ys, al, ll)
+        torch.cuda.synchronize()
+        ref.append((r[0].clone(), r[2].clone()))
+    for rep in range(5):
+        outs = [b200.ctc_loss_and_grad(a, ys, al, ll) for a, (ys, al, ll) in zip(acts, pads)]   # no sync in between
+        torch.cuda.synchronize()
+        for (c, _, g), (c0, g0) in zip(outs, ref):
+            assert torch.equal(c, c0) and torch.equal(g, g0)
+    # one call per graph, replayed without synchronisation, inputs swapped by copies on the same stream
+    a, (ys, al, ll) = acts[0].clone(), tuple(x.clone() for x in pads[0])
+    grads, costs, loss = torch.empty_like(a), torch.empty(48, device="cuda"), torch.empty(1, device="cuda")
+    s = torch.cuda.Stream()
+    s.wait_stream(torch.cuda.current_stream())
+    graph = torch.cuda.CUDAGraph()
+    with torch.cuda.stream(s):
+        b200.ctc_loss_and_grad(a, ys, al, ll, grads=grads, costs=costs, loss_sum=loss)
+        torch.cuda.synchronize()
+        with torch.cuda.graph(graph, stream=s):
+            b200.ctc_loss_and_grad(a, ys, al, ll, grads=grads, costs=costs, loss_sum=loss)
+        got = []
+        for k in range(9):
+            i = k % 3
+            a.copy_(acts[i]); ys.copy_(pads[i][0]); al.copy_(pads[i][1]); ll.copy_(pads[i][2])
+            graph.replay()
+            got.append((costs.clone(), grads.clone()))
+    torch.cuda.synchronize()
+    for k, (c, g) in enumerate(got):
+        assert torch.equal(c, ref[k % 3][0]) and torch.equal(g, ref[k % 3][1]), k

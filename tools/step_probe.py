@@ -46,6 +46,13 @@ for key in (sys.argv[1:] or ["C1", "C3"]):
         fn(8)
     res = {"host-label call, eager": timed(host_path, 48), "device-resident call, eager": timed(dev_eager, 48),
            "device-resident call, graph of %d" % r.group: timed(lambda n: r.run(n), 48)}
+    for grp in (8, 16):
+        bench.GROUP = grp
+        r2 = bench.Runner(wl, dev, 1, 0, acts_dev=r.acts_dev)
+        r2.run(2 * grp)
+        res["device-resident call, graph of %d" % r2.group] = timed(lambda n: r2.run(n), 48)
+        del r2
+    bench.GROUP = 8
     k = bench.kernel_times(r, ctc_mod, 8)
     print(key, "kernels (library events, eager): softmax %.4f lattice %.4f third %.4f ms" % tuple(k))
     for name, (d, h) in res.items():
