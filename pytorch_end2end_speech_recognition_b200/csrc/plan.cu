@@ -70,6 +70,25 @@ __global__ void __launch_bounds__(kPlanThreads) plan_kernel(CallParams p, UttMet
       if (lane == 0) { s_meta[b] = m; s_flag[b] = f; }
     }
     __syncthreads();
+    // compact scratch / emission regions (exclusive prefix sums over the mini-batch, one warp): the workspace is
+    // sized for the worst case, but the part that is touched stays as dense as in the host-planned call
+    if (warp == 0) {
+      long long base_s = 0, base_e = 0;
+      for (int b0 = 0; b0 < B; b0 += 32) {
+        const int b = b0 + lane;
+        const long long ns = b < B ? (long long)(s_meta[b].T + 1) * s_meta[b].J : 0;
+        const long long ne = b < B ? (long long)s_meta[b].T * s_meta[b].W : 0;
+        long long is = ns, ie = ne;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+          const long long vs = __shfl_up_sync(0xffffffffu, is, o), ve = __shfl_up_sync(0xffffffffu, ie, o);
+          if (lane >= o) { is += vs; ie += ve; }
+        }
+        if (b < B) { s_meta[b].scratch_off = base_s + is - ns; s_meta[b].em_off = base_e + ie - ne; }
+        base_s += __shfl_sync(0xffffffffu, is, 31);
+        base_e += __shfl_sync(0xffffffffu, ie, 31);
+      }
+    }
     for (int b = tid; b < B; b += blockDim.x) {
       const long long kb = work_key(s_meta[b]);
       int rank = 0;
