@@ -593,12 +593,15 @@ def main():
     sampler.active.set()
     t_host0 = time.perf_counter()
     ms = timed(lambda: runner.run(args.steps), runner.drain)
-    host_ms_per_step = (time.perf_counter() - t_host0) * 1e3 / args.steps   # wall clock of the same loop incl. both barriers (diagnostic)
+    host_wall = (time.perf_counter() - t_host0) * 1e3        # wall clock of the same region incl. both barriers (diagnostic)
     repeats = 1
     if world > 1 and ms < MIN_REGION_MS:
         # a multi-rank region of a few milliseconds measures start-up skew, not the step: repeat the K steps
         repeats = int(min(200, np.ceil(MIN_REGION_MS / max(ms, 1e-3))))
+        t_host0 = time.perf_counter()
         ms = timed(lambda: [runner.run(args.steps) for _ in range(repeats)], runner.drain) / repeats
+        host_wall = (time.perf_counter() - t_host0) * 1e3 / repeats
+    host_ms_per_step = host_wall / args.steps
     sampler.active.clear()
 
     def agree_min(n):

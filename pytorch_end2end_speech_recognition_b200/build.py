@@ -97,5 +97,49 @@ def _build_variant(extra_flags, lib_path, verbose):
     return lib_path
 
 
+EXT_NAME = "b200ctc_torch"
+EXT_DIR = os.path.join(LIB_DIR, "torch_ext")
+
+
+def extension_path():
+    import sysconfig
+    return os.path.join(EXT_DIR, EXT_NAME + (sysconfig.get_config_var("EXT_SUFFIX") or ".so"))
+
+
+def build_extension(force=False, verbose=False):
+    """Compile csrc/torch_binding.cpp -- the thin PyTorch C++ extension over the C ABI -- in-tree with the host
+    compiler against this interpreter's torch headers, linked to lib/libb200ctc.so (rpath $ORIGIN/..).
+    Returns the path of the extension module; a no-op when its source hash is unchanged."""
+    import sysconfig
+    import torch
+    from torch.utils import cpp_extension
+    build_library()
+    os.makedirs(EXT_DIR, exist_ok=True)
+    src = os.path.join(CSRC, "torch_binding.cpp")
+    out = extension_path()
+    deps = [src, os.path.join(REPO_DIR, "include", "b200ctc.h")]
+    flags = ["torch=" + torch.__version__, "py=" + sys.version.split()[0]]
+    if not force and not _stale(out, deps, flags):
+        return out
+    cuda_home = os.environ.get("CUDA_HOME", "/usr/local/cuda")
+    inc = ["-I" + p for p in cpp_extension.include_paths()] + ["-I" + os.path.join(cuda_home, "include"),
+           "-I" + sysconfig.get_paths()["include"], "-I" + os.path.join(REPO_DIR, "include")]
+    torch_lib = os.path.join(os.path.dirname(torch.__file__), "lib")
+    abi = "-D_GLIBCXX_USE_CXX11_ABI=%d" % int(torch._C._GLIBCXX_USE_CXX11_ABI)
+    cmd = ["g++", "-O2", "-std=c++17", "-fPIC", "-shared", abi, "-DTORCH_EXTENSION_NAME=" + EXT_NAME,
+           "-DTORCH_API_INCLUDE_EXTENSION_H", src, "-o", out] + inc + [
+           "-L" + LIB_DIR, "-lb200ctc", "-Wl,-rpath,$ORIGIN/..",
+           "-L" + torch_lib, "-ltorch", "-ltorch_cpu", "-ltorch_cuda", "-lc10", "-lc10_cuda", "-ltorch_python",
+           "-Wl,-rpath," + torch_lib, "-L" + os.path.join(cuda_home, "lib64"), "-lcudart"]
+    if verbose:
+        print(" ".join(cmd), file=sys.stderr)
+    subprocess.run(cmd, check=True)
+    with open(out + ".srchash", "w") as f:
+        f.write(_source_hash(deps, flags))
+    return out
+
+
 if __name__ == "__main__":
     print(build_library(force="--force" in sys.argv, verbose="-v" in sys.argv))
+    if "--ext" in sys.argv:
+        print(build_extension(force="--force" in sys.argv, verbose="-v" in sys.argv))

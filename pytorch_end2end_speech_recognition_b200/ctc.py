@@ -16,6 +16,7 @@ Native additions: ``ctc_loss_and_grad`` (device-resident results, no host sync) 
 """
 
 import ctypes
+import os
 
 import numpy as np
 import torch
@@ -25,15 +26,49 @@ from ._lib import B200CTCError
 
 _HANDLES = {}
 _WORKSPACES = {}     # (device index, stream handle) -> growing uint8 workspace tensor
+_EXT = None          # the PyTorch C++ extension over the C ABI (csrc/torch_binding.cpp), False when not built
+
+
+def _ext():
+    """The thin PyTorch C++ extension (north_star: "a thin PyTorch C++/CUDA extension over a C-ABI"), built
+    in-tree by ``__graft_entry__.build()`` / ``build.build_extension()``.  When it is not built (or
+    ``B200CTC_BINDING=ctypes``) the ctypes binding calls the same C entry points."""
+    global _EXT
+    if _EXT is None:
+        _EXT = False
+        if os.environ.get("B200CTC_BINDING", "ext") != "ctypes":
+            try:
+                import importlib.util
+                from . import build as _build
+                _lib.load()                                   # libb200ctc.so first (also builds it when missing)
+                path = _build.extension_path()
+                if os.path.exists(path):
+                    spec = importlib.util.spec_from_file_location(_build.EXT_NAME, path)
+                    mod = importlib.util.module_from_spec(spec)
+                    spec.loader.exec_module(mod)
+                    _EXT = mod
+            except Exception:                                 # an extension built for another torch / python: fall back
+                _EXT = False
+    return _EXT
+
+
+def binding():
+    """'extension' or 'ctypes': which binding ``ctc_loss_and_grad`` goes through."""
+    return "extension" if _ext() else "ctypes"
 
 
 def _handle(device_index):
-    """One library handle per device (the handle serialises its calls with a mutex, include/b200ctc.h)."""
+    """One library handle per device (the handle serialises its calls with a mutex, include/b200ctc.h);
+    shared between the extension and the ctypes entry points (diagnostics, decoders)."""
     h = _HANDLES.get(device_index)
     if h is None:
-        lib = _lib.load()
-        hp = ctypes.c_void_p()
-        _lib.check(lib.b200ctc_create(ctypes.byref(hp), int(device_index)), "b200ctc_create")
+        ext = _ext()
+        if ext:
+            hp = ctypes.c_void_p(ext.handle_address(int(device_index)))
+        else:
+            lib = _lib.load()
+            hp = ctypes.c_void_p()
+            _lib.check(lib.b200ctc_create(ctypes.byref(hp), int(device_index)), "b200ctc_create")
         h = _HANDLES[device_index] = hp
     return h
 
@@ -54,6 +89,8 @@ def _workspace(dev_index, stream, nbytes):
 def release_workspaces():
     """Drop the cached workspaces (they are re-allocated on the next call)."""
     _WORKSPACES.clear()
+    if _ext():
+        _ext().release_workspaces()
 
 
 def set_profiling(enable, device_index=None):
@@ -107,6 +144,13 @@ def _host_i32(x, name):
     if arr.ndim != 1:
         raise B200CTCError("%s must be 1-dimensional" % name)
     return arr
+
+
+def _as_cpu_tensor(x):
+    """labels / lengths for the extension's host-label entry point: a 1-D CPU int32 tensor (no copy for int32 numpy)."""
+    if isinstance(x, torch.Tensor):
+        return x
+    return torch.from_numpy(np.ascontiguousarray(np.asarray(x), dtype=np.int32))
 
 
 def _i32_ptr(arr):
@@ -185,6 +229,23 @@ def ctc_loss_and_grad(acts, labels, act_lens, label_lens, blank=0, grads=None, n
     Returns device tensors ``(costs[B], loss_sum[1], grads[T,B,V] or None)``; nothing synchronises the host.
     """
     _require_cuda(acts)
+    ext = _ext()
+    if ext:
+        try:
+            if isinstance(labels, torch.Tensor) and labels.is_cuda:
+                return ext.loss_and_grad_dev(acts, labels, act_lens, label_lens, int(blank), grads, bool(need_grad), costs,
+                                             loss_sum, -1 if max_label_len is None else int(max_label_len),
+                                             float(logit_scale), float(label_smoothing), float(loss_scale),
+                                             float(grad_scale), ls_costs)
+            if logit_scale != 1.0 or label_smoothing != 0.0 or loss_scale != 1.0 or grad_scale != 1.0:
+                raise B200CTCError("logit_scale / label_smoothing / loss_scale / grad_scale need device-resident labels "
+                                   "(the warp-ctc style call has no such arguments); see ctc_loss_from_padded")
+            return ext.loss_and_grad_host(acts, _as_cpu_tensor(labels), _as_cpu_tensor(act_lens), _as_cpu_tensor(label_lens),
+                                          int(blank), grads, bool(need_grad), costs, loss_sum)
+        except B200CTCError:
+            raise
+        except (RuntimeError, TypeError) as exc:
+            raise B200CTCError(str(exc).split("\n")[0])
     lib = _lib.load()
     if acts.stride(2) != 1 and acts.size(2) > 1:
         acts = acts.contiguous()

@@ -1,6 +1,8 @@
 """GPU tests added in round 2: the device-resident call (plan kernel, CUDA-graph capture), the plan cache of
 the host call, cost-only calls at full size, label sequences beyond the shared-memory budget of the
 gathered mode, input clamping in the decoder, sharded evaluation of one batch."""
+import os
+
 import numpy as np
 import pytest
 import torch
@@ -334,3 +336,42 @@ def test_back_to_back_device_resident_calls_and_single_call_graph_replays_do_not
     torch.cuda.synchronize()
     for k, (c, g) in enumerate(got):
         assert torch.equal(c, ref[k % 3][0]) and torch.equal(g, ref[k % 3][1]), k
+
+
+def test_extension_and_ctypes_bindings_agree():
+    """The product call goes through the thin PyTorch C++ extension (csrc/torch_binding.cpp) when it is built --
+    as it is by __graft_entry__.build() -- and through ctypes otherwise; both reach the same C entry points."""
+    import subprocess
+    import sys
+    assert ctc_mod.binding() == "extension"
+    wl = workloads.make_lengths_and_labels(None, B=6, T=70, V=30, Lmax=20, kind="var", seed=80)
+    acts = workloads.make_acts(wl).cuda()
+    ys, al, ll = padded(wl)
+    c1, l1, g1 = b200.ctc_loss_and_grad(acts, wl.labels, wl.act_lens, wl.label_lens)
+    c2, l2, g2 = b200.ctc_loss_and_grad(acts, ys, al, ll, label_smoothing=0.1, loss_scale=0.5, grad_scale=0.25, logit_scale=0.8)
+    torch.cuda.synchronize()
+    code = (
+        "import os, sys, torch, numpy as np\n"
+        "os.environ['B200CTC_BINDING'] = 'ctypes'\n"
+        "sys.path.insert(0, %r)\n"
+        "import pytorch_end2end_speech_recognition_b200 as b200\n"
+        "from pytorch_end2end_speech_recognition_b200 import ctc, workloads\n"
+        "assert ctc.binding() == 'ctypes'\n"
+        "wl = workloads.make_lengths_and_labels(None, B=6, T=70, V=30, Lmax=20, kind='var', seed=80)\n"
+        "acts = workloads.make_acts(wl).cuda()\n"
+        "Lm = int(wl.label_lens.max()); ys = np.full((wl.B, Lm), -7, np.int32); off = 0\n"
+        "for b, L in enumerate(wl.label_lens):\n"
+        "    ys[b, :L] = wl.labels[off:off + L]; off += L\n"
+        "r1 = b200.ctc_loss_and_grad(acts, wl.labels, wl.act_lens, wl.label_lens)\n"
+        "r2 = b200.ctc_loss_and_grad(acts, torch.from_numpy(ys).cuda(), torch.from_numpy(wl.act_lens).cuda(),\n"
+        "                            torch.from_numpy(wl.label_lens).cuda(), label_smoothing=0.1, loss_scale=0.5,\n"
+        "                            grad_scale=0.25, logit_scale=0.8)\n"
+        "torch.save([r1[0].cpu(), r1[2].cpu(), r2[0].cpu(), r2[1].cpu(), r2[2].cpu()], sys.argv[1])\n"
+    ) % os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    import tempfile
+    with tempfile.TemporaryDirectory() as d:
+        out = os.path.join(d, "r.pt")
+        subprocess.run([sys.executable, "-c", code, out], check=True)
+        o = torch.load(out)
+    assert torch.equal(o[0], c1.cpu()) and torch.equal(o[1], g1.cpu())
+    assert torch.equal(o[2], c2.cpu()) and torch.equal(o[3], l2.cpu()) and torch.equal(o[4], g2.cpu())
