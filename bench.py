@@ -305,7 +305,9 @@ class Runner:
         self.n_groups_done = 0
         self.graphs = None
         self.launches_per_step = 3            # plan, softmax rows, lattice (+ cost sum in its last CTA)
-        if use_graph:
+        # long steps (C4, C5: two buffer sets, 0.7-0.9 ms per step) are issued eagerly: the host needs ~0.02 ms per
+        # call, and a graph that holds only two steps costs ~0.04 ms per step at its boundaries (tools/step_probe.py)
+        if use_graph and self.group >= 4:
             self._capture()
 
     def one(self, j, slot):
@@ -314,7 +316,8 @@ class Runner:
 
     def _capture(self):
         torch = self.torch
-        n_graphs = self.n_rot // self.group
+        n_sets = self.n_rot // self.group                       # groups of buffer sets
+        n_graphs = n_sets if n_sets % 2 == 0 else 2 * n_sets    # even: graph k writes loss group k % 2
         side = torch.cuda.Stream(device=self.dev)
         side.wait_stream(torch.cuda.current_stream(self.dev))
         graphs = []
@@ -325,7 +328,7 @@ class Runner:
                 gr = torch.cuda.CUDAGraph()
                 with torch.cuda.graph(gr, stream=side):
                     for k in range(self.group):
-                        self.one(g * self.group + k, self.loss_groups[g % 2][k:k + 1])
+                        self.one((g % n_sets) * self.group + k, self.loss_groups[g % 2][k:k + 1])
                 graphs.append(gr)
         torch.cuda.current_stream(self.dev).wait_stream(side)
         torch.cuda.synchronize()
@@ -338,9 +341,8 @@ class Runner:
         if self.world > 1 and self.pending[g] is not None:      # a loss group is rewritten only after its all-reduce
             self.pending[g].wait()
             self.pending[g] = None
-        n_graphs = self.n_rot // self.group
-        if self.graphs is not None and not eager and (gi % n_graphs) % 2 == g:
-            self.graphs[gi % n_graphs].replay()
+        if self.graphs is not None and not eager:
+            self.graphs[gi % len(self.graphs)].replay()
         else:
             for k in range(self.group):
                 self.one((gi * self.group + k) % self.n_rot, self.loss_groups[g][k:k + 1])
@@ -743,7 +745,8 @@ def main():
         "config": config_dict(wl, frames, total_bytes, world),
         "details": {"utterances_per_sec": wl.B * world / (ms_per_step * 1e-3), "timed_region_repeats": repeats,
                     "l2": "rotating %d acts/grads buffer sets (%.0f MB > L2)" % (n_rot, 2 * n_rot * acts_bytes / 1e6),
-                    "launch": "device-resident labels/lengths, %d steps per CUDA graph; N > 1: the %d losses of a graph in one asynchronous all-reduce" % (runner.group, runner.group)},
+                    "launch": ("device-resident labels/lengths, %d steps per CUDA graph" % runner.group if runner.graphs is not None else
+                               "device-resident labels/lengths, eager calls") + "; N > 1: the %d losses of a group of steps in one asynchronous all-reduce" % runner.group},
         "host": {"wall_ms_per_step": host_ms_per_step, "enqueue_ms_per_step": host_enqueue_ms, "cpus": _host_threads()},
         "roofline": roofline, "e2e": e2e, "gpu_launches": runner.launches_per_step * args.steps * repeats, "clocks": clocks,
     }

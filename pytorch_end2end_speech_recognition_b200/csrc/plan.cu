@@ -11,7 +11,7 @@ namespace b200ctc {
 namespace {
 
 constexpr int kPlanThreads = 256;    // few registers and threads: the CTA fits next to a lattice CTA of the previous call
-constexpr int kPlanSmemUtts = 768;   // up to this many utterances are planned in shared memory, underneath the previous call
+constexpr int kPlanSmemUtts = 704;   // up to this many utterances are planned in shared memory, underneath the previous call
 
 __device__ __forceinline__ long long work_key(const UttMeta& m) {
   return (long long)m.T * (2 * m.L + 1) * m.feasible;
@@ -62,12 +62,56 @@ __global__ void __launch_bounds__(kPlanThreads) plan_kernel(CallParams p, UttMet
   const int J_max = groups_of(p.max_label_len), W_max = em_width_of(p.max_label_len);
   if (B <= kPlanSmemUtts) {
     UttMeta* s_meta = reinterpret_cast<UttMeta*>(s_raw);
-    int* s_flag = reinterpret_cast<int*>(s_meta + B);
+    long long* s_key = reinterpret_cast<long long*>(s_meta + B);
+    int* s_flag = reinterpret_cast<int*>(s_key + B);
     int* s_order = s_flag + B;
-    for (int b = warp; b < B; b += n_warps) {
-      int f;
-      const UttMeta m = plan_utterance(p, b, lane, J_max, W_max, &f);
-      if (lane == 0) { s_meta[b] = m; s_flag[b] = f; }
+    // lengths: one thread per utterance
+    for (int b = tid; b < B; b += blockDim.x) {
+      int L = p.dev_label_lens[b], T = p.dev_act_lens[b];
+      const bool bad_len = L < 0 || L > p.max_label_len || T < 0 || T > p.T;
+      if (bad_len) { L = 0; T = 0; }
+      s_meta[b].T = T;
+      s_meta[b].L = L;
+      s_meta[b].feasible = bad_len ? 0 : 1;
+      s_flag[b] = bad_len ? FLAG_INVALID_INPUT : 0;
+      s_order[b] = 0;                                     // repeats of the utterance, for now
+    }
+    __syncthreads();
+    // labels: one work item per 32 consecutive labels of an utterance, so that the loads of all utterances are
+    // in flight together (a warp per utterance, one utterance after the other, took 40 us for 128 utterances)
+    {
+      const int n_chunks = (p.max_label_len + 31) >> 5, items = B * n_chunks;
+      for (int it = tid; it < items; it += blockDim.x) {
+        const int b = it / n_chunks, i0 = (it - b * n_chunks) << 5, L = s_meta[b].L;
+        if (i0 >= L) continue;
+        const int* lab = p.labels + (long long)b * p.label_stride + i0;
+        const int n = min(32, L - i0);
+        int prev = i0 > 0 ? lab[-1] : -1, rep = 0;
+        bool bad = false;
+#pragma unroll 8
+        for (int k = 0; k < n; ++k) {
+          const int sym = lab[k];
+          bad |= sym < 0 || sym >= p.V || sym == p.blank;
+          rep += (sym == prev) ? 1 : 0;                   // prev == -1 at the first label: never equal to a valid symbol
+          prev = sym;
+        }
+        if (rep) atomicAdd(&s_order[b], rep);
+        if (bad) atomicOr(&s_flag[b], FLAG_INVALID_INPUT);
+      }
+    }
+    __syncthreads();
+    for (int b = tid; b < B; b += blockDim.x) {
+      UttMeta m = s_meta[b];
+      if (s_flag[b] || m.L + s_order[b] > m.T) m.feasible = 0;
+      m.lab_off = b * p.label_stride;
+      m.J = groups_of(m.L);
+      m.W = em_width_of(m.L);
+      m.scratch_off = 0;
+      m.em_off = 0;
+      m.sym_off = b * p.max_label_len;
+      m.pad_ = 0;
+      s_meta[b] = m;
+      s_key[b] = work_key(m);
     }
     __syncthreads();
     // compact scratch / emission regions (exclusive prefix sums over the mini-batch, one warp): the workspace is
@@ -90,10 +134,11 @@ __global__ void __launch_bounds__(kPlanThreads) plan_kernel(CallParams p, UttMet
       }
     }
     for (int b = tid; b < B; b += blockDim.x) {
-      const long long kb = work_key(s_meta[b]);
+      const long long kb = s_key[b];
       int rank = 0;
+#pragma unroll 4
       for (int j = 0; j < B; ++j) {
-        const long long kj = work_key(s_meta[j]);
+        const long long kj = s_key[j];
         rank += (kj > kb || (kj == kb && j < b)) ? 1 : 0;
       }
       s_order[rank] = b;
@@ -132,7 +177,7 @@ __global__ void __launch_bounds__(kPlanThreads) plan_kernel(CallParams p, UttMet
 }  // namespace
 
 cudaError_t launch_plan(const CallParams& p, UttMeta* meta, int* order, int* flags, cudaStream_t stream) {
-  const size_t smem = p.B <= kPlanSmemUtts ? (size_t)p.B * (sizeof(UttMeta) + 2 * sizeof(int)) : 0;   // <= 43 KB
+  const size_t smem = p.B <= kPlanSmemUtts ? (size_t)p.B * (sizeof(UttMeta) + sizeof(long long) + 2 * sizeof(int)) : 0;   // <= 44 KB
   // Programmatic dependent launch: the lattice kernel of the PREVIOUS call on this stream signals its
   // dependents at its start, so this kernel runs underneath it instead of after it (see plan_kernel).
   cudaLaunchConfig_t cfg = {};

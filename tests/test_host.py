@@ -143,3 +143,52 @@ def test_bench_roofline_inputs_are_readable():
     wl = workloads.make_lengths_and_labels("C3")
     total, strict, frames = workloads.algorithmic_bytes(wl)
     assert frames == 102400 and strict < total < 7e8
+
+
+def test_workspace_bound_covers_every_length_combination():
+    rng = np.random.RandomState(3)
+    for _ in range(20):
+        B, T, V, Lmax = rng.randint(1, 40), rng.randint(1, 300), int(rng.choice([5, 30, 62, 200, 3386])), rng.randint(0, 120)
+        ll = rng.randint(0, Lmax + 1, size=B).astype(np.int32)
+        al = rng.randint(0, T + 1, size=B).astype(np.int32)
+        assert b200.workspace_bytes(ll, al, T, V) <= b200.ctc.workspace_bound(T, V, B, Lmax)
+
+
+def test_evaluation_entry_points_have_no_cpu_path():
+    with pytest.raises(RuntimeError):
+        b200.beam_search_decode(torch.randn(2, 5, 4), [5, 5], 3)
+    with pytest.raises(RuntimeError):
+        b200.edit_distance(torch.zeros(2, 3, dtype=torch.int32), [3, 3], torch.zeros(2, 3, dtype=torch.int32), [3, 3])
+    with pytest.raises(RuntimeError):
+        b200.posteriors(torch.randn(2, 5, 4))
+    with pytest.raises(RuntimeError):
+        b200.ctc_loss_from_padded(torch.randn(2, 5, 4), np.zeros((2, 2), np.int64), [5, 5], [1, 1])
+    lib = _lib.load()
+    n = ctypes.c_size_t()
+    assert lib.b200ctc_beam_search_workspace(4, 100, 30, 10, ctypes.byref(n)) == 0 and n.value > 0
+    assert lib.b200ctc_beam_search_workspace(4, 100, 30, 65, ctypes.byref(n)) == 1          # beam_width > 64
+    assert lib.b200ctc_edit_distance_workspace(4, 50, 60, ctypes.byref(n)) == 0 and n.value >= 4 * 51 * 61
+    assert lib.b200ctc_get_workspace_bound(100, 30, 4, 20, ctypes.byref(n)) == 0 and n.value > 0
+
+
+def test_torch_extension_builds_in_tree_and_loads():
+    """The thin PyTorch C++ extension over the C ABI: built next to the library (not into site-packages), so
+    that it travels with the repository snapshot and shows up as loaded native code."""
+    path = build.build_extension()
+    assert path.startswith(ROOT) and os.path.exists(path)
+    from pytorch_end2end_speech_recognition_b200 import ctc
+    if os.environ.get("B200CTC_BINDING", "ext") != "ctypes":
+        assert ctc.binding() == "extension"
+        with pytest.raises(RuntimeError):
+            ctc._ext().loss_and_grad_host(torch.zeros(2, 1, 3), torch.zeros(1), torch.zeros(1), torch.zeros(1))
+
+
+def test_both_bench_arms_describe_the_same_config():
+    import bench
+    wl = workloads.make_lengths_and_labels("C3")
+    total, _, frames = workloads.algorithmic_bytes(wl)
+    a = bench.config_dict(wl, frames, total, 1)
+    assert set(a) == {"workload", "per_gpu_batch", "frames_per_step_per_gpu", "algorithmic_bytes_per_step_per_gpu",
+                      "n_gpus", "parallelism"}
+    src = open(os.path.join(ROOT, "bench.py")).read()
+    assert src.count('"config": config_dict(') == 2                   # the b200 arm and the reference arm
