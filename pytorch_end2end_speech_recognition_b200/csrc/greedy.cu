@@ -54,6 +54,31 @@ __global__ void __launch_bounds__(256) frame_argmax_warp_kernel(
   if (lane == 0) out_tokens[row] = key_index(best);
 }
 
+// very small vocabulary (V <= 4 * LPR, LPR = 8 or 16 lanes per frame): a warp decodes 32 / LPR frames at once, so
+// that one load instruction of the warp covers several short rows instead of one 120-byte row
+template <int LPR>
+__global__ void __launch_bounds__(256) frame_argmax_group_kernel(
+    const float* __restrict__ logits, long long stride_b, long long stride_t,
+    const int* __restrict__ lens, int T, int V, int B, int* __restrict__ out_tokens) {
+  constexpr int RPW = 32 / LPR;
+  const int lane = threadIdx.x & 31, q = lane & (LPR - 1), sub = lane / LPR;
+  long long row = ((long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * RPW + sub;
+  const bool in_range = row < (long long)B * T;
+  if (!in_range) row = (long long)B * T - 1;                // keep the lane in the shuffles; it stores nothing
+  const int b = (int)(row / T), t = (int)(row - (long long)b * T);
+  const bool live = in_range && t < min(lens[b], T);
+  const float* x = logits + b * stride_b + t * stride_t;
+  unsigned long long best = 0ull;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int v = q + LPR * i;
+    if (live && v < V) best = umax64(best, argmax_key(__ldg(x + v), v));
+  }
+#pragma unroll
+  for (int o = LPR / 2; o > 0; o >>= 1) best = umax64(best, __shfl_xor_sync(0xffffffffu, best, o));
+  if (live && q == 0) out_tokens[row] = key_index(best);
+}
+
 // large vocabulary: one CTA per frame, 128-bit loads on the aligned body
 __global__ void __launch_bounds__(256) frame_argmax_cta_kernel(
     const float* __restrict__ logits, long long stride_b, long long stride_t,
@@ -154,7 +179,11 @@ cudaError_t launch_greedy(const float* logits, long long stride_b, long long str
   if (B == 0) return cudaSuccess;
   const long long rows = (long long)B * T;
   if (rows > 0) {
-    if (V <= 512) {
+    if (V <= 32) {
+      frame_argmax_group_kernel<8><<<(unsigned)((rows + 31) / 32), 256, 0, stream>>>(logits, stride_b, stride_t, lens, T, V, B, out_tokens);
+    } else if (V <= 64) {
+      frame_argmax_group_kernel<16><<<(unsigned)((rows + 15) / 16), 256, 0, stream>>>(logits, stride_b, stride_t, lens, T, V, B, out_tokens);
+    } else if (V <= 512) {
       const unsigned grid = (unsigned)((rows + 7) / 8);
       frame_argmax_warp_kernel<<<grid, 256, 0, stream>>>(logits, stride_b, stride_t, lens, T, V, B, out_tokens);
     } else {
