@@ -659,29 +659,35 @@ def main():
     for i, a in enumerate(acts_host):
         pinned_all[i].copy_(a)
     pinned = [pinned_all[i] for i in range(len(acts_host))]
-    ys_host, al_host, ll_host = runner.ys.cpu().pin_memory(), runner.al.cpu().pin_memory(), runner.ll.cpu().pin_memory()
+    # labels and lengths of a step: ONE pinned int32 buffer [lengths | label lengths | padded labels] and one copy
+    # (three small copies in front of the logits cost that copy stream ~15 us per step)
+    B_, Lw = runner.ys.shape
+    lab_host = torch.cat([runner.al.cpu(), runner.ll.cpu(), runner.ys.cpu().reshape(-1)]).pin_memory()
     stage = [torch.empty_like(a) for a in runner.acts_dev[:2]]
-    stage_lab = [(torch.empty_like(runner.ys), torch.empty_like(runner.al), torch.empty_like(runner.ll)) for _ in range(2)]
-    h2d = acts_bytes + ys_host.numel() * 4 + al_host.numel() * 4 + ll_host.numel() * 4
+    lab_dev = [torch.empty_like(lab_host, device=dev) for _ in range(2)]
+    stage_lab = [(ld[2 * B_:].view(B_, Lw), ld[:B_], ld[B_:2 * B_]) for ld in lab_dev]
+    h2d = acts_bytes + lab_host.numel() * 4
     e2e_loss = []
-    copy_streams = [torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev)]
-    copied = [[torch.cuda.Event(), torch.cuda.Event()], [torch.cuda.Event(), torch.cuda.Event()]]
-    half = wl.T // 2
+    n_split = int(os.environ.get("B200CTC_E2E_SPLITS", "2"))
+    copy_streams = [torch.cuda.Stream(device=dev) for _ in range(n_split)]
+    label_stream = torch.cuda.Stream(device=dev)
+    copied = [[torch.cuda.Event() for _ in range(n_split + 1)] for _ in range(2)]
+    cuts = [wl.T * k // n_split for k in range(n_split + 1)]
     consumed = [torch.cuda.Event(), torch.cuda.Event()]
     compute_stream = torch.cuda.current_stream(dev)
 
     def issue_copy(i):
         d = i % 2
         src = pinned[i % n_rot]
-        for k, (cs, lo, hi) in enumerate(((copy_streams[0], 0, half), (copy_streams[1], half, wl.T))):
+        for k, cs in enumerate(copy_streams):
             with torch.cuda.stream(cs):
                 cs.wait_event(consumed[d])                               # the step that last read stage[d] is done
-                if k == 0:                                               # labels and lengths of step i (device-resident call)
-                    stage_lab[d][0].copy_(ys_host, non_blocking=True)
-                    stage_lab[d][1].copy_(al_host, non_blocking=True)
-                    stage_lab[d][2].copy_(ll_host, non_blocking=True)
-                stage[d][lo:hi].copy_(src[lo:hi], non_blocking=True)      # H2D of step i's logits, frames [lo, hi)
+                stage[d][cuts[k]:cuts[k + 1]].copy_(src[cuts[k]:cuts[k + 1]], non_blocking=True)   # H2D of step i's logits, a slice of frames
                 copied[d][k].record(cs)
+        with torch.cuda.stream(label_stream):
+            label_stream.wait_event(consumed[d])
+            lab_dev[d].copy_(lab_host, non_blocking=True)                # labels and lengths of step i (device-resident call)
+            copied[d][n_split].record(label_stream)
 
     # The loss of every step is copied device -> host (pinned) right behind its kernels and READ on the host one
     # step later, after the next step has been enqueued: the host never idles the GPU while it prepares a call
@@ -701,8 +707,8 @@ def main():
 
     def e2e_step(i, first):
         d = i % 2
-        compute_stream.wait_event(copied[d][0])
-        compute_stream.wait_event(copied[d][1])
+        for ev in copied[d]:
+            compute_stream.wait_event(ev)
         b200.ctc_loss_and_grad(stage[d], stage_lab[d][0], stage_lab[d][1], stage_lab[d][2],
                                grads=runner.grads_dev[i % n_rot], costs=runner.costs, loss_sum=e2e_dev[d])
         consumed[d].record(compute_stream)
@@ -733,7 +739,7 @@ def main():
     e2e_ms = timed(lambda: e2e_run(args.steps, n_rot + 2), lambda: None) / args.steps
     e2e = {"value": frames * world / (e2e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": int(h2d),
            "d2h_bytes_per_step": 4, "ms_per_step": e2e_ms,
-           "pipeline": "double-buffered: H2D of step i+1's logits (two halves on two copy streams), padded labels and lengths overlaps the kernels of step i; the loss of step i is copied D2H behind its kernels (own stream) and read on the host after step i+1 is enqueued (one extra prefetch copy per run is also inside the timed region)"}
+           "pipeline": "double-buffered: H2D of step i+1's logits (%d slices on %d copy streams), padded labels and lengths (one copy, own stream) overlaps the kernels of step i; the loss of step i is copied D2H behind its kernels (own stream) and read on the host after step i+1 is enqueued (one extra prefetch copy per run is also inside the timed region)" % (n_split, n_split)}
     del pinned_all, pinned, stage
 
     out = {
