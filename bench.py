@@ -48,15 +48,17 @@ def parse():
 
 
 def measured_traffic(workload_key):
-    """DRAM bytes per lattice launch from the committed ncu capture (profiles/r01_traffic.json, C3 only)."""
+    """DRAM bytes per lattice launch from the committed ncu capture (profiles/r02_traffic.json, C3 only)."""
     if workload_key != "C3":
         return None
-    try:
-        with open(os.path.join(ROOT, "profiles", "r01_traffic.json")) as f:
-            k = json.load(f)["lattice_kernel"]
-        return int(k["dram_bytes_read"]) + int(k["dram_bytes_write"])
-    except Exception:
-        return None
+    for name in ("r02_traffic.json", "r01_traffic.json"):
+        try:
+            with open(os.path.join(ROOT, "profiles", name)) as f:
+                k = json.load(f)["lattice_kernel"]
+            return int(k["dram_bytes_read"]) + int(k["dram_bytes_write"])
+        except Exception:
+            continue
+    return None
 
 
 def peaks():

@@ -75,7 +75,8 @@ def build_library(force=False, verbose=False, extra_flags=(), lib_path=None):
             print(" ".join(cmd), file=sys.stderr)
         subprocess.run(cmd, check=True)
         objs.append(obj)
-    cmd = [_nvcc(), "-shared", "-o", LIB_PATH] + objs + ["-Xcompiler", "-fPIC"]
+    # the link step names the architecture too: without it nvcc adds an (empty) sm_52 device-link stub
+    cmd = [_nvcc(), "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", LIB_PATH] + objs + ["-Xcompiler", "-fPIC"]
     subprocess.run(cmd, check=True)
     with open(LIB_PATH + ".srchash", "w") as f:
         f.write(_source_hash(deps, NVCC_FLAGS))
@@ -93,7 +94,8 @@ def _build_variant(extra_flags, lib_path, verbose):
             print(" ".join(cmd), file=sys.stderr)
         subprocess.run(cmd, check=True)
         objs.append(obj)
-    subprocess.run([_nvcc(), "-shared", "-o", lib_path] + objs + ["-Xcompiler", "-fPIC"], check=True)
+    subprocess.run([_nvcc(), "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", lib_path] + objs +
+                   ["-Xcompiler", "-fPIC"], check=True)
     return lib_path
 
 
