@@ -12,6 +12,60 @@ namespace {
 
 constexpr int kChunk = 4;  // frames between halo exchanges (K)
 
+// What every utterance ends with (the CTA that owns it; at least 128 threads): the label-smoothing term of the
+// utterance and, in the CTA that finishes last, the fixed-order sum of the costs (K3).
+__device__ void utterance_tail(const CallParams& p, int b, const UttMeta& m, unsigned char* smem) {
+  constexpr int NT = 128;          // the same summation order whatever the block size of the kernel variant
+  // A CTA that never needed K1's output (infeasible or empty utterance) still must not let this kernel complete
+  // before K1 does: whatever follows in the stream is ordered behind THIS kernel.  A no-op for everybody else.
+  pdl_wait_primary();
+  // Label smoothing (b200ctc_options): -sum_{t<T_b} sum_k log y[t,k] of this utterance from K1's per-row terms,
+  // strided partial sums in double, then a tree: fixed order.
+  double* part = reinterpret_cast<double*>(smem);
+  if (p.xe_rows != nullptr) {
+    __syncthreads();               // the utterance's own use of the shared memory is over
+    if (threadIdx.x < NT) {
+      double acc = 0.0;
+      const int n_rows = m.feasible ? m.T : 0;     // K1 writes the term for live rows only
+      for (int t = threadIdx.x; t < n_rows; t += NT) acc += (double)__ldcg(p.xe_rows + (long long)t * p.B + b);
+      part[threadIdx.x] = acc;
+    }
+    __syncthreads();
+    for (int o = NT / 2; o > 0; o >>= 1) {
+      if ((int)threadIdx.x < o) part[threadIdx.x] += part[threadIdx.x + o];
+      __syncthreads();
+    }
+    if (threadIdx.x == 0) p.xe_costs[b] = (float)part[0];
+  }
+  // K3, fused: the CTA that finishes last sums the per-utterance costs in a fixed order (NT strided
+  // partial sums in double, then a tree), so the returned loss is bit-reproducible run to run.
+  if (p.loss_sum == nullptr) return;
+  __shared__ int s_last;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();                 // this CTA's cost is visible before the ticket is taken
+    s_last = atomicAdd(p.done_counter, 1) == p.B - 1;
+  }
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence();
+  if (threadIdx.x < NT) {
+    double acc = 0.0;
+    for (int i = threadIdx.x; i < p.B; i += NT) {
+      double c = (double)__ldcg(p.costs + i) * (double)p.ctc_w;
+      if (p.xe_rows != nullptr) c += (double)__ldcg(p.xe_costs + i) * (double)p.ls_w;
+      acc += c;
+    }
+    part[threadIdx.x] = acc;
+  }
+  __syncthreads();
+  for (int o = NT / 2; o > 0; o >>= 1) {
+    if ((int)threadIdx.x < o) part[threadIdx.x] += part[threadIdx.x + o];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) *p.loss_sum = (float)(part[0] * (double)p.loss_scale);
+}
+
 // One CTA per utterance, longest lattice first (p.order): per side NWMAX lattice warps and kReducers
 // reducer warps (lattice_fast.cuh); NS lattice states per lane.  The block-exponent fast path runs unless
 // the utterance was flagged by K1 or is too long for the lattice window; when the fast path gives
@@ -63,55 +117,56 @@ __global__ void __launch_bounds__(2 * (NWMAX + kReducers) * 32, 1) lattice_kerne
     g_cta_time[blockIdx.x * 2 + 1] = (long long)t;
   }
 #endif
-  // A CTA that never needed K1's output (infeasible or empty utterance) still must not let this kernel complete
-  // before K1 does: whatever follows in the stream is ordered behind THIS kernel.  A no-op for everybody else.
-  pdl_wait_primary();
-  // Label smoothing (b200ctc_options): -sum_{t<T_b} sum_k log y[t,k] of this utterance from K1's per-row terms,
-  // strided partial sums in double, then a tree: fixed order.
-  double* part = reinterpret_cast<double*>(smem);
-  if (p.xe_rows != nullptr) {
-    pdl_wait_primary();
-    __syncthreads();               // the utterance's own use of the shared memory is over
-    if (threadIdx.x < 256) {
-      double acc = 0.0;
-      const int n_rows = m.feasible ? m.T : 0;     // K1 writes the term for live rows only
-      for (int t = threadIdx.x; t < n_rows; t += 256) acc += (double)__ldcg(p.xe_rows + (long long)t * p.B + b);
-      part[threadIdx.x] = acc;
-    }
-    __syncthreads();
-    for (int o = 128; o > 0; o >>= 1) {
-      if ((int)threadIdx.x < o) part[threadIdx.x] += part[threadIdx.x + o];
+  utterance_tail(p, b, m, smem);
+}
+
+// The thread-block-cluster variant: TWO CTAs per utterance, the forward sweep on one SM and the backward sweep on
+// another (NWMAX lattice warps + kReducers helper warps each), for mini-batches that leave at least half of the
+// SMs idle.  The sides meet once, at the midpoint (a cluster barrier: everything phase 1 stored is visible to the
+// other SM afterwards), and compare their abort words through distributed shared memory at the end; the CTA of
+// rank 0 owns the utterance-level duties (safe lattice, flags, the tail).
+template <int K, int NWMAX, int NS>
+__global__ void __launch_bounds__((NWMAX + kReducers) * 32, 1) lattice_cluster_kernel(CallParams p) {
+  extern __shared__ __align__(16) unsigned char smem[];
+  pdl_launch_dependents();
+  const unsigned rank = cluster_ctarank();
+  const int b = p.order[blockIdx.x >> 1];
+  const UttMeta m = p.meta[b];
+  const bool owner = rank == 0;
+  if (!m.feasible) {
+    if (owner && threadIdx.x == 0) p.costs[b] = (p.flags[b] & FLAG_INVALID_INPUT) ? NAN : INFINITY;
+  } else if (m.T == 0) {
+    if (owner && threadIdx.x == 0) p.costs[b] = 0.f;
+  } else {
+    bool use_safe = m.L > p.fast_l_cap;
+    bool dirty = false;
+    if (!use_safe) {
+      int* abort_word = nullptr;
+      lattice_fast_utterance<K, NWMAX, NS, true>(p, b, smem, &abort_word);
       __syncthreads();
+      cluster_sync_all();                                   // both sweeps are over, both abort words final
+      const int why = *abort_word | ld_peer_s32(abort_word, rank ^ 1u);
+      cluster_sync_all();                                   // neither CTA reuses its shared memory before the peer has read it
+      use_safe = why != 0;
+      if (owner) {
+        if (!use_safe && p.gathered && p.grads != nullptr && threadIdx.x == 0) atomicOr(p.flags + b, FLAG_OCC_ROWS);
+        if (use_safe && why != kAbortExtremeRow) {
+          dirty = p.grads != nullptr;
+          if (threadIdx.x == 0) atomicOr(p.flags + b, FLAG_PRECISION_LOST);
+          __threadfence();
+          __syncthreads();
+        }
+      }
+    } else {
+      pdl_wait_primary();
     }
-    if (threadIdx.x == 0) p.xe_costs[b] = (float)part[0];
+    if (use_safe && owner) lattice_safe_utterance(p, b, smem, dirty);
   }
-  // K3, fused: the CTA that finishes last sums the per-utterance costs in a fixed order (256 strided
-  // partial sums in double, then a tree), so the returned loss is bit-reproducible run to run.
-  if (p.loss_sum == nullptr) return;
-  __shared__ int s_last;
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    __threadfence();                 // this CTA's cost is visible before the ticket is taken
-    s_last = atomicAdd(p.done_counter, 1) == p.B - 1;
+  if (!owner) {
+    pdl_wait_primary();
+    return;
   }
-  __syncthreads();
-  if (!s_last) return;
-  __threadfence();
-  if (threadIdx.x < 256) {
-    double acc = 0.0;
-    for (int i = threadIdx.x; i < p.B; i += 256) {
-      double c = (double)__ldcg(p.costs + i) * (double)p.ctc_w;
-      if (p.xe_rows != nullptr) c += (double)__ldcg(p.xe_costs + i) * (double)p.ls_w;
-      acc += c;
-    }
-    part[threadIdx.x] = acc;
-  }
-  __syncthreads();
-  for (int o = 128; o > 0; o >>= 1) {
-    if ((int)threadIdx.x < o) part[threadIdx.x] += part[threadIdx.x + o];
-    __syncthreads();
-  }
-  if (threadIdx.x == 0) *p.loss_sum = (float)(part[0] * (double)p.loss_scale);
+  utterance_tail(p, b, m, smem);
 }
 
 constexpr size_t kSmemBudget = 227 * 1024 - 6 * 1024;   // dynamic shared memory: 227 KB per CTA minus the kernel's static arrays (4.4 KB)
@@ -124,6 +179,7 @@ constexpr size_t kSmemBudget = 227 * 1024 - 6 * 1024;   // dynamic shared memory
 struct LatticeCfg {
   int nwmax, l_cap;
   size_t smem;
+  bool cluster;      // two CTAs per utterance (lattice_cluster_kernel)
 };
 template <int NWMAX>
 size_t fast_bytes_at(const CallParams& p, int L) {
@@ -132,6 +188,25 @@ size_t fast_bytes_at(const CallParams& p, int L) {
 }
 size_t fast_bytes(const CallParams& p, int nwmax, int L) {
   return nwmax == 1 ? fast_bytes_at<1>(p, L) : (nwmax == 2 ? fast_bytes_at<2>(p, L) : fast_bytes_at<4>(p, L));
+}
+template <int NWMAX>
+size_t fast_bytes_cluster_at(const CallParams& p, int L) {
+  const int rw = p.gathered ? em_width_of(L) : (p.V + 3) / 4 * 4;
+  return fast_smem_bytes_cluster<kChunk, NWMAX, 8>(L, rw, p.V);
+}
+size_t fast_bytes_cluster(const CallParams& p, int nwmax, int L) {
+  return nwmax == 1 ? fast_bytes_cluster_at<1>(p, L) : (nwmax == 2 ? fast_bytes_cluster_at<2>(p, L) : fast_bytes_cluster_at<4>(p, L));
+}
+// Two CTAs per utterance pay when every CTA gets an SM of its own: 2 * B <= number of SMs (B200CTC_CLUSTER=0 / 1
+// overrides the choice, for A/B measurements).
+bool want_cluster(int B) {
+  static int n_sm = 0;
+  if (n_sm == 0) {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) n_sm = 1;
+  }
+  if (const char* e = std::getenv("B200CTC_CLUSTER")) return e[0] == '1';
+  return 2 * B <= n_sm;
 }
 int round_nw(int nw) { return nw <= 1 ? 1 : (nw <= 2 ? 2 : 4); }
 
@@ -147,6 +222,13 @@ cudaError_t lattice_cfg(const CallParams& p, int max_L, LatticeCfg* out) {
   out->nwmax = nwmax;
   out->l_cap = fast <= kSmemBudget ? l_cap : -1;   // -1: every utterance takes the safe lattice
   out->smem = (out->l_cap >= 0 && fast > safe) ? fast : safe;
+  out->cluster = out->l_cap >= 0 && want_cluster(p.B);
+  if (out->cluster) {
+    // one side per CTA; at least 116 KB so that the two CTAs of a cluster cannot share an SM
+    const size_t one = fast_bytes_cluster(p, nwmax, out->l_cap);
+    size_t sm = one > safe ? one : safe;
+    out->smem = sm > (size_t)116 * 1024 ? sm : (size_t)116 * 1024;
+  }
   return cudaSuccess;
 }
 
@@ -169,6 +251,28 @@ cudaError_t launch_lattice_t(const CallParams& p, size_t smem, cudaStream_t stre
   cfg.attrs = attr;
   cfg.numAttrs = 1;
   return cudaLaunchKernelEx(&cfg, lattice_kernel<K, NWMAX, NS>, p);
+}
+
+template <int K, int NWMAX, int NS>
+cudaError_t launch_lattice_cluster_t(const CallParams& p, size_t smem, cudaStream_t stream) {
+  cudaError_t e = cudaFuncSetAttribute(lattice_cluster_kernel<K, NWMAX, NS>,
+                                       cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return e;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)(2 * p.B));
+  cfg.blockDim = dim3((NWMAX + kReducers) * 32);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[2];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  attr[1].id = cudaLaunchAttributeClusterDimension;
+  attr[1].val.clusterDim.x = 2;
+  attr[1].val.clusterDim.y = 1;
+  attr[1].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 2;
+  return cudaLaunchKernelEx(&cfg, lattice_cluster_kernel<K, NWMAX, NS>, p);
 }
 
 // Gathered mode, after the lattice: grads[t,b,symbol] -= s_occ * occupancy for the blank and every distinct symbol
@@ -216,6 +320,11 @@ cudaError_t launch_lattice(const CallParams& p, int max_L, cudaStream_t stream) 
   cudaError_t e = lattice_cfg(p, max_L, &c);
   if (e != cudaSuccess) return e;
   // eight lattice states per lane; one, two or four 256-state windows per sweep
+  if (c.cluster) {
+    if (c.nwmax == 1) return launch_lattice_cluster_t<kChunk, 1, 8>(p, c.smem, stream);
+    if (c.nwmax == 2) return launch_lattice_cluster_t<kChunk, 2, 8>(p, c.smem, stream);
+    return launch_lattice_cluster_t<kChunk, 4, 8>(p, c.smem, stream);
+  }
   if (c.nwmax == 1) return launch_lattice_t<kChunk, 1, 8>(p, c.smem, stream);
   if (c.nwmax == 2) return launch_lattice_t<kChunk, 2, 8>(p, c.smem, stream);
   return launch_lattice_t<kChunk, 4, 8>(p, c.smem, stream);   // longer label sequences (L > 463) take the safe lattice

@@ -88,6 +88,27 @@ __device__ __forceinline__ void named_bar_sync(int id, int count) {
 __device__ __forceinline__ void named_bar_arrive(int id, int count) {
   asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(count) : "memory");
 }
+// ---- thread-block cluster (the two-CTA variant: alpha sweep on one SM, beta sweep on another) ----
+__device__ __forceinline__ unsigned cluster_ctarank() {
+  unsigned r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+// All threads of both CTAs.  Release/acquire at cluster scope: global and shared writes before the barrier are
+// visible to the other CTA after it; the fence also orders them against the other CTA's TMA (async proxy) reads.
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("fence.proxy.async;" ::: "memory");
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+  asm volatile("fence.proxy.async;" ::: "memory");
+}
+__device__ __forceinline__ int ld_peer_s32(const int* local_ptr, unsigned peer_rank) {   // the same word in the peer CTA's shared memory
+  unsigned a = (unsigned)__cvta_generic_to_shared(local_ptr), pa;
+  int v;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(pa) : "r"(a), "r"(peer_rank));
+  asm volatile("ld.shared::cluster.s32 %0, [%1];" : "=r"(v) : "r"(pa) : "memory");
+  return v;
+}
 __device__ __forceinline__ void cp_async_4(void* smem, const void* gmem) {
   unsigned s = (unsigned)__cvta_generic_to_shared(smem);
   asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(s), "l"(gmem) : "memory");
@@ -253,6 +274,12 @@ __host__ __device__ inline size_t fast_smem_bytes(int L, int RW, int V) {
   return common + 2 * fast_side_bytes<K, NWMAX, NS>(L, RW, V) + 16;
 }
 
+template <int K, int NWMAX, int NS>
+__host__ __device__ inline size_t fast_smem_bytes_cluster(int L, int RW, int V) {   // one side per CTA
+  size_t common = (size_t)(16 + 6 * L + 16 + (V <= kUntouchedMaxV ? V : 0)) * 4;
+  common = (common + 15) / 16 * 16;
+  return common + fast_side_bytes<K, NWMAX, NS>(L, RW, V) + 16;
+}
 template <int K, int NWMAX, int NS>
 __device__ __forceinline__ FastSideSmem carve_fast_side(unsigned char* base, int L, int RW, int V) {
   constexpr int HL = 2 * exchange_frames<K, NS>() / NS;
@@ -696,7 +723,9 @@ __device__ __forceinline__ SidePlan side_plan(int T) {
 // ---------------------------------------------------------------------------------------------
 // lattice warps of one side
 // ---------------------------------------------------------------------------------------------
-template <int K, int NWMAX, int SIDE, int NS>
+// CL: the two sides are the two CTAs of a thread-block cluster; the one rendezvous of the sides (midpoint) then is
+// a cluster barrier instead of a named barrier.
+template <int K, int NWMAX, int SIDE, int NS, bool CL>
 __device__ void fast_side_sweep(const CallParams& p, int b, const UttMeta& m, const FastCommon& cm,
                                 unsigned char* side_smem, int w, int lane) {
   constexpr int NP = NS / 2, NH = NS / 4;
@@ -841,7 +870,7 @@ __device__ void fast_side_sweep(const CallParams& p, int b, const UttMeta& m, co
   // Lattice and helper warps of both sides meet here exactly once: everything phase 1 stored is
   // visible afterwards.
   B200CTC_TRACE_EVENT(tc, 4);
-  named_bar_sync(kBarMidpoint, 2 * (NW + kReducers) * 32);
+  if (CL) cluster_sync_all(); else named_bar_sync(kBarMidpoint, 2 * (NW + kReducers) * 32);
   if (nc2 == 0) return;
   named_bar_sync(bar_chunk(SIDE), (NW + kReducers) * 32);       // the helpers fetched the records of the first phase-2 chunk
 
@@ -982,7 +1011,7 @@ __device__ __forceinline__ void reduce_frame(const CallParams& p, const FastComm
 // of chunk c+1 needs (emission row; in phase 2 the other side's records of all position groups) and,
 // in phase 2, reduces the posteriors the lattice warps produced for its frame of chunk c-1 into the
 // gradient row.  It meets the lattice warps at the one barrier per chunk.
-template <int K, int NWMAX, int SIDE, int NS>
+template <int K, int NWMAX, int SIDE, int NS, bool CL>
 __device__ void fast_side_helper(const CallParams& p, int b, const UttMeta& m, const FastCommon& cm,
                                  unsigned char* side_smem, int hj, int lane) {
   static_assert(kReducers == K, "one helper warp per frame of a chunk");
@@ -1030,7 +1059,7 @@ __device__ void fast_side_helper(const CallParams& p, int b, const UttMeta& m, c
   }
 
   // ================================ midpoint ================================
-  named_bar_sync(kBarMidpoint, 2 * nbar);
+  if (CL) cluster_sync_all(); else named_bar_sync(kBarMidpoint, 2 * nbar);
   if (pl.nc2 == 0) return;
   if (M_side + hj < T) {                             // records of the first phase-2 chunk
     prefetch_other<SIDE>(c, hj, M_side + hj, mbar);
@@ -1100,7 +1129,9 @@ __device__ void fast_side_helper(const CallParams& p, int b, const UttMeta& m, c
 // The whole fast path for one utterance; every thread of the CTA calls it.  On return the shared
 // word (*smem_abort)[0] is non-zero when the utterance must be redone by the safe lattice (the
 // caller reads it after a __syncthreads()).
-template <int K, int NWMAX, int NS>
+// CL (cluster variant): the CTA holds ONE side -- the one its rank in the two-CTA cluster names -- with NWMAX
+// lattice warps and kReducers helper warps; both CTAs run the (cheap) prologue.
+template <int K, int NWMAX, int NS, bool CL = false>
 __device__ void lattice_fast_utterance(const CallParams& p, int b, unsigned char* smem, int** smem_abort) {
   const UttMeta m = p.meta[b];
   const int L = m.L;
@@ -1112,12 +1143,12 @@ __device__ void lattice_fast_utterance(const CallParams& p, int b, unsigned char
   const int NW = NWMAX > 1 ? __shfl_sync(0xffffffffu, fast_warps_needed<K, NS>(L), 0) : fast_warps_needed<K, NS>(L);
   const int warp = NWMAX > 1 ? __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0) : (int)(threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
-  const int side = warp / (NWMAX + kReducers);
-  int w = warp - side * (NWMAX + kReducers);
+  const int side = CL ? (int)cluster_ctarank() : warp / (NWMAX + kReducers);
+  int w = CL ? warp : warp - side * (NWMAX + kReducers);
   // Scheduler balance: warp i issues on SM sub-partition i % 4.  Early in phase 1 (and late in phase 2)
   // only the lowest lattice windows of each side are inside the reachable band; giving the backward
   // side its windows in reverse warp order puts the two busy windows on different sub-partitions.
-  if (side == 1 && w < NWMAX) w = NWMAX - 1 - w;
+  if (!CL && side == 1 && w < NWMAX) w = NWMAX - 1 - w;
 
   // ---- shared memory: common part, then one block per side ----
   FastCommon cm;
@@ -1148,7 +1179,7 @@ __device__ void lattice_fast_utterance(const CallParams& p, int b, unsigned char
   // posterior buffers start all-zero: padding slots and the blank partials of idle threads are never written
   {
     const int PS = post_stride<NWMAX>(L, p.V);
-    for (int sd = 0; sd < 2; ++sd) {
+    for (int sd = 0; sd < (CL ? 1 : 2); ++sd) {
       FastSideSmem s = carve_fast_side<K, NWMAX, NS>(smem + common + sd * side_bytes, L, RW, p.V);
       for (int i = threadIdx.x; i < 2 * K * PS; i += blockDim.x) s.post[i] = 0.f;
     }
@@ -1188,7 +1219,7 @@ __device__ void lattice_fast_utterance(const CallParams& p, int b, unsigned char
       cm.slot_of_label[cm.ix.sorted[k]] = cm.seg_slot[lo] + (k - cm.ix.seg_start[lo]);
     }
     __syncthreads();
-    if (p.gathered && p.grads != nullptr) {      // apply_occupancy_kernel needs the distinct symbols in global memory
+    if (p.gathered && p.grads != nullptr && (!CL || side == 0)) {   // apply_occupancy_kernel needs the distinct symbols in global memory
       for (int u = threadIdx.x; u < n_seg; u += blockDim.x) p.sym_tab[m.sym_off + u] = cm.ix.seg_sym[u];
       if (threadIdx.x == 0) p.nseg[b] = n_seg;
     }
@@ -1229,12 +1260,15 @@ __device__ void lattice_fast_utterance(const CallParams& p, int b, unsigned char
     if (threadIdx.x == 0) *cm.abort_flag = kAbortExtremeRow;
     return;
   }
+  unsigned char* side_smem = smem + common + (CL ? 0 : side) * side_bytes;
   if (w < NW) {
-    if (side == 0) fast_side_sweep<K, NWMAX, 0, NS>(p, b, m, cm, smem + common, w, lane);
-    else           fast_side_sweep<K, NWMAX, 1, NS>(p, b, m, cm, smem + common + side_bytes, w, lane);
+    if (side == 0) fast_side_sweep<K, NWMAX, 0, NS, CL>(p, b, m, cm, side_smem, w, lane);
+    else           fast_side_sweep<K, NWMAX, 1, NS, CL>(p, b, m, cm, side_smem, w, lane);
   } else if (w >= NWMAX) {
-    if (side == 0) fast_side_helper<K, NWMAX, 0, NS>(p, b, m, cm, smem + common, w - NWMAX, lane);
-    else           fast_side_helper<K, NWMAX, 1, NS>(p, b, m, cm, smem + common + side_bytes, w - NWMAX, lane);
+    if (side == 0) fast_side_helper<K, NWMAX, 0, NS, CL>(p, b, m, cm, side_smem, w - NWMAX, lane);
+    else           fast_side_helper<K, NWMAX, 1, NS, CL>(p, b, m, cm, side_smem, w - NWMAX, lane);
+  } else if (CL) {
+    cluster_sync_all();          // an idle lattice warp: the midpoint rendezvous counts every thread of the cluster
   }
   // idle warps wait at the caller's __syncthreads()
 }

@@ -375,3 +375,40 @@ def test_extension_and_ctypes_bindings_agree():
         o = torch.load(out)
     assert torch.equal(o[0], c1.cpu()) and torch.equal(o[1], g1.cpu())
     assert torch.equal(o[2], c2.cpu()) and torch.equal(o[3], l2.cpu()) and torch.equal(o[4], g2.cpu())
+
+
+@pytest.mark.parametrize("B,T,V,Lmax", [(6, 300, 30, 140), (3, 500, 30, 400), (8, 120, 62, 40), (4, 200, 300, 60), (2, 64, 12, 0)])
+def test_cluster_and_single_cta_lattice_agree(B, T, V, Lmax, monkeypatch):
+    """Mini-batches that leave half of the SMs idle run the lattice as a two-CTA thread-block cluster per utterance
+    (alpha sweep on one SM, beta sweep on another); B200CTC_CLUSTER=0/1 forces either variant.  Same arithmetic in
+    the same order: bit-identical costs and gradients, and both within tolerance of the oracle."""
+    wl = workloads.make_lengths_and_labels(None, B=B, T=T, V=V, Lmax=max(Lmax, 1), kind="var", seed=90 + B)
+    if Lmax == 0:
+        wl = workloads.Workload(wl.name, T, B, V, np.zeros(0, np.int32), np.zeros(B, np.int32), wl.act_lens, 0)
+    acts_t = workloads.make_acts(wl)
+    acts = acts_t.cuda()
+    out = {}
+    for mode in ("0", "1"):
+        monkeypatch.setenv("B200CTC_CLUSTER", mode)
+        c, l, g = b200.ctc_loss_and_grad(acts, wl.labels, wl.act_lens, wl.label_lens)
+        c2 = b200.ctc_loss_and_grad(acts, wl.labels, wl.act_lens, wl.label_lens, need_grad=False)[0]
+        torch.cuda.synchronize()
+        assert ctc_mod.last_fallbacks() == (0, 0)
+        out[mode] = (c.clone(), l.clone(), g.clone(), c2.clone())
+    for a, b_ in zip(out["0"], out["1"]):
+        assert torch.equal(a, b_)
+    assert_parity(out["1"][0], out["1"][2], acts_t.numpy(), wl)
+
+
+def test_cluster_variant_falls_back_to_the_safe_lattice(monkeypatch):
+    monkeypatch.setenv("B200CTC_CLUSTER", "1")
+    rng = np.random.RandomState(95)
+    wl = workloads.make_lengths_and_labels(None, B=4, T=90, V=12, Lmax=20, kind="var", seed=95)
+    acts = workloads.make_acts(wl).numpy()
+    acts[:, 1] *= 60.0                                             # extreme rows: utterance 1 takes the fp64 safe lattice
+    c, l, g = b200.ctc_loss_and_grad(torch.from_numpy(acts).cuda(), wl.labels, wl.act_lens, wl.label_lens)
+    torch.cuda.synchronize()
+    assert ctc_mod.last_fallbacks()[0] >= 1
+    c_ref, g_ref = ctc_ref.ctc_cost_and_grad(acts, wl.labels, wl.act_lens, wl.label_lens)
+    assert np.max(np.abs(c.cpu().numpy() - c_ref) / np.maximum(np.abs(c_ref), 1e-3)) < LOSS_RTOL
+    assert np.max(np.abs(g.cpu().numpy() - g_ref)) < GRAD_ATOL
