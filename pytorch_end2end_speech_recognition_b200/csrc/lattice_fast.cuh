@@ -72,12 +72,21 @@ __device__ __forceinline__ void trace_event(int& cnt, int tag) {
 #endif
 
 #ifndef B200CTC_ABLATE
-#define B200CTC_ABLATE 0   // developer timing experiments (tools/ablate_lattice.py); 0 = product
+#define B200CTC_ABLATE 0   // developer timing experiments (tools/ablate_lattice.py): a bit mask, bit n = experiment n; 0 = product
 #endif
+#define B200CTC_ABL(n) (((B200CTC_ABLATE) >> (n)) & 1)
 constexpr int kAbortExtremeRow = 2;  // abort word: K1 flagged the utterance (nothing was written yet); 1 = redo after a lost range
 constexpr int kEZero = -(1 << 28);  // exponent of an all-zero lane
 constexpr int kRowsRing = 4;        // emission-row ring, in halo-exchange intervals (KX/K chunks each): the reducers' one, the current one, the next (landed), the one after (in flight)
 constexpr int kReducers = 4;        // reducer warps per side: warp j takes frame j of every phase-2 chunk (== K)
+// Depth of the record ring (phase 2), in chunks: the helper warps fetch the opposite side's records kOthDepth - 1
+// chunks ahead.  A bulk copy out of the HBM scratch takes ~2000 cycles under load -- longer than a chunk computes --
+// so with a ring of two (fetch during chunk c what chunk c + 1 reads) its latency sat on the critical path of every
+// chunk (B200, C3: 0.191 -> 0.17x ms per step, see experiments/README.md).
+#ifndef B200CTC_OTH_DEPTH
+#define B200CTC_OTH_DEPTH 4
+#endif
+constexpr int kOthDepth = B200CTC_OTH_DEPTH;
 
 // ---------------------------------------------------------------------------------------------
 // PTX helpers
@@ -237,13 +246,13 @@ __host__ __device__ inline int post_label_slots(int L, int V) {
 
 struct FastSideSmem {
   float* rows;      // [kRowsRing * KX/K][K][RWS]   staged emission rows (+ a zero slot at index RW)
-  unsigned char* oth;   // [2][K] frame blocks   the opposite side's stored records, two chunks (+ one all-zero block)
+  unsigned char* oth;   // [kOthDepth][K] frame blocks   the opposite side's stored records, a ring of chunks (+ one all-zero block)
   float* post;      // [2][K][PS]              symbol-sorted label posteriors + blank partials + dump slot
   float4* halo_m;   // [2][NWMAX][HL][NS/4]    halo lanes
   int* halo_e;      // [2][NWMAX][HL]
   float* red_m;     // [NWMAX]
   int* red_e;       // [NWMAX]
-  unsigned long long* mbar;   // [kReducers]   one mbarrier per helper warp (TMA bulk copies of the records)
+  unsigned long long* mbar;   // [kReducers][kOthDepth]   one mbarrier per helper warp and ring slot (TMA bulk copies of the records)
 };
 
 template <int NWMAX>
@@ -256,13 +265,13 @@ __host__ __device__ inline size_t fast_side_bytes(int L, int RW, int V) {
   constexpr int HL = 2 * exchange_frames<K, NS>() / NS;
   constexpr int RCH = kRowsRing * exchange_frames<K, NS>() / K;   // chunk slots of the emission-row ring
   size_t b = 0;
-  b += (size_t)(2 * K + 1) * frame_block_bytes<NS>(L);       // oth (+ the zero block)
+  b += (size_t)(kOthDepth * K + 1) * frame_block_bytes<NS>(L);   // oth (+ the zero block)
   b += (size_t)2 * NWMAX * HL * (NS / 4) * 16;               // halo_m
   b += (size_t)RCH * K * (size_t)(RW + 4) * 4;               // rows
   b += 2 * (size_t)K * post_stride<NWMAX>(L, V) * 4;         // post
   b += (size_t)2 * NWMAX * HL * 4;                           // halo_e
   b += NWMAX * 8;                                            // red
-  b += (size_t)kReducers * 8 + 8;                            // mbar
+  b += (size_t)kReducers * kOthDepth * 8 + 8;                // mbar
   return (b + 15) / 16 * 16;
 }
 constexpr int kUntouchedMaxV = 256;   // the small-vocabulary (non-gathered) lattice never sees a larger vocabulary
@@ -286,7 +295,7 @@ __device__ __forceinline__ FastSideSmem carve_fast_side(unsigned char* base, int
   constexpr int RCH = kRowsRing * exchange_frames<K, NS>() / K;
   FastSideSmem s;
   unsigned char* p = base;
-  s.oth = p;                               p += (size_t)(2 * K + 1) * frame_block_bytes<NS>(L);
+  s.oth = p;                               p += (size_t)(kOthDepth * K + 1) * frame_block_bytes<NS>(L);
   s.halo_m = reinterpret_cast<float4*>(p); p += (size_t)2 * NWMAX * HL * (NS / 4) * 16;
   s.rows = reinterpret_cast<float*>(p);    p += (size_t)RCH * K * (size_t)(RW + 4) * 4;
   s.post = reinterpret_cast<float*>(p);    p += 2 * (size_t)K * post_stride<NWMAX>(L, V) * 4;
@@ -362,7 +371,7 @@ __device__ __forceinline__ void lattice_frame(LaneState<NS>& st, const LaneConst
                                               bool lane0, f2 (&ACC)[NS / 2], int& E) {
   constexpr int NP = NS / 2;
   const float a_top = el_j4<SIDE>(st.A[NP - 1]), a_top2 = el_j4<SIDE>(st.A[NP - 2]);
-#if B200CTC_ABLATE == 4
+#if B200CTC_ABL(4)
   const float n1 = a_top, n2 = a_top2;
   int ne = st.e;
 #else
@@ -371,7 +380,7 @@ __device__ __forceinline__ void lattice_frame(LaneState<NS>& st, const LaneConst
   int ne = __shfl_up_sync(0xffffffffu, st.e, 1);
 #endif
   // emissions: one broadcast load for the blank positions, one gather per label position
-#if B200CTC_ABLATE == 2
+#if B200CTC_ABL(2)
   const float yb = 0.5f;
   float y[NP];
 #pragma unroll
@@ -409,7 +418,7 @@ __device__ __forceinline__ void lattice_frame(LaneState<NS>& st, const LaneConst
       W[j] = f2_mul(ACC[j], YB);
     }
   }
-#if B200CTC_ABLATE == 3
+#if B200CTC_ABL(3)
   const float mx = 1.0f;
 #else
   const float mx = f2_max_all<NP>(W);
@@ -474,9 +483,7 @@ __device__ __forceinline__ void prefetch_other(const FastCtx<SIDE>& c, int slot,
 
 // Helper warp: stage the emission row of the frame of step n into row `slot` (= ring slot * K + frame).
 template <int SIDE>
-__device__ __forceinline__ void stage_row(const FastCtx<SIDE>& c, int slot, int n) {
-  const char* src = c.st_src + (long long)c.frame_of(n) * c.st_stride;
-  const unsigned dst = c.st_dst + (unsigned)(slot * c.RWS * 4);
+__device__ __forceinline__ void stage_row_at(const FastCtx<SIDE>& c, unsigned dst, const char* src) {
 #pragma unroll 1
   for (int e = c.lane; e < c.per_row; e += 32) {
     const unsigned d = dst + (unsigned)(e - c.lane) * (unsigned)c.st_vecB;
@@ -485,6 +492,10 @@ __device__ __forceinline__ void stage_row(const FastCtx<SIDE>& c, int slot, int 
     else if (c.st_vecB == 8) asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(d), "l"(g) : "memory");
     else asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(d), "l"(g) : "memory");
   }
+}
+template <int SIDE>
+__device__ __forceinline__ void stage_row(const FastCtx<SIDE>& c, int slot, int n) {
+  stage_row_at<SIDE>(c, c.st_dst + (unsigned)(slot * c.RWS * 4), c.st_src + (long long)c.frame_of(n) * c.st_stride);
 }
 
 // Posterior of one frame for one lane: the fresh renormalised state times the stored record of the
@@ -569,17 +580,17 @@ __device__ __forceinline__ void run_chunk(const FastCtx<SIDE>& c, SweepState<NS>
     const int plane = c.JG * 16;
     const int eoff = ss.weoff;                                    // exponent slot relative to the first mantissa plane slot
     unsigned char* blk = ss.wblk;
-#if B200CTC_ABLATE == 8
+#if B200CTC_ABL(8)
     LaneState<NS> dummy = ss.st;
 #endif
 #pragma unroll 2
     for (int j = 0; j < kc; ++j) {
       f2 ACC[NP]; int E;
-#if B200CTC_ABLATE == 8
+#if B200CTC_ABL(8)
       { f2 ACC2[NP]; int E2; lattice_frame<SIDE, NS>(dummy, lc, row, lane0, ACC2, E2); }
 #endif
       lattice_frame<SIDE, NS>(ss.st, lc, row, lane0, ACC, E);
-      if (B200CTC_ABLATE != 1) {
+      if (!B200CTC_ABL(1)) {
         // the reader's pair j is this lane's pair NP-1-j (mirrored group, mirrored packing); lanes that
         // own no group (halo, beyond the lattice) store into the dump block: no branch in the loop
 #pragma unroll
@@ -592,7 +603,7 @@ __device__ __forceinline__ void run_chunk(const FastCtx<SIDE>& c, SweepState<NS>
       blk += ss.wstep;
     }
     ss.wblk = blk;
-#if B200CTC_ABLATE == 8
+#if B200CTC_ABL(8)
     if (dummy.e == 12345) ss.maxbound = 1 << 20;   // keep the duplicate chain alive
 #endif
   } else {
@@ -602,14 +613,14 @@ __device__ __forceinline__ void run_chunk(const FastCtx<SIDE>& c, SweepState<NS>
     const bool store = write_post;
     if (active) {
       const unsigned char* blk = c.sm.oth + (size_t)obuf * K * c.FB;
-      const unsigned char* zero_blk = c.sm.oth + (size_t)2 * K * c.FB;
+      const unsigned char* zero_blk = c.sm.oth + (size_t)kOthDepth * K * c.FB;
       const int plane = c.JG * 16;
 #pragma unroll 2
       for (int j = 0; j < kc; ++j) {
         f2 ACC[NP]; int E;
         lattice_frame<SIDE, NS>(ss.st, lc, row, lane0, ACC, E);
         const bool wr = (unsigned)(ss.rd_hi - (n0 + j)) < (unsigned)ss.wr_len;   // did the other side store this record?
-        if (B200CTC_ABLATE != 5) posterior_frame<SIDE, NS>(ss, wr ? blk : zero_blk, plane, post);
+        if (!B200CTC_ABL(5)) posterior_frame<SIDE, NS>(ss, wr ? blk : zero_blk, plane, post);
         row += row_bytes;
         post += post_bytes;
         blk += c.FB;
@@ -631,7 +642,7 @@ __device__ __forceinline__ void run_chunk(const FastCtx<SIDE>& c, SweepState<NS>
 // of the previous chunk is consumed), import the halo.
 template <int K, int NWMAX, int SIDE, int NS>
 __device__ __forceinline__ void chunk_boundary(const FastCtx<SIDE>& c, SweepState<NS>& ss, int cc, int* abort_flag, int& tc,
-                                               bool exchange = true) {
+                                               bool exchange = true, bool sync = true) {
   constexpr int NH = NS / 4, HL = 2 * exchange_frames<K, NS>() / NS;
   static_assert(HL * NS == 2 * exchange_frames<K, NS>() && HL >= 1, "the halo must be whole lanes");
   const int hb = cc & 1, NW = c.NW, w = c.w, lane = c.lane;
@@ -645,10 +656,7 @@ __device__ __forceinline__ void chunk_boundary(const FastCtx<SIDE>& c, SweepStat
   }
   if (ss.lc.owned && ss.maxbound > kLostBound) *abort_flag = 1;
   B200CTC_TRACE_EVENT(tc, 30);
-#if B200CTC_ABLATE == 7
-  if ((cc & 7) == 7)
-#endif
-  named_bar_sync(bar_chunk(SIDE), (NW + kReducers) * 32);
+  if (sync) named_bar_sync(bar_chunk(SIDE), (NW + kReducers) * 32);
   B200CTC_TRACE_EVENT(tc, 31);
   if (exchange && w > 0 && lane < HL) {
     const int slot = (hb * NWMAX + (w - 1)) * HL + lane;
@@ -836,7 +844,7 @@ __device__ void fast_side_sweep(const CallParams& p, int b, const UttMeta& m, co
   int* abort_flag = cm.abort_flag;
 
   // the all-zero frame block (stands in for records the other side never wrote)
-  for (int i = c.tid_side; i < c.FB / 4; i += NW * 32) reinterpret_cast<int*>(c.sm.oth + (size_t)2 * K * c.FB)[i] = (i >= NH * JG * 4) ? kEZero : 0;
+  for (int i = c.tid_side; i < c.FB / 4; i += NW * 32) reinterpret_cast<int*>(c.sm.oth + (size_t)kOthDepth * K * c.FB)[i] = (i >= NH * JG * 4) ? kEZero : 0;
   // zero slots of the row buffers (the helper warps stage the rows themselves)
   for (int i = c.tid_side; i < RCH * K; i += NW * 32) {
     float* z = c.sm.rows + (size_t)i * c.RWS + c.RW;
@@ -885,7 +893,7 @@ __device__ void fast_side_sweep(const CallParams& p, int b, const UttMeta& m, co
       if (lc.owned) {
         // no band masks: outside the band one of the two factors is exactly zero (posterior_frame)
         const bool wr = (unsigned)(ss.rd_hi - n0) < (unsigned)ss.wr_len;
-        const unsigned char* blk = c.sm.oth + (wr ? (size_t)0 : (size_t)2 * K * c.FB);
+        const unsigned char* blk = c.sm.oth + (wr ? (size_t)0 : (size_t)kOthDepth * K * c.FB);
         float sum = 0.f;
 #pragma unroll
         for (int h = 0; h < NH; ++h) {
@@ -919,11 +927,11 @@ __device__ void fast_side_sweep(const CallParams& p, int b, const UttMeta& m, co
   for (int n0 = M_side; n0 < T; n0 += K, ++k2, ++cc) {
     const int kc = min(K, T - n0), par = k2 & 1;
     B200CTC_TRACE_EVENT(tc, 13);
-    run_chunk<K, true, SIDE, NT, NS>(c, ss, rs, par, par, n0, kc, write_post);
+    run_chunk<K, true, SIDE, NT, NS>(c, ss, rs, par, k2 % kOthDepth, n0, kc, write_post);
     B200CTC_TRACE_EVENT(tc, 14);
     // the barrier with the helpers is per chunk; the halo is good for KX frames after an exchange
     const bool exchange = (k2 + 1) % (KX / K) == 0;
-    chunk_boundary<K, NWMAX, SIDE, NS>(c, ss, xc, abort_flag, tc, exchange);
+    chunk_boundary<K, NWMAX, SIDE, NS>(c, ss, xc, abort_flag, tc, exchange, !B200CTC_ABL(7) || exchange);
     rs = (rs + 1) & (RCH - 1);
     xc += exchange ? 1 : 0;
   }
@@ -935,11 +943,17 @@ __device__ void fast_side_sweep(const CallParams& p, int b, const UttMeta& m, co
 // ---------------------------------------------------------------------------------------------
 // Sum of one symbol's group of the posterior row: n4 16-byte chunks starting at row4.  Every lane of the
 // warp runs max_n4 (warp-uniform) iterations; chunks past the lane's own group read as zero.  Fixed order.
-__device__ __forceinline__ float post_group_sum(const float4* __restrict__ row4, int n4, int max_n4) {
+__device__ __forceinline__ float4 lds128(unsigned a) {   // 16 bytes at a shared-window address
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(a));
+  return v;
+}
+// [a, end): the lane's group as shared-window addresses; `zero`: sixteen zero bytes (what chunks past the group read)
+__device__ __forceinline__ float post_group_sum(unsigned a, unsigned end, unsigned zero, int max_n4) {
   float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
-#pragma unroll 4
-  for (int r = 0; r < max_n4; ++r) {
-    const float4 v = r < n4 ? row4[r] : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll 2
+  for (int r = 0; r < max_n4; ++r, a += 16) {
+    const float4 v = lds128(a < end ? a : zero);
     a0 += v.x; a1 += v.y; a2 += v.z; a3 += v.w;
   }
   return (a0 + a1) + (a2 + a3);
@@ -956,10 +970,10 @@ __device__ __forceinline__ float warp_sum_q30(float v) {
 // of its gradient row.
 template <int NWMAX>
 __device__ __forceinline__ void reduce_frame(const CallParams& p, const FastCommon& cm, const float* __restrict__ post,
-                                             const float* __restrict__ yrow, float* __restrict__ grow,
+                                             const float* __restrict__ yrow, float* __restrict__ grow, unsigned zero,
                                              int RC, int NW, int n_seg, int max_n4, const int (&base4)[2], const int (&n4)[2],
                                              const int (&sym)[2], int lane) {
-  const float4* post4 = reinterpret_cast<const float4*>(post);
+  const unsigned post_a = smem_u32(post);
   const bool gathered = p.gathered != 0;
   // blank: partial sums of the lattice threads
   float accb = 0.f;
@@ -969,12 +983,12 @@ __device__ __forceinline__ void reduce_frame(const CallParams& p, const FastComm
   const float sy = p.s_y, so = p.s_occ, cl = p.c_ls;   // (1, 1, 0) unless the call carries b200ctc_options
   if (n_seg <= 64 && !gathered) {
     // small vocabularies, straight line: lane u owns symbols u and u + 32 (their groups are in registers)
-    const float tot0 = post_group_sum(post4 + base4[0], n4[0], max_n4);
+    const float tot0 = post_group_sum(post_a + 16u * base4[0], post_a + 16u * (base4[0] + n4[0]), zero, max_n4);
     const float y0 = lane < n_seg ? yrow[sym[0]] : 0.f;
     const float yb = yrow[p.blank];
     float tot1 = 0.f, y1 = 0.f;
     if (n_seg > 32) {
-      tot1 = post_group_sum(post4 + base4[1], n4[1], max_n4);
+      tot1 = post_group_sum(post_a + 16u * base4[1], post_a + 16u * (base4[1] + n4[1]), zero, max_n4);
       y1 = lane + 32 < n_seg ? yrow[sym[1]] : 0.f;
     }
     accb = warp_sum_q30(accb);
@@ -985,7 +999,7 @@ __device__ __forceinline__ void reduce_frame(const CallParams& p, const FastComm
     for (int u0 = 0; u0 < n_seg; u0 += 32) {
       const int u = u0 + lane;
       const int s0 = u < n_seg ? cm.seg_slot[u] : 0, s1 = u < n_seg ? cm.seg_slot[u + 1] : 0;
-      const float tot = post_group_sum(post4 + (s0 >> 2), (s1 - s0) >> 2, max_n4);
+      const float tot = post_group_sum(post_a + 4u * s0, post_a + 4u * s1, zero, max_n4);
       if (u < n_seg) {
         const int sy_ = cm.ix.seg_sym[u];
         if (!gathered) grow[sy_] = fmaf(-so, tot, fmaf(sy, yrow[sy_], -cl));
@@ -1023,10 +1037,9 @@ __device__ void fast_side_helper(const CallParams& p, int b, const UttMeta& m, c
   const int nbar = (NW + kReducers) * 32;
   B200CTC_TRACE_DECL(tc);
 
-  unsigned long long* mbar = c.sm.mbar + hj;
-  unsigned mphase = 0;
+  unsigned long long* mbar = c.sm.mbar + hj * kOthDepth;   // one per ring slot: slot s completes phase (q / kOthDepth) & 1 for chunk q
   if (lane == 0) {
-    mbar_init(mbar, 1);
+    for (int s = 0; s < kOthDepth; ++s) mbar_init(mbar + s, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   __syncwarp();
@@ -1061,23 +1074,27 @@ __device__ void fast_side_helper(const CallParams& p, int b, const UttMeta& m, c
   // ================================ midpoint ================================
   if (CL) cluster_sync_all(); else named_bar_sync(kBarMidpoint, 2 * nbar);
   if (pl.nc2 == 0) return;
-  if (M_side + hj < T) {                             // records of the first phase-2 chunk
-    prefetch_other<SIDE>(c, hj, M_side + hj, mbar);
-    if (!mbar_wait(mbar, mphase) && lane == 0) *cm.abort_flag = 1;   // never observed; the safe lattice would redo the utterance
-    mphase ^= 1;
-  }
+  // The records frame hj of phase-2 chunk q needs travel into ring slot q % kOthDepth, kOthDepth - 1 chunks ahead of
+  // the lattice warps (the slot is free: they finished chunk q - kOthDepth before the barrier that precedes the copy).
+  const int nc2 = pl.nc2;
+  auto fetch = [&](int q) {
+    const int n = M_side + q * K + hj;
+    if (!B200CTC_ABL(10) && q < nc2 && n < T) prefetch_other<SIDE>(c, (q % kOthDepth) * K + hj, n, mbar + q % kOthDepth);
+  };
+  auto landed = [&](int q) {
+    const int n = M_side + q * K + hj;
+    if (!B200CTC_ABL(10) && !B200CTC_ABL(11) && q < nc2 && n < T)
+      if (!mbar_wait(mbar + q % kOthDepth, (unsigned)(q / kOthDepth) & 1u) && lane == 0) *cm.abort_flag = 1;   // never observed; the safe lattice would redo the utterance
+  };
+  for (int q = 0; q < kOthDepth - 1; ++q) fetch(q);
+  landed(0);
   named_bar_sync(bar_chunk(SIDE), nbar);
   named_bar_sync(bar_total(SIDE), nbar);
   {
     float inv_mP; int eP; double log2P;
     if (!total_probability(c.sm, NW, inv_mP, eP, log2P)) return;
   }
-  const bool reduce = p.grads != nullptr && B200CTC_ABLATE != 9;   // ablation 9: helpers do not reduce (timing only)
-  // the row reduce_frame updates: the gradient row of the frame, or (gathered mode) the frame's emission row in the
-  // workspace, which nobody reads any more once its posteriors exist and which becomes its occupancy row
-  auto out_row = [&](int frame) -> float* {
-    return p.gathered ? p.em + m.em_off + (long long)frame * m.W : p.grads + ((long long)frame * p.B + b) * V;
-  };
+  const bool reduce = p.grads != nullptr && !B200CTC_ABL(9);   // ablation 9: helpers do not reduce (timing only)
 
   const int n_seg = *cm.ix.n_seg, max_n4 = *cm.max_n4;
   int sym[2], base4[2], n4[2];                        // this lane's symbol groups (u = lane, lane + 32)
@@ -1090,39 +1107,59 @@ __device__ void fast_side_helper(const CallParams& p, int b, const UttMeta& m, c
   }
 
   // ================================ phase 2 ================================
+  // Running addresses, advanced once per chunk: the loop holds no multiplication by a frame index.  (The helper
+  // warps execute ~7 cycles per instruction next to the lattice warps; every instruction here delays the barrier.)
+  // By now every chunk phase 1's look-ahead requested is a phase-2 chunk or the last chunk of phase 1.
+  const int sgn = SIDE ? -1 : 1;
+  // (a) emission rows: chunk `staged` is the next one to request (at most one per iteration)
+  const int st_adv = sgn * K * c.st_stride;
+  const char* st_src = c.st_src + (long long)c.frame_of(chunk_start(staged) + hj) * c.st_stride;
+  int st_n = chunk_start(staged) + hj;
+  // (b) the opposite side's records: chunk k2 + kOthDepth - 1 goes into ring slot (k2 - 1) % kOthDepth
+  const int rec_adv = sgn * K * c.FB;
+  int rec_n = M_side + (kOthDepth - 1) * K + hj;
+  const unsigned char* rec_src = c.scr + (long long)c.frame_of(rec_n) * c.FB;
+  // (c) the row reduce_frame updates: the gradient row of the frame, or (gathered mode) the frame's emission row in
+  // the workspace, which nobody reads any more once its posteriors exist and which becomes its occupancy row
+  const long long out_stride = p.gathered ? (long long)m.W : (long long)p.B * V;
+  float* out = (p.gathered ? p.em + m.em_off : p.grads + (long long)b * V) + (long long)c.frame_of(M_side + hj) * out_stride;
+  const long long out_adv = sgn * K * out_stride;
+  const unsigned zero16 = smem_u32(c.sm.rows + c.RW);          // the zero slot of emission row 0
+  const float* post_hj = c.sm.post + (size_t)hj * c.PS;
+  const int post_half = K * c.PS;                               // floats per posterior buffer
+  const float* rows_hj = c.sm.rows + (size_t)hj * c.RWS;
+  const int row_chunk = K * c.RWS;                              // floats per chunk slot of the row ring
+  const unsigned st_dst_hj = c.st_dst + (unsigned)(hj * c.RWS * 4);
+
   int k2 = 0;
-  for (int n0 = M_side; n0 < T; n0 += K, ++k2, ++cc) {
-    const int par = k2 & 1;
+  for (; k2 < nc2; ++k2, ++cc) {
     B200CTC_TRACE_EVENT(tc, 7);
-    bool copying = false;
-    stage_upto(cc + 3);                               // chunk cc+2 (a no-op while phase 1's look-ahead lasts)
-    if (n0 + K + hj < T) {                            // the other side's records frame hj of the next chunk needs
-      prefetch_other<SIDE>(c, (par ^ 1) * K + hj, n0 + K + hj, mbar);
-      copying = true;
+    if (staged < cc + 3 && staged < n_chunks) {       // chunk cc+2 (nothing to do while phase 1's look-ahead lasts)
+      if (st_n < T) stage_row_at<SIDE>(c, st_dst_hj + (unsigned)((staged & (RCH - 1)) * row_chunk * 4), st_src);   // a row past a short chunk is harmless
+      ++staged; st_n += K; st_src += st_adv;
     }
+    cp_async_commit();
+    if (!B200CTC_ABL(10) && rec_n < T && lane == 0) {
+      unsigned long long* mb = mbar + ((k2 + kOthDepth - 1) % kOthDepth);
+      mbar_expect_tx(mb, (unsigned)c.FB);
+      bulk_g2s(c.sm.oth + (size_t)(((k2 + kOthDepth - 1) % kOthDepth) * K + hj) * c.FB, rec_src, (unsigned)c.FB, mb);
+    }
+    rec_n += K; rec_src += rec_adv;
     B200CTC_TRACE_EVENT(tc, 8);
     if (reduce && k2 >= 1) {                          // frame hj of the previous chunk (it was a full chunk)
-      const int n = n0 - K + hj;
-      reduce_frame<NWMAX>(p, cm, c.sm.post + (size_t)((par ^ 1) * K + hj) * c.PS,
-                          c.sm.rows + (size_t)(((cc - 1) & (RCH - 1)) * K + hj) * c.RWS,
-                          out_row(c.frame_of(n)), c.RC, NW, n_seg, max_n4, base4, n4, sym, lane);
+      reduce_frame<NWMAX>(p, cm, post_hj + ((k2 - 1) & 1) * post_half, rows_hj + ((cc - 1) & (RCH - 1)) * row_chunk,
+                          out, zero16, c.RC, NW, n_seg, max_n4, base4, n4, sym, lane);
+      out += out_adv;
     }
     B200CTC_TRACE_EVENT(tc, 9);
     cp_async_wait<1>();
-    if (copying) {
-      if (!mbar_wait(mbar, mphase) && lane == 0) *cm.abort_flag = 1;
-      mphase ^= 1;
-    }
-    named_bar_sync(bar_chunk(SIDE), nbar);
+    landed(k2 + 1);
+    if (!B200CTC_ABL(7) || (k2 + 1) % (KX / K) == 0) named_bar_sync(bar_chunk(SIDE), nbar);
   }
   // the last chunk
-  if (reduce) {
-    const int n0 = M_side + (k2 - 1) * K, par = (k2 - 1) & 1;
-    if (n0 + hj < T)
-      reduce_frame<NWMAX>(p, cm, c.sm.post + (size_t)(par * K + hj) * c.PS,
-                          c.sm.rows + (size_t)(((cc - 1) & (RCH - 1)) * K + hj) * c.RWS,
-                          out_row(c.frame_of(n0 + hj)), c.RC, NW, n_seg, max_n4, base4, n4, sym, lane);
-  }
+  if (reduce && M_side + (k2 - 1) * K + hj < T)
+    reduce_frame<NWMAX>(p, cm, post_hj + ((k2 - 1) & 1) * post_half, rows_hj + ((cc - 1) & (RCH - 1)) * row_chunk,
+                        out, zero16, c.RC, NW, n_seg, max_n4, base4, n4, sym, lane);
   cp_async_wait<0>();
 }
 
