@@ -75,6 +75,13 @@ __device__ __forceinline__ void trace_event(int& cnt, int tag) {
 #define B200CTC_ABLATE 0   // developer timing experiments (tools/ablate_lattice.py): a bit mask, bit n = experiment n; 0 = product
 #endif
 #define B200CTC_ABL(n) (((B200CTC_ABLATE) >> (n)) & 1)
+#ifndef B200CTC_PH1_UNROLL
+#define B200CTC_PH1_UNROLL 2   // frames per unrolled iteration of the phase-1 / phase-2 frame loops
+#endif
+#ifndef B200CTC_PH2_UNROLL
+#define B200CTC_PH2_UNROLL 2
+#endif
+constexpr int kPh1Unroll = B200CTC_PH1_UNROLL, kPh2Unroll = B200CTC_PH2_UNROLL;
 constexpr int kAbortExtremeRow = 2;  // abort word: K1 flagged the utterance (nothing was written yet); 1 = redo after a lost range
 constexpr int kEZero = -(1 << 28);  // exponent of an all-zero lane
 constexpr int kRowsRing = 4;        // emission-row ring, in halo-exchange intervals (KX/K chunks each): the reducers' one, the current one, the next (landed), the one after (in flight)
@@ -583,7 +590,7 @@ __device__ __forceinline__ void run_chunk(const FastCtx<SIDE>& c, SweepState<NS>
 #if B200CTC_ABL(8)
     LaneState<NS> dummy = ss.st;
 #endif
-#pragma unroll 2
+#pragma unroll kPh1Unroll
     for (int j = 0; j < kc; ++j) {
       f2 ACC[NP]; int E;
 #if B200CTC_ABL(8)
@@ -615,7 +622,7 @@ __device__ __forceinline__ void run_chunk(const FastCtx<SIDE>& c, SweepState<NS>
       const unsigned char* blk = c.sm.oth + (size_t)obuf * K * c.FB;
       const unsigned char* zero_blk = c.sm.oth + (size_t)kOthDepth * K * c.FB;
       const int plane = c.JG * 16;
-#pragma unroll 2
+#pragma unroll kPh2Unroll
       for (int j = 0; j < kc; ++j) {
         f2 ACC[NP]; int E;
         lattice_frame<SIDE, NS>(ss.st, lc, row, lane0, ACC, E);

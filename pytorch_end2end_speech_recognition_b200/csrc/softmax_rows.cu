@@ -11,6 +11,8 @@
 // models/pytorch_v3/ctc/ctc.py:36; here that fill is fused into this pass).
 //
 // Bound: HBM.  Algorithmic bytes per row: 4V read + 4V written.
+#include <cstdlib>
+
 #include "common.cuh"
 
 namespace b200ctc {
@@ -259,6 +261,207 @@ __global__ void __launch_bounds__(kRowThreads) softmax_rows_cta_kernel(CallParam
   }
 }
 
+
+// ---- large vocabulary, streaming: persistent warps, rows arrive through per-warp rings of TMA bulk copies ----
+// The CTA-per-row kernel above spends ~3600 warp instructions per row of V = 3386 (block reductions replicated in
+// eight warps, barriers, short loops) and is bound by the issue slots, not by HBM: 4.0 TB/s on B200.  Here ONE WARP
+// owns a row (no block-wide reduction, no CTA barrier) and keeps the next row of its own in flight with
+// cp.async.bulk (global -> shared, completion on an mbarrier) while it works on the current one; warp w of the
+// grid walks rows w, w + W, w + 2W, ...  A row of V floats is not 16-byte aligned in general: the copy moves the
+// enclosing aligned window and the row sits `phase` floats into its stage.  Rows whose window would leave the
+// logits tensor (first / last row of an unaligned tensor) are loaded with plain loads; padding frames need no
+// load at all (zero fill).
+constexpr int kStreamMaxWarps = 8;     // warps per CTA (fewer when two rows per warp do not fit the shared memory)
+constexpr float kLog2e = 1.4426950408889634f;
+
+__device__ __forceinline__ unsigned sm_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ bool stream_mbar_wait(unsigned bar, unsigned parity) {
+  for (int it = 0; it < (1 << 22); ++it) {     // bounded: a copy that never completes must not hang the GPU
+    unsigned done;
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}\n" : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+    if (done) return true;
+  }
+  return false;
+}
+__device__ __forceinline__ float ex2_approx(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
+struct StreamRow {
+  int t, b;
+  bool live, bulk;
+  const float* arow;
+  int phase;              // floats between the aligned window start and the row
+  unsigned bytes;         // size of the aligned window
+};
+__device__ __forceinline__ StreamRow stream_row(const CallParams& p, unsigned row, uintptr_t acts_lo, uintptr_t acts_hi) {
+  StreamRow r;
+  r.t = (int)(row / (unsigned)p.B);
+  r.b = (int)(row - (unsigned)r.t * (unsigned)p.B);
+  const int mT = p.meta[r.b].T, feas = p.meta[r.b].feasible;
+  r.live = r.t < mT && feas;
+  r.arow = p.acts + (long long)r.t * p.as_t + (long long)r.b * p.as_b;
+  const uintptr_t a = reinterpret_cast<uintptr_t>(r.arow);
+  const uintptr_t lo = a & ~(uintptr_t)15, hi = (a + (uintptr_t)p.V * 4 + 15) & ~(uintptr_t)15;
+  r.phase = (int)((a - lo) >> 2);
+  r.bytes = (unsigned)(hi - lo);
+  r.bulk = r.live && lo >= acts_lo && hi <= acts_hi;
+  return r;
+}
+
+template <bool XE>   // XE: the label-smoothing row term needs sum_k z
+__global__ void __launch_bounds__(kStreamMaxWarps * 32) softmax_rows_stream_kernel(CallParams p, unsigned n_rows, int stage_floats,
+                                                                                  int n_warps, uintptr_t acts_lo, uintptr_t acts_hi) {
+  extern __shared__ __align__(128) float stages[];   // [n_warps][2][stage_floats]
+  __shared__ unsigned long long full_bar[kStreamMaxWarps][2];
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const int V = p.V;
+  const float ls = p.logit_scale;
+  if (wid < n_warps) {
+    const unsigned bar0 = sm_u32(&full_bar[wid][0]);
+    if (lane == 0) {
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar0) : "memory");
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar0 + 8) : "memory");
+      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncwarp();
+    float* ring = stages + (size_t)wid * 2 * stage_floats;
+    const unsigned first = blockIdx.x * (unsigned)n_warps + wid, stride = gridDim.x * (unsigned)n_warps;
+    auto issue = [&](unsigned row, int st) {      // lane 0: request a row of this warp into stage st
+      if (row >= n_rows) return;
+      const StreamRow r = stream_row(p, row, acts_lo, acts_hi);
+      if (!r.bulk) return;
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // the stage was read and written through the generic proxy
+      asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar0 + 8 * st), "r"(r.bytes) : "memory");
+      asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                   ::"r"(sm_u32(ring + (size_t)st * stage_floats)), "l"(reinterpret_cast<const char*>(r.arow) - 4 * r.phase),
+                     "r"(r.bytes), "r"(bar0 + 8 * st) : "memory");
+    };
+    if (lane == 0) issue(first, 0);
+    unsigned parity = 0;                          // bit st: the phase of the stage's mbarrier its next bulk row completes
+    int st = 0;
+    for (unsigned row = first; row < n_rows; row += stride, st ^= 1) {
+      if (lane == 0 && row + stride > row) issue(row + stride, st ^ 1);   // the other stage: this warp finished with it (closing __syncwarp)
+      const StreamRow r = stream_row(p, row, acts_lo, acts_hi);
+      float* grow = p.yrows ? p.yrows + (long long)row * V : nullptr;
+      if (!r.live) {
+        if (grow) {       // zero fill with 128-bit stores on the aligned body
+          int head = (int)(((16 - ((uintptr_t)grow & 15)) & 15) >> 2);
+          if (head > V) head = V;
+          if (lane < head) grow[lane] = 0.f;
+          const int nvec = (V - head) >> 2;
+          float4* g4 = reinterpret_cast<float4*>(grow + head);
+#pragma unroll 4
+          for (int v = lane; v < nvec; v += 32) __stcs(g4 + v, make_float4(0.f, 0.f, 0.f, 0.f));
+          const int tail = head + (nvec << 2) + lane;
+          if (tail < V) grow[tail] = 0.f;
+        }
+        continue;
+      }
+      float* s = ring + (size_t)st * stage_floats + r.phase;     // s[v] <-> arow[v]
+      if (r.bulk) {
+        if (!stream_mbar_wait(bar0 + 8 * st, (parity >> st) & 1u)) __trap();   // never observed; fail loudly rather than read a row that did not land
+        parity ^= 1u << st;
+      } else {            // a row at the edge of an unaligned tensor: plain loads
+        for (int v = lane; v < V; v += 32) s[v] = __ldg(r.arow + v);
+        __syncwarp();
+      }
+      // ---- pass 1: maximum / minimum (/ sum, label smoothing) of the raw logits ----
+      int head = (4 - r.phase) & 3;
+      if (head > V) head = V;
+      const int nvec = (V - head) >> 2, tail0 = head + (nvec << 2);
+      float4* s4 = reinterpret_cast<float4*>(s + head);
+      float mx = -INFINITY, mn = INFINITY, sx = 0.f;
+      if (lane < head) { const float x = s[lane]; mx = x; mn = x; sx = x; }
+      {
+        float mx1 = -INFINITY, mn1 = INFINITY, sx1 = 0.f;
+#pragma unroll 4
+        for (int v = lane; v < nvec; v += 32) {
+          const float4 x = s4[v];
+          mx = fmaxf(mx, fmaxf(x.x, x.y)); mx1 = fmaxf(mx1, fmaxf(x.z, x.w));
+          mn = fminf(mn, fminf(x.x, x.y)); mn1 = fminf(mn1, fminf(x.z, x.w));
+          if (XE) { sx += x.x + x.y; sx1 += x.z + x.w; }
+        }
+        mx = fmaxf(mx, mx1); mn = fminf(mn, mn1); sx += sx1;
+      }
+      if (tail0 + lane < V) { const float x = s[tail0 + lane]; mx = fmaxf(mx, x); mn = fminf(mn, x); sx += x; }
+      mx = warp_max(mx); mn = warp_min(mn);
+      if (XE) sx = warp_sum(sx);
+      // z = ls * x: the scale is positive in every use (1 / temperature), a negative one swaps the extremes
+      const float zmax = ls >= 0.f ? ls * mx : ls * mn, zmin = ls >= 0.f ? ls * mn : ls * mx;
+      // ---- pass 2: e = exp(z - zmax) in place, row sum ----
+      const float a2 = ls * kLog2e, b2 = -zmax * kLog2e;
+      float sum = 0.f, sum1 = 0.f;
+      if (lane < head) { const float e = ex2_approx(fmaf(s[lane], a2, b2)); s[lane] = e; sum = e; }
+#pragma unroll 4
+      for (int v = lane; v < nvec; v += 32) {
+        float4 x = s4[v];
+        x.x = ex2_approx(fmaf(x.x, a2, b2)); x.y = ex2_approx(fmaf(x.y, a2, b2));
+        x.z = ex2_approx(fmaf(x.z, a2, b2)); x.w = ex2_approx(fmaf(x.w, a2, b2));
+        s4[v] = x;
+        sum += x.x + x.y; sum1 += x.z + x.w;
+      }
+      if (tail0 + lane < V) { const float e = ex2_approx(fmaf(s[tail0 + lane], a2, b2)); s[tail0 + lane] = e; sum += e; }
+      sum = warp_sum(sum + sum1);
+      const float inv = 1.0f / sum;
+      const float lse = zmax + logf(sum);
+      if (lane == 0) {
+        p.lse[row] = lse;
+        if (XE) p.xe_rows[row] = (float)V * lse - ls * sx;
+        if (zmin - lse < kExtremeLogProb) atomicOr(p.flags + r.b, FLAG_EXTREME_ROW);
+      }
+      // ---- pass 3: the row in its final form minus the occupancy (gathered mode), label-gathered emissions ----
+      if (grow) {
+        const float sy = p.gathered ? p.s_y * inv : inv, c = p.gathered ? p.c_ls : 0.f;
+        int ghead = (int)(((16 - ((uintptr_t)grow & 15)) & 15) >> 2);
+        if (ghead > V) ghead = V;
+        const int gvec = (V - ghead) >> 2;
+        float4* g4 = reinterpret_cast<float4*>(grow + ghead);
+        if (ghead == head) {          // source and destination rows share the 16-byte phase (contiguous logits): 128-bit both ways,
+          if (lane < ghead) grow[lane] = fmaf(s[lane], sy, -c);   // and every lane re-reads exactly what it wrote in pass 2
+#pragma unroll 4
+          for (int v = lane; v < gvec; v += 32) {
+            const float4 e = s4[v];
+            __stcs(g4 + v, make_float4(fmaf(e.x, sy, -c), fmaf(e.y, sy, -c), fmaf(e.z, sy, -c), fmaf(e.w, sy, -c)));
+          }
+        } else {
+          __syncwarp();
+          if (lane < ghead) grow[lane] = fmaf(s[lane], sy, -c);
+          for (int v = lane; v < gvec; v += 32) {
+            const int o = ghead + (v << 2);
+            __stcs(g4 + v, make_float4(fmaf(s[o], sy, -c), fmaf(s[o + 1], sy, -c), fmaf(s[o + 2], sy, -c), fmaf(s[o + 3], sy, -c)));
+          }
+        }
+        const int gt = ghead + (gvec << 2) + lane;
+        if (gt < V) grow[gt] = fmaf(s[gt], sy, -c);
+      }
+      __syncwarp();       // pass 2's values are visible to every lane
+      if (p.gathered) {
+        const UttMeta m = p.meta[r.b];
+        float* erow = p.em + m.em_off + (long long)r.t * m.W;
+        const int* lab = p.labels + m.lab_off;
+        for (int i = lane; i < m.W; i += 32) {
+          float val = 0.f;
+          if (i == 0) val = s[p.blank] * inv;
+          else if (i <= m.L) val = s[__ldg(lab + i - 1)] * inv;
+          erow[i] = val;
+        }
+      }
+      __syncwarp();       // closing: every lane is done with the stage
+    }
+  }
+  // The lattice kernel may begin its prologue now.  Not earlier: its CTAs (one per utterance, most of an SM's shared
+  // memory each) would sit on their SMs waiting for this grid to finish while this grid still needs them.
+  pdl_launch_dependents();
+}
+
 }  // namespace
 
 cudaError_t launch_softmax_rows(const CallParams& p, cudaStream_t stream) {
@@ -276,6 +479,29 @@ cudaError_t launch_softmax_rows(const CallParams& p, cudaStream_t stream) {
     else if (p.V <= 128) softmax_rows_warp_kernel<32, 4><<<grid_for(1), warps * 32, 0, stream>>>(p);
     else softmax_rows_warp_kernel<32, 8><<<grid_for(1), warps * 32, 0, stream>>>(p);
   } else {
+    // streaming kernel when at least two warps with two rows each fit the shared memory (V <= ~14000), else one CTA per row
+    const int stage_floats = (p.V + 6 + 3) & ~3;
+    const size_t per_warp = (size_t)2 * stage_floats * sizeof(float);
+    int n_warps = (int)((size_t)220 * 1024 / per_warp);
+    if (n_warps > kStreamMaxWarps) n_warps = kStreamMaxWarps;
+    if (n_warps >= 2 && n_rows < (1ll << 31) && !std::getenv("B200CTC_SOFTMAX_CTA_PER_ROW")) {
+      const size_t ring = per_warp * n_warps;
+      auto kern = p.xe_rows ? softmax_rows_stream_kernel<true> : softmax_rows_stream_kernel<false>;
+      cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ring);
+      if (e != cudaSuccess) return e;
+      static int n_sm = 0;
+      if (n_sm == 0) {
+        int dev = 0;
+        if ((e = cudaGetDevice(&dev)) != cudaSuccess) return e;
+        if ((e = cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev)) != cudaSuccess) return e;
+      }
+      long long grid = n_sm;                       // one CTA per SM (the ring takes most of its shared memory)
+      if (grid * n_warps > n_rows) grid = (n_rows + n_warps - 1) / n_warps;
+      const uintptr_t lo = reinterpret_cast<uintptr_t>(p.acts);
+      const uintptr_t hi = lo + (uintptr_t)(((long long)(p.T - 1) * p.as_t + (long long)(p.B - 1) * p.as_b + p.V) * 4);
+      kern<<<(unsigned)grid, kStreamMaxWarps * 32, ring, stream>>>(p, (unsigned)n_rows, stage_floats, n_warps, lo, hi);
+      return cudaGetLastError();
+    }
     const size_t smem = (size_t)(p.V + 4) * sizeof(float);
     if (smem > 48 * 1024) {
       cudaError_t e = cudaFuncSetAttribute(softmax_rows_cta_kernel,
