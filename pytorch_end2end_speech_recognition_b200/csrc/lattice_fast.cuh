@@ -330,6 +330,16 @@ struct FastCommon {
 __device__ __forceinline__ int bar_chunk(int side) { return 1 + side * 2; }   // lattice + helper warps of a side, once per chunk
 __device__ __forceinline__ int bar_total(int side) { return 2 + side * 2; }
 constexpr int kBarMidpoint = 5;
+// The one rendezvous of the two sides.  Phase 1's records were written with ordinary stores (generic proxy); the
+// helper warps read them back with TMA bulk copies (async proxy) right after this barrier.  A CTA barrier orders
+// generic accesses only: without the proxy fence a copy of the newest records -- the frames next to the midpoint
+// -- could overtake the stores and deliver what the scratch held before (found with a poisoned workspace,
+// tools/stress_repro.py --poison: one utterance in a few thousand got NaN or slightly rescaled rows; invisible
+// whenever the scratch still holds the same call's records).
+__device__ __forceinline__ void midpoint_sync(int count) {
+  asm volatile("fence.proxy.async;" ::: "memory");
+  named_bar_sync(kBarMidpoint, count);
+}
 
 // ---------------------------------------------------------------------------------------------
 // per-lane state of a lattice warp.  NP = NS/2 packed pairs; pair j holds elements (j, j+NP).
@@ -885,7 +895,7 @@ __device__ void fast_side_sweep(const CallParams& p, int b, const UttMeta& m, co
   // Lattice and helper warps of both sides meet here exactly once: everything phase 1 stored is
   // visible afterwards.
   B200CTC_TRACE_EVENT(tc, 4);
-  if (CL) cluster_sync_all(); else named_bar_sync(kBarMidpoint, 2 * (NW + kReducers) * 32);
+  if (CL) cluster_sync_all(); else midpoint_sync(2 * (NW + kReducers) * 32);
   if (nc2 == 0) return;
   named_bar_sync(bar_chunk(SIDE), (NW + kReducers) * 32);       // the helpers fetched the records of the first phase-2 chunk
 
@@ -1079,7 +1089,7 @@ __device__ void fast_side_helper(const CallParams& p, int b, const UttMeta& m, c
   }
 
   // ================================ midpoint ================================
-  if (CL) cluster_sync_all(); else named_bar_sync(kBarMidpoint, 2 * nbar);
+  if (CL) cluster_sync_all(); else midpoint_sync(2 * nbar);
   if (pl.nc2 == 0) return;
   // The records frame hj of phase-2 chunk q needs travel into ring slot q % kOthDepth, kOthDepth - 1 chunks ahead of
   // the lattice warps (the slot is free: they finished chunk q - kOthDepth before the barrier that precedes the copy).

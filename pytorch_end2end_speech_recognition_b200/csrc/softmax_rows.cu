@@ -300,13 +300,16 @@ struct StreamRow {
   const float* arow;
   int phase;              // floats between the aligned window start and the row
   unsigned bytes;         // size of the aligned window
+  int L, W, lab_off;      // of the row's utterance (gathered emissions)
+  long long em_off;
 };
 __device__ __forceinline__ StreamRow stream_row(const CallParams& p, unsigned row, uintptr_t acts_lo, uintptr_t acts_hi) {
   StreamRow r;
   r.t = (int)(row / (unsigned)p.B);
   r.b = (int)(row - (unsigned)r.t * (unsigned)p.B);
-  const int mT = p.meta[r.b].T, feas = p.meta[r.b].feasible;
-  r.live = r.t < mT && feas;
+  const UttMeta m = p.meta[r.b];
+  r.live = r.t < m.T && m.feasible;
+  r.L = m.L; r.W = m.W; r.lab_off = m.lab_off; r.em_off = m.em_off;
   r.arow = p.acts + (long long)r.t * p.as_t + (long long)r.b * p.as_b;
   const uintptr_t a = reinterpret_cast<uintptr_t>(r.arow);
   const uintptr_t lo = a & ~(uintptr_t)15, hi = (a + (uintptr_t)p.V * 4 + 15) & ~(uintptr_t)15;
@@ -366,6 +369,18 @@ __global__ void __launch_bounds__(kStreamMaxWarps * 32) softmax_rows_stream_kern
         continue;
       }
       float* s = ring + (size_t)st * stage_floats + r.phase;     // s[v] <-> arow[v]
+      // The labels whose emissions this lane gathers at the end of the row, requested now: the ring leaves the L1
+      // almost no capacity, so every one of these loads is an L2 round trip that would otherwise end the row.
+      constexpr int kLabPre = 8;
+      int lab_pre[kLabPre];
+      if (p.gathered) {
+        const int* lab = p.labels + r.lab_off;
+#pragma unroll
+        for (int j = 0; j < kLabPre; ++j) {
+          const int i = lane + 32 * j;
+          lab_pre[j] = (i >= 1 && i <= r.L) ? __ldg(lab + i - 1) : p.blank;
+        }
+      }
       if (r.bulk) {
         if (!stream_mbar_wait(bar0 + 8 * st, (parity >> st) & 1u)) __trap();   // never observed; fail loudly rather than read a row that did not land
         parity ^= 1u << st;
@@ -444,15 +459,15 @@ __global__ void __launch_bounds__(kStreamMaxWarps * 32) softmax_rows_stream_kern
       }
       __syncwarp();       // pass 2's values are visible to every lane
       if (p.gathered) {
-        const UttMeta m = p.meta[r.b];
-        float* erow = p.em + m.em_off + (long long)r.t * m.W;
-        const int* lab = p.labels + m.lab_off;
-        for (int i = lane; i < m.W; i += 32) {
-          float val = 0.f;
-          if (i == 0) val = s[p.blank] * inv;
-          else if (i <= m.L) val = s[__ldg(lab + i - 1)] * inv;
-          erow[i] = val;
+        float* erow = p.em + r.em_off + (long long)r.t * r.W;
+        const int* lab = p.labels + r.lab_off;
+#pragma unroll
+        for (int j = 0; j < kLabPre; ++j) {        // i = 0: the blank; padding entries (L < i < W): zero
+          const int i = lane + 32 * j;
+          if (i < r.W) erow[i] = i <= r.L ? s[lab_pre[j]] * inv : 0.f;
         }
+        for (int i = lane + 32 * kLabPre; i < r.W; i += 32)
+          erow[i] = i <= r.L ? s[__ldg(lab + i - 1)] * inv : 0.f;
       }
       __syncwarp();       // closing: every lane is done with the stage
     }
