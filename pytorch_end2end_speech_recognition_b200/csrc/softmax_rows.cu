@@ -489,9 +489,15 @@ cudaError_t launch_softmax_rows(const CallParams& p, cudaStream_t stream) {
       const int ty = p.T < 65535 ? p.T : 65535;
       return dim3((unsigned)((p.B + per_cta - 1) / per_cta), (unsigned)ty, (unsigned)((p.T + 65534) / 65535));
     };
-    if (p.V <= 32) softmax_rows_warp_kernel<8, 4><<<grid_for(4), warps * 32, 0, stream>>>(p);
-    else if (p.V <= 64) softmax_rows_warp_kernel<16, 4><<<grid_for(2), warps * 32, 0, stream>>>(p);
-    else if (p.V <= 128) softmax_rows_warp_kernel<32, 4><<<grid_for(1), warps * 32, 0, stream>>>(p);
+    // eight elements per lane: the per-row work (reductions, 1/s, log, flags) is shared by fewer lanes -- the kernel is
+    // bound by its instruction count, not by HBM (profiles/r02_softmax_ncu_summary.txt: 75 % of the issue slots)
+    static const bool nv4 = std::getenv("B200CTC_K1_NV4") != nullptr;   // the previous geometry, for A/B measurements
+    if (nv4 && p.V <= 32) softmax_rows_warp_kernel<8, 4><<<grid_for(4), warps * 32, 0, stream>>>(p);
+    else if (nv4 && p.V <= 64) softmax_rows_warp_kernel<16, 4><<<grid_for(2), warps * 32, 0, stream>>>(p);
+    else if (nv4 && p.V <= 128) softmax_rows_warp_kernel<32, 4><<<grid_for(1), warps * 32, 0, stream>>>(p);
+    else if (p.V <= 32) softmax_rows_warp_kernel<4, 8><<<grid_for(8), warps * 32, 0, stream>>>(p);
+    else if (p.V <= 64) softmax_rows_warp_kernel<8, 8><<<grid_for(4), warps * 32, 0, stream>>>(p);
+    else if (p.V <= 128) softmax_rows_warp_kernel<16, 8><<<grid_for(2), warps * 32, 0, stream>>>(p);
     else softmax_rows_warp_kernel<32, 8><<<grid_for(1), warps * 32, 0, stream>>>(p);
   } else {
     // streaming kernel when at least two warps with two rows each fit the shared memory (V <= ~14000), else one CTA per row

@@ -10,7 +10,8 @@ import pytorch_end2end_speech_recognition_b200 as b200
 from pytorch_end2end_speech_recognition_b200 import workloads
 
 for kw in (dict(B=3, T=37, V=30, Lmax=12), dict(B=2, T=90, V=30, Lmax=40), dict(B=2, T=300, V=30, Lmax=140),
-           dict(B=2, T=60, V=200, Lmax=20), dict(B=1, T=5, V=4, Lmax=2)):
+           dict(B=2, T=60, V=200, Lmax=20), dict(B=1, T=5, V=4, Lmax=2), dict(B=3, T=50, V=301, Lmax=16),
+           dict(B=2, T=40, V=1003, Lmax=12)):
     wl = workloads.make_lengths_and_labels(None, kind="var", seed=3, **kw)
     acts = workloads.make_acts(wl).cuda()
     costs, loss, grads = b200.ctc_loss_and_grad(acts, wl.labels, wl.act_lens, wl.label_lens)
