@@ -457,3 +457,34 @@ def test_results_do_not_depend_on_what_the_workspace_held(key, repeats):
     finally:
         lib.b200ctc_destroy.argtypes = [ctypes.c_void_p]
         lib.b200ctc_destroy(h)
+
+
+@pytest.mark.parametrize("V", [301, 515, 1003])
+@pytest.mark.parametrize("layout", ["contiguous", "batch_major_view", "offset_by_one_float", "offset_by_three_floats"])
+def test_streaming_softmax_row_alignment(V, layout):
+    """K1 for V > 256 moves the 16-byte-aligned window around every row with a TMA bulk copy: rows at every
+    16-byte phase (odd V), source and destination rows at different phases (batch-major view), and a tensor whose
+    first / last rows' windows would leave it (base not 16-byte aligned: those rows take plain loads)."""
+    wl = workloads.make_lengths_and_labels(None, B=5, T=37, V=V, Lmax=9, kind="var", seed=V)
+    ref_acts = workloads.make_acts(wl)                                  # [T, B, V] on the host
+    if layout == "contiguous":
+        acts = ref_acts.cuda()
+    elif layout == "batch_major_view":
+        acts = ref_acts.transpose(0, 1).contiguous().cuda().transpose(0, 1)
+        assert not acts.is_contiguous()
+    else:
+        k = 1 if layout == "offset_by_one_float" else 3
+        buf = torch.empty(ref_acts.numel() + 8, device="cuda")
+        acts = buf[k:k + ref_acts.numel()].view(wl.T, wl.B, V)
+        acts.copy_(ref_acts)
+        assert acts.data_ptr() % 16 == 4 * k
+    costs, loss, grads = b200.ctc_loss_and_grad(acts, wl.labels, wl.act_lens, wl.label_lens)
+    torch.cuda.synchronize()
+    c_ref, g_ref = ctc_ref.ctc_cost_and_grad(ref_acts.numpy(), wl.labels, wl.act_lens, wl.label_lens)
+    c = costs.cpu().numpy()
+    assert np.max(np.abs(c - c_ref) / np.maximum(np.abs(c_ref), 1e-3)) < LOSS_RTOL
+    g = grads.cpu().numpy()
+    assert np.max(np.abs(g - g_ref)) < GRAD_ATOL
+    for b in range(wl.B):
+        assert np.all(g[wl.act_lens[b]:, b] == 0)                       # padding rows: exactly zero
+    assert ctc_mod.last_fallbacks() == (0, 0)
