@@ -281,18 +281,22 @@ __host__ __device__ inline size_t fast_side_bytes(int L, int RW, int V) {
   b += (size_t)kReducers * kOthDepth * 8 + 8;                // mbar
   return (b + 15) / 16 * 16;
 }
+#ifndef B200CTC_GROUP_SPLIT
+#define B200CTC_GROUP_SPLIT 1   // 0: one reducer group per symbol, whatever its size (A/B measurements)
+#endif
+constexpr int kReducerGroups = 64;    // reducer groups of the straight-line reducer path: two per lane
 constexpr int kUntouchedMaxV = 256;   // the small-vocabulary (non-gathered) lattice never sees a larger vocabulary
 template <int K, int NWMAX, int NS>
 __host__ __device__ inline size_t fast_smem_bytes(int L, int RW, int V) {
   // control words, lab, sorted, seg_start, seg_sym, slot_of_label, seg_slot, untouched
-  size_t common = (size_t)(16 + 6 * L + 16 + (V <= kUntouchedMaxV ? V : 0)) * 4;
+  size_t common = (size_t)(16 + 6 * L + 16 + 4 * kReducerGroups + (V <= kUntouchedMaxV ? V : 0)) * 4;
   common = (common + 15) / 16 * 16;
   return common + 2 * fast_side_bytes<K, NWMAX, NS>(L, RW, V) + 16;
 }
 
 template <int K, int NWMAX, int NS>
 __host__ __device__ inline size_t fast_smem_bytes_cluster(int L, int RW, int V) {   // one side per CTA
-  size_t common = (size_t)(16 + 6 * L + 16 + (V <= kUntouchedMaxV ? V : 0)) * 4;
+  size_t common = (size_t)(16 + 6 * L + 16 + 4 * kReducerGroups + (V <= kUntouchedMaxV ? V : 0)) * 4;
   common = (common + 15) / 16 * 16;
   return common + fast_side_bytes<K, NWMAX, NS>(L, RW, V) + 16;
 }
@@ -321,7 +325,14 @@ struct FastCommon {
   SymbolIndex ix;      // sorted / seg_start / seg_sym / n_seg
   int* slot_of_label;  // [L]    slot of label i in the symbol-sorted posterior row
   int* seg_slot;       // [n_seg+1] first slot of every symbol's group in the posterior row (a multiple of 4)
-  int* max_n4;         // the largest group, in 16-byte chunks
+  int* max_n4;         // [0] iterations of a reducer's group sum (16-byte chunks), [1] number of reducer groups, [2] most pieces of one symbol
+  // Reducer groups (small vocabularies, <= 64 of them).  Normally one per distinct symbol; when a few symbols
+  // carry most of the labels (text: the space, 'e') their slot ranges are cut into pieces of at most max_n4[0]
+  // chunks that different lanes sum, so that the reducers' trip count follows the AVERAGE group, not the largest.
+  int* vg_base4;       // [64] first 16-byte chunk
+  int* vg_n4;          // [64] chunks
+  int* vg_sym;         // [64] symbol
+  int* vg_cnt;         // [64] pieces of the symbol if this is its first piece (the lane that writes the entry), else 0
   int* untouched;      // [V] vocabulary entries that are neither the blank nor a label of the utterance (rescaled rows only)
   int* n_untouched;
 };
@@ -985,11 +996,17 @@ __device__ __forceinline__ float warp_sum_q30(float v) {
 
 // Per-symbol occupancy of one phase-2 frame (posterior row `post`, softmax row `yrow`) and the update
 // of its gradient row.
-template <int NWMAX>
+struct ReducerLane {
+  int sym[2], base4[2], n4[2], cnt[2];   // reducer groups lane and lane + 32 (FastCommon::vg_*)
+  int nvg, mp;                           // number of groups; most pieces of one symbol
+};
+// SPLIT: some symbol's slots are cut into pieces (ReducerLane::mp > 1).  A separate instantiation: the combination's
+// shuffles between the group sums and the stores cost the common, unsplit case 5 % of the step (B200, C1 / C2) by
+// merely being there.
+template <int NWMAX, bool SPLIT>
 __device__ __forceinline__ void reduce_frame(const CallParams& p, const FastCommon& cm, const float* __restrict__ post,
                                              const float* __restrict__ yrow, float* __restrict__ grow, unsigned zero,
-                                             int RC, int NW, int n_seg, int max_n4, const int (&base4)[2], const int (&n4)[2],
-                                             const int (&sym)[2], int lane) {
+                                             int RC, int NW, int n_seg, int max_n4, const ReducerLane& rl, int lane) {
   const unsigned post_a = smem_u32(post);
   const bool gathered = p.gathered != 0;
   // blank: partial sums of the lattice threads
@@ -999,18 +1016,29 @@ __device__ __forceinline__ void reduce_frame(const CallParams& p, const FastComm
     if (i < NW) accb += post[RC + i * 32 + lane];
   const float sy = p.s_y, so = p.s_occ, cl = p.c_ls;   // (1, 1, 0) unless the call carries b200ctc_options
   if (n_seg <= 64 && !gathered) {
-    // small vocabularies, straight line: lane u owns symbols u and u + 32 (their groups are in registers)
-    const float tot0 = post_group_sum(post_a + 16u * base4[0], post_a + 16u * (base4[0] + n4[0]), zero, max_n4);
-    const float y0 = lane < n_seg ? yrow[sym[0]] : 0.f;
+    // small vocabularies, straight line: lane u owns reducer groups u and u + 32 (in registers)
+    float tot0 = post_group_sum(post_a + 16u * rl.base4[0], post_a + 16u * (rl.base4[0] + rl.n4[0]), zero, max_n4);
+    const float y0 = rl.cnt[0] > 0 ? yrow[rl.sym[0]] : 0.f;
     const float yb = yrow[p.blank];
     float tot1 = 0.f, y1 = 0.f;
-    if (n_seg > 32) {
-      tot1 = post_group_sum(post_a + 16u * base4[1], post_a + 16u * (base4[1] + n4[1]), zero, max_n4);
-      y1 = lane + 32 < n_seg ? yrow[sym[1]] : 0.f;
+    if (rl.nvg > 32) {
+      tot1 = post_group_sum(post_a + 16u * rl.base4[1], post_a + 16u * (rl.base4[1] + rl.n4[1]), zero, max_n4);
+      y1 = rl.cnt[1] > 0 ? yrow[rl.sym[1]] : 0.f;
+    }
+    if (SPLIT) {
+      // a symbol cut into pieces: its first piece (group v) collects the pieces v + 1 .. v + cnt - 1 in that order
+      const float p0 = tot0, p1 = tot1;
+      for (int j = 1; j < rl.mp; ++j) {
+        const int src = (lane + j) & 31;
+        const float a = __shfl_sync(0xffffffffu, p0, src), b = __shfl_sync(0xffffffffu, p1, src);
+        const bool wrap = lane + j >= 32;                       // group lane + j lives in the second slot of lane `src`
+        if (j < rl.cnt[0]) tot0 += wrap ? b : a;
+        if (j < rl.cnt[1] && !wrap) tot1 += b;                  // group lane + 32 + j (< 64: the pieces of one symbol are consecutive)
+      }
     }
     accb = warp_sum_q30(accb);
-    if (lane < n_seg) grow[sym[0]] = fmaf(-so, tot0, fmaf(sy, y0, -cl));   // the touched symbols of a frame share one or two 128-byte rows
-    if (lane + 32 < n_seg) grow[sym[1]] = fmaf(-so, tot1, fmaf(sy, y1, -cl));
+    if (rl.cnt[0] > 0) grow[rl.sym[0]] = fmaf(-so, tot0, fmaf(sy, y0, -cl));   // the touched symbols of a frame share one or two 128-byte rows
+    if (rl.cnt[1] > 0) grow[rl.sym[1]] = fmaf(-so, tot1, fmaf(sy, y1, -cl));
     if (lane == 0) grow[p.blank] = fmaf(-so, accb, fmaf(sy, yb, -cl));
   } else {
     for (int u0 = 0; u0 < n_seg; u0 += 32) {
@@ -1042,7 +1070,7 @@ __device__ __forceinline__ void reduce_frame(const CallParams& p, const FastComm
 // of chunk c+1 needs (emission row; in phase 2 the other side's records of all position groups) and,
 // in phase 2, reduces the posteriors the lattice warps produced for its frame of chunk c-1 into the
 // gradient row.  It meets the lattice warps at the one barrier per chunk.
-template <int K, int NWMAX, int SIDE, int NS, bool CL>
+template <int K, int NWMAX, int SIDE, int NS, bool CL, bool SPLIT>
 __device__ void fast_side_helper(const CallParams& p, int b, const UttMeta& m, const FastCommon& cm,
                                  unsigned char* side_smem, int hj, int lane) {
   static_assert(kReducers == K, "one helper warp per frame of a chunk");
@@ -1113,14 +1141,18 @@ __device__ void fast_side_helper(const CallParams& p, int b, const UttMeta& m, c
   }
   const bool reduce = p.grads != nullptr && !B200CTC_ABL(9);   // ablation 9: helpers do not reduce (timing only)
 
-  const int n_seg = *cm.ix.n_seg, max_n4 = *cm.max_n4;
-  int sym[2], base4[2], n4[2];                        // this lane's symbol groups (u = lane, lane + 32)
+  const int n_seg = *cm.ix.n_seg, max_n4 = cm.max_n4[0];
+  ReducerLane rl;                                     // this lane's reducer groups (lane, lane + 32)
+  rl.nvg = cm.max_n4[1]; rl.mp = cm.max_n4[2];
+  const bool straight = n_seg <= kReducerGroups && !p.gathered;
 #pragma unroll
   for (int i = 0; i < 2; ++i) {
     const int u = lane + 32 * i;
-    sym[i] = u < n_seg ? cm.ix.seg_sym[u] : 0;
-    base4[i] = u < n_seg ? cm.seg_slot[u] >> 2 : 0;
-    n4[i] = u < n_seg ? (cm.seg_slot[u + 1] - cm.seg_slot[u]) >> 2 : 0;
+    const bool ok = straight && u < rl.nvg;
+    rl.sym[i] = ok ? cm.vg_sym[u] : 0;
+    rl.base4[i] = ok ? cm.vg_base4[u] : 0;
+    rl.n4[i] = ok ? cm.vg_n4[u] : 0;
+    rl.cnt[i] = ok ? cm.vg_cnt[u] : 0;
   }
 
   // ================================ phase 2 ================================
@@ -1164,8 +1196,9 @@ __device__ void fast_side_helper(const CallParams& p, int b, const UttMeta& m, c
     rec_n += K; rec_src += rec_adv;
     B200CTC_TRACE_EVENT(tc, 8);
     if (reduce && k2 >= 1) {                          // frame hj of the previous chunk (it was a full chunk)
-      reduce_frame<NWMAX>(p, cm, post_hj + ((k2 - 1) & 1) * post_half, rows_hj + ((cc - 1) & (RCH - 1)) * row_chunk,
-                          out, zero16, c.RC, NW, n_seg, max_n4, base4, n4, sym, lane);
+      const float* post_row = post_hj + ((k2 - 1) & 1) * post_half;
+      const float* y_row = rows_hj + ((cc - 1) & (RCH - 1)) * row_chunk;
+      reduce_frame<NWMAX, SPLIT>(p, cm, post_row, y_row, out, zero16, c.RC, NW, n_seg, max_n4, rl, lane);
       out += out_adv;
     }
     B200CTC_TRACE_EVENT(tc, 9);
@@ -1174,9 +1207,11 @@ __device__ void fast_side_helper(const CallParams& p, int b, const UttMeta& m, c
     if (!B200CTC_ABL(7) || (k2 + 1) % (KX / K) == 0) named_bar_sync(bar_chunk(SIDE), nbar);
   }
   // the last chunk
-  if (reduce && M_side + (k2 - 1) * K + hj < T)
-    reduce_frame<NWMAX>(p, cm, post_hj + ((k2 - 1) & 1) * post_half, rows_hj + ((cc - 1) & (RCH - 1)) * row_chunk,
-                        out, zero16, c.RC, NW, n_seg, max_n4, base4, n4, sym, lane);
+  if (reduce && M_side + (k2 - 1) * K + hj < T) {
+    const float* post_row = post_hj + ((k2 - 1) & 1) * post_half;
+    const float* y_row = rows_hj + ((cc - 1) & (RCH - 1)) * row_chunk;
+    reduce_frame<NWMAX, SPLIT>(p, cm, post_row, y_row, out, zero16, c.RC, NW, n_seg, max_n4, rl, lane);
+  }
   cp_async_wait<0>();
 }
 
@@ -1216,6 +1251,10 @@ __device__ void lattice_fast_utterance(const CallParams& p, int b, unsigned char
   cm.ix.seg_sym = ip;            ip += L + 1;
   cm.slot_of_label = ip;         ip += L;
   cm.seg_slot = ip;              ip += L + 2;
+  cm.vg_base4 = ip;              ip += kReducerGroups;
+  cm.vg_n4 = ip;                 ip += kReducerGroups;
+  cm.vg_sym = ip;                ip += kReducerGroups;
+  cm.vg_cnt = ip;                ip += kReducerGroups;
   cm.n_untouched = cm.abort_flag + 4;
   cm.untouched = ip;             ip += (p.V <= kUntouchedMaxV ? p.V : 0);
   size_t common = (size_t)(reinterpret_cast<unsigned char*>(ip) - smem);
@@ -1261,7 +1300,81 @@ __device__ void lattice_fast_utterance(const CallParams& p, int b, unsigned char
       }
 #pragma unroll
       for (int o = 16; o > 0; o >>= 1) mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, o));
-      if (lane == 0) { cm.seg_slot[n_seg] = base; *cm.max_n4 = (mx + 3) >> 2; }
+      if (lane == 0) cm.seg_slot[n_seg] = base;
+      __syncwarp();
+      // ---- reducer groups ----
+      const int mx4 = (mx + 3) >> 2, tot4 = base >> 2;
+      int R = mx4, nvg = n_seg, mp = 1;
+      int g4[2], first4[2];
+#pragma unroll
+      for (int i = 0; i < 2; ++i) {
+        const int u = lane + 32 * i;
+        const bool ok = u < n_seg && n_seg <= kReducerGroups;
+        first4[i] = ok ? cm.seg_slot[u] >> 2 : 0;
+        g4[i] = ok ? (cm.seg_slot[u + 1] - cm.seg_slot[u]) >> 2 : 0;
+      }
+      if (n_seg <= kReducerGroups && !p.gathered) {
+        // The smallest piece size whose pieces still fit the lanes (one per lane while the symbols do), taken only
+        // when the model says it pays: 8 instructions per chunk and group slot; the combination costs more than
+        // its instruction count (two shuffles per step on the helpers' critical path), so a split has to save a
+        // quarter of the reducer's loop.  Pieces(r) falls with r: bisection; exact small-integer division by
+        // multiplication (g4 * r < 2^16).  Skipped outright when even the ideal split could not pay (uniform labels).
+        const int limit = n_seg <= 32 ? 32 : 64, slots0 = n_seg <= 32 ? 1 : 2;
+        const int cost0 = slots0 * mx4 * 8;
+        auto split_cost = [](int slots, int r, int pm) { return slots * r * 8 + (pm - 1) * 12 + 16; };
+        int lo = max(1, (tot4 + limit - 1) / limit), hi = mx4 - 1;
+        if (B200CTC_GROUP_SPLIT && lo <= hi && mx4 <= 128 && 4 * split_cost(1, lo, 2) <= 3 * cost0) {
+          auto pieces = [&](int r, int& pm) {
+            const unsigned m = 65536u / (unsigned)r + 1u;
+            const int p0 = (int)(((unsigned)(g4[0] + r - 1) * m) >> 16), p1 = (int)(((unsigned)(g4[1] + r - 1) * m) >> 16);
+            pm = __reduce_max_sync(0xffffffffu, max(p0, p1));
+            return __reduce_add_sync(0xffffffffu, p0 + p1);
+          };
+          while (lo < hi) {                       // pieces(hi) <= n_seg <= limit always holds at hi = mx4
+            const int mid = (lo + hi) >> 1;
+            int pm;
+            if (pieces(mid, pm) <= limit) hi = mid; else lo = mid + 1;
+          }
+          int pm;
+          const int nv = pieces(lo, pm);
+          if (nv <= limit && 4 * split_cost(nv <= 32 ? 1 : 2, lo, pm) <= 3 * cost0) { R = lo; nvg = nv; mp = pm; }
+        }
+        if (mp == 1) {                            // one group per symbol
+#pragma unroll
+          for (int i = 0; i < 2; ++i) {
+            const int u = lane + 32 * i;
+            if (u < n_seg) { cm.vg_base4[u] = first4[i]; cm.vg_n4[u] = g4[i]; cm.vg_sym[u] = cm.ix.seg_sym[u]; cm.vg_cnt[u] = 1; }
+          }
+        } else {
+          // the pieces of symbol u follow one another; exclusive prefix over the symbols in (lane, lane + 32) order
+          const unsigned m = 65536u / (unsigned)R + 1u;
+          int pc[2], pre[2], run = 0;
+#pragma unroll
+          for (int i = 0; i < 2; ++i) {
+            pc[i] = (int)(((unsigned)(g4[i] + R - 1) * m) >> 16);
+            int incl = pc[i];
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+              const int v = __shfl_up_sync(0xffffffffu, incl, o);
+              if (lane >= o) incl += v;
+            }
+            pre[i] = run + incl - pc[i];
+            run += __shfl_sync(0xffffffffu, incl, 31);
+          }
+#pragma unroll
+          for (int i = 0; i < 2; ++i) {
+            const int u = lane + 32 * i;
+            for (int j = 0; j < pc[i]; ++j) {
+              const int v = pre[i] + j;
+              cm.vg_base4[v] = first4[i] + j * R;
+              cm.vg_n4[v] = min(R, g4[i] - j * R);
+              cm.vg_sym[v] = cm.ix.seg_sym[u];
+              cm.vg_cnt[v] = j == 0 ? pc[i] : 0;
+            }
+          }
+        }
+      }
+      if (lane == 0) { cm.max_n4[0] = R; cm.max_n4[1] = nvg; cm.max_n4[2] = mp; }
     }
     __syncthreads();
     for (int k = threadIdx.x; k < L; k += blockDim.x) {
@@ -1319,8 +1432,17 @@ __device__ void lattice_fast_utterance(const CallParams& p, int b, unsigned char
     if (side == 0) fast_side_sweep<K, NWMAX, 0, NS, CL>(p, b, m, cm, side_smem, w, lane);
     else           fast_side_sweep<K, NWMAX, 1, NS, CL>(p, b, m, cm, side_smem, w, lane);
   } else if (w >= NWMAX) {
-    if (side == 0) fast_side_helper<K, NWMAX, 0, NS, CL>(p, b, m, cm, side_smem, w - NWMAX, lane);
-    else           fast_side_helper<K, NWMAX, 1, NS, CL>(p, b, m, cm, side_smem, w - NWMAX, lane);
+    // (a second instantiation of the helper rather than a branch in its loop: the combination of split symbol
+    // groups costs the unsplit case 5 % of the step by merely being in the loop body; out of line -- __noinline__ --
+    // it costs every case 10-15 %: a 448-byte stack frame and the call ABI's register constraints)
+    const bool split = B200CTC_GROUP_SPLIT && __builtin_expect(cm.max_n4[2] > 1, 0);
+    if (!split) {
+      if (side == 0) fast_side_helper<K, NWMAX, 0, NS, CL, false>(p, b, m, cm, side_smem, w - NWMAX, lane);
+      else           fast_side_helper<K, NWMAX, 1, NS, CL, false>(p, b, m, cm, side_smem, w - NWMAX, lane);
+    } else {
+      if (side == 0) fast_side_helper<K, NWMAX, 0, NS, CL, true>(p, b, m, cm, side_smem, w - NWMAX, lane);
+      else           fast_side_helper<K, NWMAX, 1, NS, CL, true>(p, b, m, cm, side_smem, w - NWMAX, lane);
+    }
   } else if (CL) {
     cluster_sync_all();          // an idle lattice warp: the midpoint rendezvous counts every thread of the cluster
   }

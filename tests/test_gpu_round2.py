@@ -488,3 +488,41 @@ def test_streaming_softmax_row_alignment(V, layout):
     for b in range(wl.B):
         assert np.all(g[wl.act_lens[b]:, b] == 0)                       # padding rows: exactly zero
     assert ctc_mod.last_fallbacks() == (0, 0)
+
+
+@pytest.mark.parametrize("V,L,expo", [(30, 400, 1.0), (30, 380, 1.5), (30, 250, 0.7), (62, 330, 1.2), (50, 120, 2.0),
+                                      (64, 400, 1.0), (33, 64, 1.5)])
+@pytest.mark.parametrize("cluster", ["0", "1"])
+def test_split_symbol_groups_of_text_like_labels(V, L, expo, cluster, monkeypatch):
+    """Text-like label statistics (p_k ~ 1 / k^s: a few symbols carry most of the labels): the reducers cut the slot
+    range of a frequent symbol into pieces that several lanes sum and combine (one or two groups per lane, pieces
+    wrapping from the first slot of lane 31 into the second slot of lane 0), in both lattice variants."""
+    monkeypatch.setenv("B200CTC_CLUSTER", cluster)
+    rng = np.random.RandomState(V * 100 + L)
+    p = 1.0 / (np.arange(V - 1) + 1.0) ** expo
+    p /= p.sum()
+    lab = 1 + rng.choice(V - 1, size=L, p=p)
+    lab2 = 1 + rng.choice(V - 1, size=L // 2, p=p[::-1])          # the rare symbols of the first utterance are the frequent ones here
+    T = L + ctc_ref.count_repeats(lab) + 40
+    T2 = len(lab2) + ctc_ref.count_repeats(lab2) + 11
+    acts = rng.randn(T, 2, V).astype(np.float32)
+    labels = np.concatenate([lab, lab2]).astype(np.int32)
+    c, g = None, None
+    costs, loss, grads = b200.ctc_loss_and_grad(torch.from_numpy(acts).cuda(), labels, np.array([T, T2], np.int32),
+                                                np.array([L, len(lab2)], np.int32))
+    torch.cuda.synchronize()
+    assert ctc_mod.last_fallbacks() == (0, 0)
+    c_ref, g_ref = ctc_cpu(acts, labels, np.array([T, T2], np.int32), np.array([L, len(lab2)], np.int32), 0, precision="f64")
+    assert np.max(np.abs(costs.cpu().numpy() - c_ref) / np.maximum(np.abs(c_ref), 1e-3)) < LOSS_RTOL
+    assert np.max(np.abs(grads.cpu().numpy() - g_ref)) < GRAD_ATOL
+    # with the call-site options (every entry of a live row rewritten: the untouched-symbol list next to split groups)
+    logits = torch.from_numpy(np.ascontiguousarray(acts.transpose(1, 0, 2))).cuda().requires_grad_(True)
+    ys = np.zeros((2, L), np.int64)
+    ys[0, :L] = lab - 1
+    ys[1, :len(lab2)] = lab2 - 1
+    x_lens, y_lens = np.array([T, T2], np.int32), np.array([L, len(lab2)], np.int32)
+    out = b200.ctc_loss_from_padded(logits, ys, x_lens, y_lens, logits_temperature=1.3, label_smoothing=0.1)
+    out.backward()
+    loss_ref, gl_ref = ctc_ref.ctc_loss_call_site(acts.transpose(1, 0, 2), ys, x_lens, y_lens, 1.3, 0.1)
+    assert abs(float(out.detach().cpu()[0]) - loss_ref) < LOSS_RTOL * abs(loss_ref)
+    assert np.max(np.abs(logits.grad.cpu().numpy() - gl_ref)) < GRAD_ATOL / 2
