@@ -191,6 +191,7 @@ void fill_common(CallParams& p, const float* acts, int64_t as_t, int64_t as_b, f
   p.gathered = V >= kGatherMinV ? 1 : 0;
   p.yrows = p.gathered ? grads : (grads ? grads : p.em);   // cost only, small vocabulary: the rows go to the workspace
   p.fast_l_cap = 0;
+  p.oth_depth = 2;
   p.dev_label_lens = nullptr;
   p.dev_act_lens = nullptr;
   p.label_stride = 0;

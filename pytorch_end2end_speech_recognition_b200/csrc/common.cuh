@@ -50,6 +50,7 @@ struct CallParams {
   int* sym_tab;           // distinct symbols of every utterance (at meta[b].sym_off), written by the lattice prologue
   int* nseg;              // [B] their number
   int fast_l_cap;         // longest label sequence the block-exponent lattice takes (window count and shared-memory budget)
+  int oth_depth;          // depth of the lattice's record ring, in chunks (2..4; prepare_lattice)
   // Fused call-site arithmetic (b200ctc_options; reference: models/pytorch_v3/ctc/ctc.py:306-307,323,329-337):
   //   z = logit_scale * acts;  grads = s_y * softmax(z) - s_occ * occupancy - c_ls   (rows t < T_b)
   //   loss_sum = loss_scale * sum_b [ ctc_w * cost_b + ls_w * sum_{t<T_b} (V * lse - sum_k z) ]
@@ -92,7 +93,7 @@ __host__ __device__ inline int em_width_of(int L) { return (L + 1 + 3) / 4 * 4; 
 
 // host launchers (each in its own .cu)
 cudaError_t launch_softmax_rows(const CallParams& p, cudaStream_t stream);
-cudaError_t prepare_lattice(CallParams& p, int max_L);     // fills fast_l_cap; error when not even the safe lattice fits
+cudaError_t prepare_lattice(CallParams& p, int max_L);     // fills fast_l_cap and oth_depth; error when not even the safe lattice fits
 cudaError_t launch_lattice(const CallParams& p, int max_L, cudaStream_t stream);
 cudaError_t launch_apply_occupancy(const CallParams& p, cudaStream_t stream);
 cudaError_t launch_plan(const CallParams& p, UttMeta* meta, int* order, int* flags, cudaStream_t stream);

@@ -177,25 +177,25 @@ constexpr size_t kSmemBudget = 227 * 1024 - 6 * 1024;   // dynamic shared memory
 // ring grows with the label sequence, 256 * (L + 5) bytes per side), and the dynamic shared memory.
 // Longer utterances are evaluated by the fp64 safe lattice in the same launch.
 struct LatticeCfg {
-  int nwmax, l_cap;
+  int nwmax, l_cap, depth;   // depth: chunks in the record ring (lattice_fast.cuh)
   size_t smem;
   bool cluster;      // two CTAs per utterance (lattice_cluster_kernel)
 };
 template <int NWMAX>
-size_t fast_bytes_at(const CallParams& p, int L) {
+size_t fast_bytes_at(const CallParams& p, int L, int D) {
   const int rw = p.gathered ? em_width_of(L) : (p.V + 3) / 4 * 4;
-  return fast_smem_bytes<kChunk, NWMAX, 8>(L, rw, p.V);
+  return fast_smem_bytes<kChunk, NWMAX, 8>(L, rw, p.V, D);
 }
-size_t fast_bytes(const CallParams& p, int nwmax, int L) {
-  return nwmax == 1 ? fast_bytes_at<1>(p, L) : (nwmax == 2 ? fast_bytes_at<2>(p, L) : fast_bytes_at<4>(p, L));
+size_t fast_bytes(const CallParams& p, int nwmax, int L, int D) {
+  return nwmax == 1 ? fast_bytes_at<1>(p, L, D) : (nwmax == 2 ? fast_bytes_at<2>(p, L, D) : fast_bytes_at<4>(p, L, D));
 }
 template <int NWMAX>
-size_t fast_bytes_cluster_at(const CallParams& p, int L) {
+size_t fast_bytes_cluster_at(const CallParams& p, int L, int D) {
   const int rw = p.gathered ? em_width_of(L) : (p.V + 3) / 4 * 4;
-  return fast_smem_bytes_cluster<kChunk, NWMAX, 8>(L, rw, p.V);
+  return fast_smem_bytes_cluster<kChunk, NWMAX, 8>(L, rw, p.V, D);
 }
-size_t fast_bytes_cluster(const CallParams& p, int nwmax, int L) {
-  return nwmax == 1 ? fast_bytes_cluster_at<1>(p, L) : (nwmax == 2 ? fast_bytes_cluster_at<2>(p, L) : fast_bytes_cluster_at<4>(p, L));
+size_t fast_bytes_cluster(const CallParams& p, int nwmax, int L, int D) {
+  return nwmax == 1 ? fast_bytes_cluster_at<1>(p, L, D) : (nwmax == 2 ? fast_bytes_cluster_at<2>(p, L, D) : fast_bytes_cluster_at<4>(p, L, D));
 }
 // Two CTAs per utterance pay when every CTA gets an SM of its own: 2 * B <= number of SMs (B200CTC_CLUSTER=0 / 1
 // overrides the choice, for A/B measurements).
@@ -213,19 +213,27 @@ int round_nw(int nw) { return nw <= 1 ? 1 : (nw <= 2 ? 2 : 4); }
 cudaError_t lattice_cfg(const CallParams& p, int max_L, LatticeCfg* out) {
   const size_t safe = safe_smem_bytes(max_L) > 256 * sizeof(double) ? safe_smem_bytes(max_L) : 256 * sizeof(double);
   if (safe > kSmemBudget) return cudaErrorInvalidConfiguration;   // not even the safe lattice holds this label sequence
-  int nwmax = round_nw(fast_warps_needed<kChunk, 8>(max_L));
-  int l_cap = max_L;
-  // shared memory is monotonic in L (and in the row width, which follows L in gathered mode)
-  while (l_cap > 0 && (fast_warps_needed<kChunk, 8>(l_cap) > nwmax || fast_bytes(p, nwmax, l_cap) > kSmemBudget)) --l_cap;
+  // The deepest record ring whose shared memory still holds the longest label sequence; when none does, the
+  // shallowest (largest capacity) and the longer utterances take the safe lattice.
+  int nwmax = 1, l_cap = 0, depth = 2;
+  for (int D = kOthDepthMax; D >= 2; --D) {
+    nwmax = round_nw(fast_warps_needed<kChunk, 8>(max_L));
+    l_cap = max_L;
+    // shared memory is monotonic in L (and in the row width, which follows L in gathered mode)
+    while (l_cap > 0 && (fast_warps_needed<kChunk, 8>(l_cap) > nwmax || fast_bytes(p, nwmax, l_cap, D) > kSmemBudget)) --l_cap;
+    depth = D;
+    if (l_cap >= max_L) break;
+  }
   nwmax = round_nw(fast_warps_needed<kChunk, 8>(l_cap));
-  const size_t fast = fast_bytes(p, nwmax, l_cap);
+  const size_t fast = fast_bytes(p, nwmax, l_cap, depth);
   out->nwmax = nwmax;
+  out->depth = depth;
   out->l_cap = fast <= kSmemBudget ? l_cap : -1;   // -1: every utterance takes the safe lattice
   out->smem = (out->l_cap >= 0 && fast > safe) ? fast : safe;
   out->cluster = out->l_cap >= 0 && want_cluster(p.B);
   if (out->cluster) {
     // one side per CTA; at least 116 KB so that the two CTAs of a cluster cannot share an SM
-    const size_t one = fast_bytes_cluster(p, nwmax, out->l_cap);
+    const size_t one = fast_bytes_cluster(p, nwmax, out->l_cap, depth);
     size_t sm = one > safe ? one : safe;
     out->smem = sm > (size_t)116 * 1024 ? sm : (size_t)116 * 1024;
   }
@@ -313,7 +321,7 @@ namespace {
 cudaError_t prepare_lattice(CallParams& p, int max_L) {
   LatticeCfg c;
   cudaError_t e = lattice_cfg(p, max_L, &c);
-  if (e == cudaSuccess) p.fast_l_cap = c.l_cap;
+  if (e == cudaSuccess) { p.fast_l_cap = c.l_cap; p.oth_depth = c.depth; }
   return e;
 }
 

@@ -86,14 +86,16 @@ constexpr int kAbortExtremeRow = 2;  // abort word: K1 flagged the utterance (no
 constexpr int kEZero = -(1 << 28);  // exponent of an all-zero lane
 constexpr int kRowsRing = 4;        // emission-row ring, in halo-exchange intervals (KX/K chunks each): the reducers' one, the current one, the next (landed), the one after (in flight)
 constexpr int kReducers = 4;        // reducer warps per side: warp j takes frame j of every phase-2 chunk (== K)
-// Depth of the record ring (phase 2), in chunks: the helper warps fetch the opposite side's records kOthDepth - 1
+// Depth D of the record ring (phase 2), in chunks: the helper warps fetch the opposite side's records D - 1
 // chunks ahead.  A bulk copy out of the HBM scratch takes ~2000 cycles under load -- longer than a chunk computes --
-// so with a ring of two (fetch during chunk c what chunk c + 1 reads) its latency sat on the critical path of every
-// chunk (B200, C3: 0.191 -> 0.17x ms per step, see experiments/README.md).
+// so with a ring of two (fetch during chunk c what chunk c + 1 reads) its latency sits on the critical path of
+// some chunks (B200: C3 -2 %, C5 -6 % with four, see experiments/README.md).  Chosen per launch
+// (CallParams::oth_depth, lattice.cu): the deepest of 4, 3, 2 whose shared memory still holds the longest label
+// sequence of the call -- in gathered mode the capacity is 195 / 210 / 226 labels.
 #ifndef B200CTC_OTH_DEPTH
 #define B200CTC_OTH_DEPTH 4
 #endif
-constexpr int kOthDepth = B200CTC_OTH_DEPTH;
+constexpr int kOthDepthMax = B200CTC_OTH_DEPTH;
 
 // ---------------------------------------------------------------------------------------------
 // PTX helpers
@@ -253,13 +255,13 @@ __host__ __device__ inline int post_label_slots(int L, int V) {
 
 struct FastSideSmem {
   float* rows;      // [kRowsRing * KX/K][K][RWS]   staged emission rows (+ a zero slot at index RW)
-  unsigned char* oth;   // [kOthDepth][K] frame blocks   the opposite side's stored records, a ring of chunks (+ one all-zero block)
+  unsigned char* oth;   // [D][K] frame blocks   the opposite side's stored records, a ring of chunks (+ one all-zero block)
   float* post;      // [2][K][PS]              symbol-sorted label posteriors + blank partials + dump slot
   float4* halo_m;   // [2][NWMAX][HL][NS/4]    halo lanes
   int* halo_e;      // [2][NWMAX][HL]
   float* red_m;     // [NWMAX]
   int* red_e;       // [NWMAX]
-  unsigned long long* mbar;   // [kReducers][kOthDepth]   one mbarrier per helper warp and ring slot (TMA bulk copies of the records)
+  unsigned long long* mbar;   // [kReducers][kOthDepthMax]   one mbarrier per helper warp and ring slot (TMA bulk copies of the records)
 };
 
 template <int NWMAX>
@@ -268,17 +270,17 @@ __host__ __device__ inline int post_stride(int L, int V) {  // floats per frame 
 }
 
 template <int K, int NWMAX, int NS>
-__host__ __device__ inline size_t fast_side_bytes(int L, int RW, int V) {
+__host__ __device__ inline size_t fast_side_bytes(int L, int RW, int V, int D) {
   constexpr int HL = 2 * exchange_frames<K, NS>() / NS;
   constexpr int RCH = kRowsRing * exchange_frames<K, NS>() / K;   // chunk slots of the emission-row ring
   size_t b = 0;
-  b += (size_t)(kOthDepth * K + 1) * frame_block_bytes<NS>(L);   // oth (+ the zero block)
+  b += (size_t)(D * K + 1) * frame_block_bytes<NS>(L);       // oth (+ the zero block)
   b += (size_t)2 * NWMAX * HL * (NS / 4) * 16;               // halo_m
   b += (size_t)RCH * K * (size_t)(RW + 4) * 4;               // rows
   b += 2 * (size_t)K * post_stride<NWMAX>(L, V) * 4;         // post
   b += (size_t)2 * NWMAX * HL * 4;                           // halo_e
   b += NWMAX * 8;                                            // red
-  b += (size_t)kReducers * kOthDepth * 8 + 8;                // mbar
+  b += (size_t)kReducers * kOthDepthMax * 8 + 8;             // mbar
   return (b + 15) / 16 * 16;
 }
 #ifndef B200CTC_GROUP_SPLIT
@@ -287,26 +289,26 @@ __host__ __device__ inline size_t fast_side_bytes(int L, int RW, int V) {
 constexpr int kReducerGroups = 64;    // reducer groups of the straight-line reducer path: two per lane
 constexpr int kUntouchedMaxV = 256;   // the small-vocabulary (non-gathered) lattice never sees a larger vocabulary
 template <int K, int NWMAX, int NS>
-__host__ __device__ inline size_t fast_smem_bytes(int L, int RW, int V) {
+__host__ __device__ inline size_t fast_smem_bytes(int L, int RW, int V, int D) {
   // control words, lab, sorted, seg_start, seg_sym, slot_of_label, seg_slot, untouched
   size_t common = (size_t)(16 + 6 * L + 16 + 4 * kReducerGroups + (V <= kUntouchedMaxV ? V : 0)) * 4;
   common = (common + 15) / 16 * 16;
-  return common + 2 * fast_side_bytes<K, NWMAX, NS>(L, RW, V) + 16;
+  return common + 2 * fast_side_bytes<K, NWMAX, NS>(L, RW, V, D) + 16;
 }
 
 template <int K, int NWMAX, int NS>
-__host__ __device__ inline size_t fast_smem_bytes_cluster(int L, int RW, int V) {   // one side per CTA
+__host__ __device__ inline size_t fast_smem_bytes_cluster(int L, int RW, int V, int D) {   // one side per CTA
   size_t common = (size_t)(16 + 6 * L + 16 + 4 * kReducerGroups + (V <= kUntouchedMaxV ? V : 0)) * 4;
   common = (common + 15) / 16 * 16;
-  return common + fast_side_bytes<K, NWMAX, NS>(L, RW, V) + 16;
+  return common + fast_side_bytes<K, NWMAX, NS>(L, RW, V, D) + 16;
 }
 template <int K, int NWMAX, int NS>
-__device__ __forceinline__ FastSideSmem carve_fast_side(unsigned char* base, int L, int RW, int V) {
+__device__ __forceinline__ FastSideSmem carve_fast_side(unsigned char* base, int L, int RW, int V, int D) {
   constexpr int HL = 2 * exchange_frames<K, NS>() / NS;
   constexpr int RCH = kRowsRing * exchange_frames<K, NS>() / K;
   FastSideSmem s;
   unsigned char* p = base;
-  s.oth = p;                               p += (size_t)(kOthDepth * K + 1) * frame_block_bytes<NS>(L);
+  s.oth = p;                               p += (size_t)(D * K + 1) * frame_block_bytes<NS>(L);
   s.halo_m = reinterpret_cast<float4*>(p); p += (size_t)2 * NWMAX * HL * (NS / 4) * 16;
   s.rows = reinterpret_cast<float*>(p);    p += (size_t)RCH * K * (size_t)(RW + 4) * 4;
   s.post = reinterpret_cast<float*>(p);    p += 2 * (size_t)K * post_stride<NWMAX>(L, V) * 4;
@@ -464,7 +466,7 @@ __device__ __forceinline__ void lattice_frame(LaneState<NS>& st, const LaneConst
 template <int SIDE>
 struct FastCtx {
   const CallParams* p;
-  int b, T, L, S, JG, FB, P, NW, RW, RWS, PS, RC;    // FB: bytes of a frame block
+  int b, T, L, S, JG, FB, P, NW, RW, RWS, PS, RC, D;    // FB: bytes of a frame block; D: depth of the record ring
   int w, lane, tid_side;
   FastSideSmem sm;
   unsigned char* scr;   // [T] frame blocks: stored pre-emission pairs in the READER's group order and packing
@@ -641,7 +643,7 @@ __device__ __forceinline__ void run_chunk(const FastCtx<SIDE>& c, SweepState<NS>
     const bool store = write_post;
     if (active) {
       const unsigned char* blk = c.sm.oth + (size_t)obuf * K * c.FB;
-      const unsigned char* zero_blk = c.sm.oth + (size_t)kOthDepth * K * c.FB;
+      const unsigned char* zero_blk = c.sm.oth + (size_t)c.D * K * c.FB;
       const int plane = c.JG * 16;
 #pragma unroll kPh2Unroll
       for (int j = 0; j < kc; ++j) {
@@ -726,7 +728,8 @@ __device__ __forceinline__ void fill_ctx(FastCtx<SIDE>& c, const CallParams& p, 
   c.PS = post_stride<NWMAX>(m.L, p.V);
   c.RC = c.PS - NWMAX * 32 - 4;                 // label slots come first, then the blank partials, then the dump slot
   c.w = w; c.lane = lane; c.tid_side = w * 32 + lane;
-  c.sm = carve_fast_side<K, NWMAX, NS>(side_smem, m.L, c.RW, p.V);
+  c.D = p.oth_depth;
+  c.sm = carve_fast_side<K, NWMAX, NS>(side_smem, m.L, c.RW, p.V, c.D);
   c.scr = p.scratch + m.scratch_off * kGroupBytes;
   const float* row_src; long long row_stride; int row_vec;
   if (p.gathered) {
@@ -872,7 +875,7 @@ __device__ void fast_side_sweep(const CallParams& p, int b, const UttMeta& m, co
   int* abort_flag = cm.abort_flag;
 
   // the all-zero frame block (stands in for records the other side never wrote)
-  for (int i = c.tid_side; i < c.FB / 4; i += NW * 32) reinterpret_cast<int*>(c.sm.oth + (size_t)kOthDepth * K * c.FB)[i] = (i >= NH * JG * 4) ? kEZero : 0;
+  for (int i = c.tid_side; i < c.FB / 4; i += NW * 32) reinterpret_cast<int*>(c.sm.oth + (size_t)c.D * K * c.FB)[i] = (i >= NH * JG * 4) ? kEZero : 0;
   // zero slots of the row buffers (the helper warps stage the rows themselves)
   for (int i = c.tid_side; i < RCH * K; i += NW * 32) {
     float* z = c.sm.rows + (size_t)i * c.RWS + c.RW;
@@ -921,7 +924,7 @@ __device__ void fast_side_sweep(const CallParams& p, int b, const UttMeta& m, co
       if (lc.owned) {
         // no band masks: outside the band one of the two factors is exactly zero (posterior_frame)
         const bool wr = (unsigned)(ss.rd_hi - n0) < (unsigned)ss.wr_len;
-        const unsigned char* blk = c.sm.oth + (wr ? (size_t)0 : (size_t)kOthDepth * K * c.FB);
+        const unsigned char* blk = c.sm.oth + (wr ? (size_t)0 : (size_t)c.D * K * c.FB);
         float sum = 0.f;
 #pragma unroll
         for (int h = 0; h < NH; ++h) {
@@ -951,11 +954,12 @@ __device__ void fast_side_sweep(const CallParams& p, int b, const UttMeta& m, co
   const bool write_post = p.grads != nullptr;
 
   // ================================ phase 2 ================================
-  int k2 = 0;
+  int k2 = 0, ob = 0;                                  // ob: ring slot of the chunk's records, k2 mod D
   for (int n0 = M_side; n0 < T; n0 += K, ++k2, ++cc) {
     const int kc = min(K, T - n0), par = k2 & 1;
     B200CTC_TRACE_EVENT(tc, 13);
-    run_chunk<K, true, SIDE, NT, NS>(c, ss, rs, par, k2 % kOthDepth, n0, kc, write_post);
+    run_chunk<K, true, SIDE, NT, NS>(c, ss, rs, par, ob, n0, kc, write_post);
+    ob = ob + 1 == c.D ? 0 : ob + 1;
     B200CTC_TRACE_EVENT(tc, 14);
     // the barrier with the helpers is per chunk; the halo is good for KX frames after an exchange
     const bool exchange = (k2 + 1) % (KX / K) == 0;
@@ -1082,9 +1086,10 @@ __device__ void fast_side_helper(const CallParams& p, int b, const UttMeta& m, c
   const int nbar = (NW + kReducers) * 32;
   B200CTC_TRACE_DECL(tc);
 
-  unsigned long long* mbar = c.sm.mbar + hj * kOthDepth;   // one per ring slot: slot s completes phase (q / kOthDepth) & 1 for chunk q
+  unsigned long long* mbar = c.sm.mbar + hj * kOthDepthMax;   // one per ring slot: slot s completes phase (q / D) & 1 for chunk q
+  const int D = c.D;
   if (lane == 0) {
-    for (int s = 0; s < kOthDepth; ++s) mbar_init(mbar + s, 1);
+    for (int s = 0; s < kOthDepthMax; ++s) mbar_init(mbar + s, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   __syncwarp();
@@ -1119,20 +1124,19 @@ __device__ void fast_side_helper(const CallParams& p, int b, const UttMeta& m, c
   // ================================ midpoint ================================
   if (CL) cluster_sync_all(); else midpoint_sync(2 * nbar);
   if (pl.nc2 == 0) return;
-  // The records frame hj of phase-2 chunk q needs travel into ring slot q % kOthDepth, kOthDepth - 1 chunks ahead of
-  // the lattice warps (the slot is free: they finished chunk q - kOthDepth before the barrier that precedes the copy).
+  // The records frame hj of phase-2 chunk q needs travel into ring slot q mod D, D - 1 chunks ahead of the lattice
+  // warps (the slot is free: they finished chunk q - D before the barrier that precedes the copy).  The first D - 1
+  // chunks go into slots 0 .. D - 2 here; the loop below keeps its slot and phase counters incrementally.
   const int nc2 = pl.nc2;
-  auto fetch = [&](int q) {
+  for (int q = 0; q < D - 1; ++q) {
     const int n = M_side + q * K + hj;
-    if (!B200CTC_ABL(10) && q < nc2 && n < T) prefetch_other<SIDE>(c, (q % kOthDepth) * K + hj, n, mbar + q % kOthDepth);
+    if (!B200CTC_ABL(10) && q < nc2 && n < T) prefetch_other<SIDE>(c, q * K + hj, n, mbar + q);
+  }
+  auto landed = [&](int n, int slot, unsigned phase) {       // the copy for step n (if there was one) has arrived
+    if (!B200CTC_ABL(10) && !B200CTC_ABL(11) && n < T)
+      if (!mbar_wait(mbar + slot, phase) && lane == 0) *cm.abort_flag = 1;   // never observed; the safe lattice would redo the utterance
   };
-  auto landed = [&](int q) {
-    const int n = M_side + q * K + hj;
-    if (!B200CTC_ABL(10) && !B200CTC_ABL(11) && q < nc2 && n < T)
-      if (!mbar_wait(mbar + q % kOthDepth, (unsigned)(q / kOthDepth) & 1u) && lane == 0) *cm.abort_flag = 1;   // never observed; the safe lattice would redo the utterance
-  };
-  for (int q = 0; q < kOthDepth - 1; ++q) fetch(q);
-  landed(0);
+  landed(M_side + hj, 0, 0u);
   named_bar_sync(bar_chunk(SIDE), nbar);
   named_bar_sync(bar_total(SIDE), nbar);
   {
@@ -1164,9 +1168,12 @@ __device__ void fast_side_helper(const CallParams& p, int b, const UttMeta& m, c
   const int st_adv = sgn * K * c.st_stride;
   const char* st_src = c.st_src + (long long)c.frame_of(chunk_start(staged) + hj) * c.st_stride;
   int st_n = chunk_start(staged) + hj;
-  // (b) the opposite side's records: chunk k2 + kOthDepth - 1 goes into ring slot (k2 - 1) % kOthDepth
+  // (b) the opposite side's records: chunk k2 + D - 1 goes into ring slot (k2 - 1) mod D; chunk k2 + 1 is awaited
   const int rec_adv = sgn * K * c.FB;
-  int rec_n = M_side + (kOthDepth - 1) * K + hj;
+  int rec_n = M_side + (D - 1) * K + hj;
+  int f_slot = D - 1;                                          // slot of chunk k2 + D - 1
+  int l_slot = 1 % D, l_n = M_side + K + hj;                   // slot, step and mbarrier phase of chunk k2 + 1
+  unsigned l_phase = D == 1 ? 1u : 0u;
   const unsigned char* rec_src = c.scr + (long long)c.frame_of(rec_n) * c.FB;
   // (c) the row reduce_frame updates: the gradient row of the frame, or (gathered mode) the frame's emission row in
   // the workspace, which nobody reads any more once its posteriors exist and which becomes its occupancy row
@@ -1189,11 +1196,12 @@ __device__ void fast_side_helper(const CallParams& p, int b, const UttMeta& m, c
     }
     cp_async_commit();
     if (!B200CTC_ABL(10) && rec_n < T && lane == 0) {
-      unsigned long long* mb = mbar + ((k2 + kOthDepth - 1) % kOthDepth);
+      unsigned long long* mb = mbar + f_slot;
       mbar_expect_tx(mb, (unsigned)c.FB);
-      bulk_g2s(c.sm.oth + (size_t)(((k2 + kOthDepth - 1) % kOthDepth) * K + hj) * c.FB, rec_src, (unsigned)c.FB, mb);
+      bulk_g2s(c.sm.oth + (size_t)(f_slot * K + hj) * c.FB, rec_src, (unsigned)c.FB, mb);
     }
     rec_n += K; rec_src += rec_adv;
+    f_slot = f_slot + 1 == D ? 0 : f_slot + 1;
     B200CTC_TRACE_EVENT(tc, 8);
     if (reduce && k2 >= 1) {                          // frame hj of the previous chunk (it was a full chunk)
       const float* post_row = post_hj + ((k2 - 1) & 1) * post_half;
@@ -1203,7 +1211,9 @@ __device__ void fast_side_helper(const CallParams& p, int b, const UttMeta& m, c
     }
     B200CTC_TRACE_EVENT(tc, 9);
     cp_async_wait<1>();
-    landed(k2 + 1);
+    landed(l_n, l_slot, l_phase);
+    l_n += K;
+    if (++l_slot == D) { l_slot = 0; l_phase ^= 1u; }
     if (!B200CTC_ABL(7) || (k2 + 1) % (KX / K) == 0) named_bar_sync(bar_chunk(SIDE), nbar);
   }
   // the last chunk
@@ -1260,7 +1270,7 @@ __device__ void lattice_fast_utterance(const CallParams& p, int b, unsigned char
   size_t common = (size_t)(reinterpret_cast<unsigned char*>(ip) - smem);
   common = (common + 15) / 16 * 16;
   const int RW = p.gathered ? m.W : (p.V + 3) / 4 * 4;
-  const size_t side_bytes = fast_side_bytes<K, NWMAX, NS>(L, RW, p.V);
+  const size_t side_bytes = fast_side_bytes<K, NWMAX, NS>(L, RW, p.V, p.oth_depth);
   *smem_abort = cm.abort_flag;
 
   // ---- prologue (all threads of the CTA) ----
@@ -1273,7 +1283,7 @@ __device__ void lattice_fast_utterance(const CallParams& p, int b, unsigned char
   {
     const int PS = post_stride<NWMAX>(L, p.V);
     for (int sd = 0; sd < (CL ? 1 : 2); ++sd) {
-      FastSideSmem s = carve_fast_side<K, NWMAX, NS>(smem + common + sd * side_bytes, L, RW, p.V);
+      FastSideSmem s = carve_fast_side<K, NWMAX, NS>(smem + common + sd * side_bytes, L, RW, p.V, p.oth_depth);
       for (int i = threadIdx.x; i < 2 * K * PS; i += blockDim.x) s.post[i] = 0.f;
     }
   }

@@ -526,3 +526,21 @@ def test_split_symbol_groups_of_text_like_labels(V, L, expo, cluster, monkeypatc
     loss_ref, gl_ref = ctc_ref.ctc_loss_call_site(acts.transpose(1, 0, 2), ys, x_lens, y_lens, 1.3, 0.1)
     assert abs(float(out.detach().cpu()[0]) - loss_ref) < LOSS_RTOL * abs(loss_ref)
     assert np.max(np.abs(logits.grad.cpu().numpy() - gl_ref)) < GRAD_ATOL / 2
+
+
+@pytest.mark.parametrize("V,L", [(1500, 190), (1500, 205), (1500, 222), (1500, 240), (200, 236), (30, 463)])
+def test_record_ring_depth_follows_the_label_sequence(V, L):
+    """The lattice's record ring is four chunks deep when the shared memory allows and three or two when the longest
+    label sequence needs the room (gathered mode: the emission-row ring grows with the labels): label sequences up
+    to the capacity of the shallowest ring (195 / 210 / 226 labels for V >= 1000) still run on the block-exponent
+    lattice, longer ones on the safe lattice in the same launch; every depth gives the oracle's result."""
+    rng = np.random.RandomState(V + L)
+    labs = [rng.randint(1, V, size=n) for n in (L, L // 3)]
+    T = L + ctc_ref.count_repeats(labs[0]) + 24
+    acts = rng.randn(T, 2, V).astype(np.float32)
+    wl = workloads.Workload("x", T, 2, V, np.concatenate(labs).astype(np.int32), np.array([len(x) for x in labs], np.int32),
+                            np.array([T, T - 7], np.int32), 0)
+    c, loss, g = b200.ctc_loss_and_grad(torch.from_numpy(acts).cuda(), wl.labels, wl.act_lens, wl.label_lens)
+    torch.cuda.synchronize()
+    assert ctc_mod.last_fallbacks() == (0, 0)
+    assert_parity(c, g, acts, wl)
