@@ -1021,13 +1021,16 @@ __device__ __forceinline__ void reduce_frame(const CallParams& p, const FastComm
   const float sy = p.s_y, so = p.s_occ, cl = p.c_ls;   // (1, 1, 0) unless the call carries b200ctc_options
   if (n_seg <= 64 && !gathered) {
     // small vocabularies, straight line: lane u owns reducer groups u and u + 32 (in registers)
+    // (the unsplit instantiation tests lane < n_seg where the split one tests its per-lane piece counts: kept apart
+    // on purpose -- the common case's code is the one that was tuned, and it moves by 1-2 % when it is touched)
+    const bool own0 = SPLIT ? rl.cnt[0] > 0 : lane < n_seg, own1 = SPLIT ? rl.cnt[1] > 0 : lane + 32 < n_seg;
     float tot0 = post_group_sum(post_a + 16u * rl.base4[0], post_a + 16u * (rl.base4[0] + rl.n4[0]), zero, max_n4);
-    const float y0 = rl.cnt[0] > 0 ? yrow[rl.sym[0]] : 0.f;
+    const float y0 = own0 ? yrow[rl.sym[0]] : 0.f;
     const float yb = yrow[p.blank];
     float tot1 = 0.f, y1 = 0.f;
-    if (rl.nvg > 32) {
+    if ((SPLIT ? rl.nvg : n_seg) > 32) {
       tot1 = post_group_sum(post_a + 16u * rl.base4[1], post_a + 16u * (rl.base4[1] + rl.n4[1]), zero, max_n4);
-      y1 = rl.cnt[1] > 0 ? yrow[rl.sym[1]] : 0.f;
+      y1 = own1 ? yrow[rl.sym[1]] : 0.f;
     }
     if (SPLIT) {
       // a symbol cut into pieces: its first piece (group v) collects the pieces v + 1 .. v + cnt - 1 in that order
@@ -1041,8 +1044,8 @@ __device__ __forceinline__ void reduce_frame(const CallParams& p, const FastComm
       }
     }
     accb = warp_sum_q30(accb);
-    if (rl.cnt[0] > 0) grow[rl.sym[0]] = fmaf(-so, tot0, fmaf(sy, y0, -cl));   // the touched symbols of a frame share one or two 128-byte rows
-    if (rl.cnt[1] > 0) grow[rl.sym[1]] = fmaf(-so, tot1, fmaf(sy, y1, -cl));
+    if (own0) grow[rl.sym[0]] = fmaf(-so, tot0, fmaf(sy, y0, -cl));   // the touched symbols of a frame share one or two 128-byte rows
+    if (own1) grow[rl.sym[1]] = fmaf(-so, tot1, fmaf(sy, y1, -cl));
     if (lane == 0) grow[p.blank] = fmaf(-so, accb, fmaf(sy, yb, -cl));
   } else {
     for (int u0 = 0; u0 < n_seg; u0 += 32) {
@@ -1147,16 +1150,22 @@ __device__ void fast_side_helper(const CallParams& p, int b, const UttMeta& m, c
 
   const int n_seg = *cm.ix.n_seg, max_n4 = cm.max_n4[0];
   ReducerLane rl;                                     // this lane's reducer groups (lane, lane + 32)
-  rl.nvg = cm.max_n4[1]; rl.mp = cm.max_n4[2];
-  const bool straight = n_seg <= kReducerGroups && !p.gathered;
+  rl.nvg = SPLIT ? cm.max_n4[1] : n_seg; rl.mp = SPLIT ? cm.max_n4[2] : 1;
 #pragma unroll
   for (int i = 0; i < 2; ++i) {
     const int u = lane + 32 * i;
-    const bool ok = straight && u < rl.nvg;
-    rl.sym[i] = ok ? cm.vg_sym[u] : 0;
-    rl.base4[i] = ok ? cm.vg_base4[u] : 0;
-    rl.n4[i] = ok ? cm.vg_n4[u] : 0;
-    rl.cnt[i] = ok ? cm.vg_cnt[u] : 0;
+    if (SPLIT) {                                      // pieces of symbol groups (the prologue's tables)
+      const bool ok = u < rl.nvg;
+      rl.sym[i] = ok ? cm.vg_sym[u] : 0;
+      rl.base4[i] = ok ? cm.vg_base4[u] : 0;
+      rl.n4[i] = ok ? cm.vg_n4[u] : 0;
+      rl.cnt[i] = ok ? cm.vg_cnt[u] : 0;
+    } else {                                          // one group per symbol
+      rl.sym[i] = u < n_seg ? cm.ix.seg_sym[u] : 0;
+      rl.base4[i] = u < n_seg ? cm.seg_slot[u] >> 2 : 0;
+      rl.n4[i] = u < n_seg ? (cm.seg_slot[u + 1] - cm.seg_slot[u]) >> 2 : 0;
+      rl.cnt[i] = 0;
+    }
   }
 
   // ================================ phase 2 ================================
@@ -1349,13 +1358,7 @@ __device__ void lattice_fast_utterance(const CallParams& p, int b, unsigned char
           const int nv = pieces(lo, pm);
           if (nv <= limit && 4 * split_cost(nv <= 32 ? 1 : 2, lo, pm) <= 3 * cost0) { R = lo; nvg = nv; mp = pm; }
         }
-        if (mp == 1) {                            // one group per symbol
-#pragma unroll
-          for (int i = 0; i < 2; ++i) {
-            const int u = lane + 32 * i;
-            if (u < n_seg) { cm.vg_base4[u] = first4[i]; cm.vg_n4[u] = g4[i]; cm.vg_sym[u] = cm.ix.seg_sym[u]; cm.vg_cnt[u] = 1; }
-          }
-        } else {
+        if (mp > 1) {                             // (one group per symbol: the helpers read the symbol tables themselves)
           // the pieces of symbol u follow one another; exclusive prefix over the symbols in (lane, lane + 32) order
           const unsigned m = 65536u / (unsigned)R + 1u;
           int pc[2], pre[2], run = 0;
