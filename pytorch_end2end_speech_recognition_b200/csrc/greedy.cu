@@ -8,6 +8,8 @@
 // "larger" than everything (the first NaN wins).
 //
 // Bound: HBM (one read of the logits, 4 bytes written per frame).
+#include <cstdlib>
+
 #include "common.cuh"
 
 namespace b200ctc {
@@ -115,6 +117,63 @@ __global__ void __launch_bounds__(256) frame_argmax_cta_kernel(
   }
 }
 
+// large vocabulary, streaming: persistent warps, one WARP per frame row (no block reduction, no barrier), eight
+// 128-bit loads in flight per lane.  The one-CTA-per-frame kernel above reads C4's logits (V = 3386) at 3.8 TB/s:
+// 64 000 short-lived CTAs with three loads per thread each.
+__device__ __forceinline__ float4 ldg_stream4(const float4* p) {
+  float4 v;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
+  return v;
+}
+#ifndef B200CTC_ARGMAX_IN_FLIGHT
+#define B200CTC_ARGMAX_IN_FLIGHT 8
+#endif
+constexpr int kInFlight = B200CTC_ARGMAX_IN_FLIGHT;
+__global__ void __launch_bounds__(256) frame_argmax_stream_kernel(
+    const float* __restrict__ logits, long long stride_b, long long stride_t,
+    const int* __restrict__ lens, int T, int V, int B, int* __restrict__ out_tokens) {
+  const int lane = threadIdx.x & 31;
+  const long long n_rows = (long long)B * T;
+  const long long n_warps = (long long)gridDim.x * (blockDim.x >> 5);
+  for (long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); row < n_rows; row += n_warps) {
+    const int b = (int)(row / T), t = (int)(row - (long long)b * T);
+    if (t >= min(lens[b], T)) continue;
+    const float* x = logits + b * stride_b + t * stride_t;
+    int head = (int)(((16 - ((uintptr_t)x & 15)) & 15) >> 2);
+    if (head > V) head = V;
+    unsigned long long best = 0ull;
+    if (lane < head) best = argmax_key(__ldg(x + lane), lane);
+    const int nvec = (V - head) >> 2;
+    const float4* x4 = reinterpret_cast<const float4*>(x + head);
+    int i = lane;
+    for (; i + 32 * (kInFlight - 1) < nvec; i += 32 * kInFlight) {   // kInFlight independent loads per lane before any use
+      float4 q[kInFlight];
+#pragma unroll
+      for (int k = 0; k < kInFlight; ++k) q[k] = ldg_stream4(x4 + i + 32 * k);
+#pragma unroll
+      for (int k = 0; k < kInFlight; ++k) {
+        const int v = head + ((i + 32 * k) << 2);
+        best = umax64(best, argmax_key(q[k].x, v));
+        best = umax64(best, argmax_key(q[k].y, v + 1));
+        best = umax64(best, argmax_key(q[k].z, v + 2));
+        best = umax64(best, argmax_key(q[k].w, v + 3));
+      }
+    }
+    for (; i < nvec; i += 32) {
+      const float4 q = ldg_stream4(x4 + i);
+      const int v = head + (i << 2);
+      best = umax64(best, argmax_key(q.x, v));
+      best = umax64(best, argmax_key(q.y, v + 1));
+      best = umax64(best, argmax_key(q.z, v + 2));
+      best = umax64(best, argmax_key(q.w, v + 3));
+    }
+    const int tail = head + (nvec << 2) + lane;
+    if (tail < V) best = umax64(best, argmax_key(__ldg(x + tail), tail));
+    best = warp_max_u64(best);
+    if (lane == 0) out_tokens[row] = key_index(best);
+  }
+}
+
 // One CTA per utterance: keep frame t iff its symbol differs from frame t-1 and is not blank;
 // compact in place with a block-wide prefix sum (writes never overtake reads: compaction only
 // moves tokens to lower indices and each chunk is read in full before it is written).
@@ -186,8 +245,17 @@ cudaError_t launch_greedy(const float* logits, long long stride_b, long long str
     } else if (V <= 512) {
       const unsigned grid = (unsigned)((rows + 7) / 8);
       frame_argmax_warp_kernel<<<grid, 256, 0, stream>>>(logits, stride_b, stride_t, lens, T, V, B, out_tokens);
-    } else {
+    } else if (std::getenv("B200CTC_GREEDY_CTA_PER_ROW")) {     // the previous kernel, for A/B measurements
       frame_argmax_cta_kernel<<<(unsigned)rows, 256, 0, stream>>>(logits, stride_b, stride_t, lens, T, V, B, out_tokens);
+    } else {
+      static int n_sm = 0;
+      if (n_sm == 0) {
+        int dev = 0;
+        if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) n_sm = 148;
+      }
+      long long grid = (long long)n_sm * 8;                      // eight resident CTAs of eight warps per SM
+      if (grid * 8 > rows) grid = (rows + 7) / 8;
+      frame_argmax_stream_kernel<<<(unsigned)grid, 256, 0, stream>>>(logits, stride_b, stride_t, lens, T, V, B, out_tokens);
     }
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return e;

@@ -57,6 +57,32 @@ def test_special_values_and_nonzero_blank():
         assert np.array_equal(got[0], ref[0])
 
 
+@pytest.mark.parametrize("V", [515, 1003, 4100])
+def test_large_vocabulary_special_values_at_every_position(V):
+    """The streaming arg-max kernel (V > 512): scalar head up to 16-byte alignment, unrolled and single 128-bit body
+    loads, scalar tail; ties, NaN, infinities and signed zeros in each of those regions, rows at every alignment."""
+    rng = np.random.RandomState(V)
+    T = 24
+    logits = np.round(rng.randn(2, T, V) * 2).astype(np.float32) / 2     # many exact ties
+    pos = [v for v in (0, 1, 2, 3, 5, 130, 511, 512, 700) if v < V - 4] + [V - 4, V - 3, V - 2, V - 1]
+    for t, v in enumerate(pos):
+        logits[0, t, v] = 9.0                                             # unique maximum at a chosen position
+        logits[1, t, v] = np.nan if t % 2 else np.inf
+        logits[1, t, (v + 7) % V] = np.inf                                # inf loses to NaN, ties with inf: first index
+    logits[0, 20, :] = -0.0; logits[0, 20, 3] = 0.0                      # -0.0 == +0.0: index 0
+    logits[0, 21, :] = -np.inf                                            # all -inf: index 0
+    logits[0, 22, [V - 1, 4]] = 50.0                                      # tie across tail and head: 4
+    for blank in (0, 5):
+        for off in (0, 1, 3):                                             # base pointer at different 16-byte phases
+            buf = torch.empty(logits.size + 4, device="cuda")
+            view = buf[off:off + logits.size].view(2, T, V)
+            view.copy_(torch.from_numpy(logits))
+            tokens, lens = b200.greedy_decode(view, np.array([T, T - 3]), blank)
+            ref = ctc_ref.greedy_decode(logits, [T, T - 3], blank)
+            for b in range(2):
+                assert np.array_equal(tokens[b, :lens[b]].cpu().numpy(), ref[b]), (blank, off, b)
+
+
 def test_numpy_interface_like_the_reference():
     rng = np.random.RandomState(2)
     logits = rng.randn(3, 20, 6).astype(np.float32)
