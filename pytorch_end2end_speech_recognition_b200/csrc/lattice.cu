@@ -121,12 +121,12 @@ __global__ void __launch_bounds__(2 * (NWMAX + kReducers) * 32, 1) lattice_kerne
 }
 
 // The thread-block-cluster variant: TWO CTAs per utterance, the forward sweep on one SM and the backward sweep on
-// another (NWMAX lattice warps + kReducers helper warps each), for mini-batches that leave at least half of the
+// another (NWMAX lattice warps + kReducers fetching and kReducers reducing helper warps each), for mini-batches that leave at least half of the
 // SMs idle.  The sides meet once, at the midpoint (a cluster barrier: everything phase 1 stored is visible to the
 // other SM afterwards), and compare their abort words through distributed shared memory at the end; the CTA of
 // rank 0 owns the utterance-level duties (safe lattice, flags, the tail).
 template <int K, int NWMAX, int NS>
-__global__ void __launch_bounds__((NWMAX + kReducers) * 32, 1) lattice_cluster_kernel(CallParams p) {
+__global__ void __launch_bounds__(cluster_block_warps<NWMAX>() * 32, 1) lattice_cluster_kernel(CallParams p) {
   extern __shared__ __align__(16) unsigned char smem[];
   pdl_launch_dependents();
   const unsigned rank = cluster_ctarank();
@@ -268,7 +268,7 @@ cudaError_t launch_lattice_cluster_t(const CallParams& p, size_t smem, cudaStrea
   if (e != cudaSuccess) return e;
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3((unsigned)(2 * p.B));
-  cfg.blockDim = dim3((NWMAX + kReducers) * 32);
+  cfg.blockDim = dim3(cluster_block_warps<NWMAX>() * 32);
   cfg.dynamicSmemBytes = smem;
   cfg.stream = stream;
   cudaLaunchAttribute attr[2];

@@ -86,6 +86,28 @@ constexpr int kAbortExtremeRow = 2;  // abort word: K1 flagged the utterance (no
 constexpr int kEZero = -(1 << 28);  // exponent of an all-zero lane
 constexpr int kRowsRing = 4;        // emission-row ring, in halo-exchange intervals (KX/K chunks each): the reducers' one, the current one, the next (landed), the one after (in flight)
 constexpr int kReducers = 4;        // reducer warps per side: warp j takes frame j of every phase-2 chunk (== K)
+// Helper warps per side.  One CTA for both sides: kReducers warps that fetch (emission rows, records) AND reduce.
+// Cluster variant (one side per CTA, an SM to itself): the two jobs on different warps -- kReducers fetchers and
+// kReducers reducers -- because with one or two lattice windows the helper's fetch-then-reduce chain (~1500 cycles
+// per chunk) is what arrives last at the chunk barrier.
+template <bool CL>
+__host__ __device__ constexpr int helper_warps() { return CL ? 2 * kReducers : kReducers; }
+enum HelperRole { kFetchAndReduce = 0, kFetchOnly = 1, kReduceOnly = 2 };
+// Cluster variant, warps of a CTA.  Warp i issues on SM sub-partition i % 4, and the lattice warps are the latency-
+// critical ones: with one or two lattice windows the helper warps take the OTHER sub-partitions (a reducer next to
+// the single lattice warp of C1 cost 5 % of the step), which leaves a few warp slots idle.
+template <int NWMAX>
+__host__ __device__ constexpr int cluster_block_warps() { return NWMAX == 2 ? 16 : 12; }
+// w: lattice window (< NWMAX), NWMAX + h for helper h (0..3 fetch, 4..7 reduce), or -1 (idle)
+template <int NWMAX>
+__device__ __forceinline__ int cluster_warp_role(int warp) {
+  if (NWMAX >= 4) return warp;                                     // 0..3 lattice, 4..11 helpers: two per sub-partition
+  const int sp = warp & 3, slot = warp >> 2;
+  if (warp < NWMAX) return warp;
+  if (NWMAX == 2) return sp >= 2 ? NWMAX + slot * 2 + (sp - 2) : -1;           // sub-partitions 2, 3: four helpers each
+  const int h = slot * 3 + sp - 1;                                 // NWMAX == 1: sub-partitions 1, 2, 3
+  return (sp != 0 && h < 2 * kReducers) ? NWMAX + h : -1;
+}
 // Depth D of the record ring (phase 2), in chunks: the helper warps fetch the opposite side's records D - 1
 // chunks ahead.  A bulk copy out of the HBM scratch takes ~2000 cycles under load -- longer than a chunk computes --
 // so with a ring of two (fetch during chunk c what chunk c + 1 reads) its latency sits on the critical path of
@@ -672,7 +694,7 @@ __device__ __forceinline__ void run_chunk(const FastCtx<SIDE>& c, SweepState<NS>
 // of the previous chunk is consumed), import the halo.
 template <int K, int NWMAX, int SIDE, int NS>
 __device__ __forceinline__ void chunk_boundary(const FastCtx<SIDE>& c, SweepState<NS>& ss, int cc, int* abort_flag, int& tc,
-                                               bool exchange = true, bool sync = true) {
+                                               int nbar, bool exchange = true, bool sync = true) {
   constexpr int NH = NS / 4, HL = 2 * exchange_frames<K, NS>() / NS;
   static_assert(HL * NS == 2 * exchange_frames<K, NS>() && HL >= 1, "the halo must be whole lanes");
   const int hb = cc & 1, NW = c.NW, w = c.w, lane = c.lane;
@@ -686,7 +708,7 @@ __device__ __forceinline__ void chunk_boundary(const FastCtx<SIDE>& c, SweepStat
   }
   if (ss.lc.owned && ss.maxbound > kLostBound) *abort_flag = 1;
   B200CTC_TRACE_EVENT(tc, 30);
-  if (sync) named_bar_sync(bar_chunk(SIDE), (NW + kReducers) * 32);
+  if (sync) named_bar_sync(bar_chunk(SIDE), nbar);
   B200CTC_TRACE_EVENT(tc, 31);
   if (exchange && w > 0 && lane < HL) {
     const int slot = (hb * NWMAX + (w - 1)) * HL + lane;
@@ -886,7 +908,8 @@ __device__ void fast_side_sweep(const CallParams& p, int b, const UttMeta& m, co
   // side's records) was fetched by the helper warps during the previous chunk.
   int rs = 0;
   B200CTC_TRACE_EVENT(tc, 1);
-  named_bar_sync(bar_chunk(SIDE), (NW + kReducers) * 32);       // rows of chunk 0 staged, wr_tab visible
+  const int nbar = (NW + helper_warps<CL>()) * 32;              // lattice warps + the side's helper warps
+  named_bar_sync(bar_chunk(SIDE), nbar);                        // rows of chunk 0 staged, wr_tab visible
 
   // ================================ phase 1 ================================
   // KX/K chunks between two halo exchanges (one barrier with the helpers per exchange)
@@ -902,16 +925,16 @@ __device__ void fast_side_sweep(const CallParams& p, int b, const UttMeta& m, co
     rs = (rs + nch) & (RCH - 1);
     n0 += kc;
     cc += nch;
-    chunk_boundary<K, NWMAX, SIDE, NS>(c, ss, xc, abort_flag, tc);
+    chunk_boundary<K, NWMAX, SIDE, NS>(c, ss, xc, abort_flag, tc, nbar);
   }
 
   // ================================ midpoint ================================
   // Lattice and helper warps of both sides meet here exactly once: everything phase 1 stored is
   // visible afterwards.
   B200CTC_TRACE_EVENT(tc, 4);
-  if (CL) cluster_sync_all(); else midpoint_sync(2 * (NW + kReducers) * 32);
+  if (CL) cluster_sync_all(); else midpoint_sync(2 * nbar);
   if (nc2 == 0) return;
-  named_bar_sync(bar_chunk(SIDE), (NW + kReducers) * 32);       // the helpers fetched the records of the first phase-2 chunk
+  named_bar_sync(bar_chunk(SIDE), nbar);                        // the helpers fetched the records of the first phase-2 chunk
 
   // ---- total probability P = sum_s alpha_t(s) beta'_t(s) at the first phase-2 frame (state copy) ----
   {
@@ -941,7 +964,7 @@ __device__ void fast_side_sweep(const CallParams& p, int b, const UttMeta& m, co
     float scaled = part * pow2_neg(pe - emax);
     scaled = warp_sum(scaled);
     if (lane == 0) { c.sm.red_m[w] = scaled; c.sm.red_e[w] = emax; }
-    named_bar_sync(bar_total(SIDE), (NW + kReducers) * 32);   // lattice warps + the side's helpers
+    named_bar_sync(bar_total(SIDE), nbar);                    // lattice warps + the side's helpers
     double log2P;
     if (!total_probability(c.sm, NW, ss.inv_mP, ss.eP, log2P)) {
       // zero / underflowed / garbage total probability: the safe lattice decides
@@ -963,7 +986,7 @@ __device__ void fast_side_sweep(const CallParams& p, int b, const UttMeta& m, co
     B200CTC_TRACE_EVENT(tc, 14);
     // the barrier with the helpers is per chunk; the halo is good for KX frames after an exchange
     const bool exchange = (k2 + 1) % (KX / K) == 0;
-    chunk_boundary<K, NWMAX, SIDE, NS>(c, ss, xc, abort_flag, tc, exchange, !B200CTC_ABL(7) || exchange);
+    chunk_boundary<K, NWMAX, SIDE, NS>(c, ss, xc, abort_flag, tc, nbar, exchange, !B200CTC_ABL(7) || exchange);
     rs = (rs + 1) & (RCH - 1);
     xc += exchange ? 1 : 0;
   }
@@ -1077,21 +1100,22 @@ __device__ __forceinline__ void reduce_frame(const CallParams& p, const FastComm
 // of chunk c+1 needs (emission row; in phase 2 the other side's records of all position groups) and,
 // in phase 2, reduces the posteriors the lattice warps produced for its frame of chunk c-1 into the
 // gradient row.  It meets the lattice warps at the one barrier per chunk.
-template <int K, int NWMAX, int SIDE, int NS, bool CL, bool SPLIT>
+template <int K, int NWMAX, int SIDE, int NS, bool CL, bool SPLIT, int ROLE>
 __device__ void fast_side_helper(const CallParams& p, int b, const UttMeta& m, const FastCommon& cm,
                                  unsigned char* side_smem, int hj, int lane) {
   static_assert(kReducers == K, "one helper warp per frame of a chunk");
+  constexpr bool FETCH = ROLE != kReduceOnly, REDUCE = ROLE != kFetchOnly;
   FastCtx<SIDE> c;
   fill_ctx<K, NWMAX, SIDE, NS>(c, p, b, m, side_smem, NWMAX + hj, lane);
   const int T = c.T, NW = c.NW, V = p.V;
   const SidePlan pl = side_plan<K, SIDE>(T);
   const int M_side = pl.M_side;
-  const int nbar = (NW + kReducers) * 32;
+  const int nbar = (NW + helper_warps<CL>()) * 32;
   B200CTC_TRACE_DECL(tc);
 
   unsigned long long* mbar = c.sm.mbar + hj * kOthDepthMax;   // one per ring slot: slot s completes phase (q / D) & 1 for chunk q
   const int D = c.D;
-  if (lane == 0) {
+  if (FETCH && lane == 0) {
     for (int s = 0; s < kOthDepthMax; ++s) mbar_init(mbar + s, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -1104,15 +1128,17 @@ __device__ void fast_side_helper(const CallParams& p, int b, const UttMeta& m, c
   auto chunk_start = [&](int cc) { return cc < nc1 ? cc * K : M_side + (cc - nc1) * K; };
   int staged = 0;                                    // chunks [0, staged) have been requested
   auto stage_upto = [&](int end) {                   // one cp.async group: this warp's row of chunks [staged, end)
-    for (; staged < min(end, n_chunks); ++staged) {
-      const int n = chunk_start(staged) + hj;
-      if (n < T) stage_row<SIDE>(c, (staged & (RCH - 1)) * K + hj, n);   // a row past a short chunk is harmless
+    if (FETCH) {
+      for (; staged < min(end, n_chunks); ++staged) {
+        const int n = chunk_start(staged) + hj;
+        if (n < T) stage_row<SIDE>(c, (staged & (RCH - 1)) * K + hj, n);   // a row past a short chunk is harmless
+      }
+      cp_async_commit();
     }
-    cp_async_commit();
   };
   stage_upto(M);
   stage_upto(2 * M);
-  cp_async_wait<1>();
+  if (FETCH) cp_async_wait<1>();
   named_bar_sync(bar_chunk(SIDE), nbar);
 
   // ================================ phase 1 ================================
@@ -1120,7 +1146,7 @@ __device__ void fast_side_helper(const CallParams& p, int b, const UttMeta& m, c
   int cc = 0;
   for (int xc = 0; cc < nc1; ++xc, cc = min(cc + M, nc1)) {
     stage_upto((xc + 3) * M);
-    cp_async_wait<1>();                       // rows up to chunk (xc+2)*M - 1 have landed
+    if (FETCH) cp_async_wait<1>();            // rows up to chunk (xc+2)*M - 1 have landed
     named_bar_sync(bar_chunk(SIDE), nbar);
   }
 
@@ -1131,12 +1157,12 @@ __device__ void fast_side_helper(const CallParams& p, int b, const UttMeta& m, c
   // warps (the slot is free: they finished chunk q - D before the barrier that precedes the copy).  The first D - 1
   // chunks go into slots 0 .. D - 2 here; the loop below keeps its slot and phase counters incrementally.
   const int nc2 = pl.nc2;
-  for (int q = 0; q < D - 1; ++q) {
+  for (int q = 0; FETCH && q < D - 1; ++q) {
     const int n = M_side + q * K + hj;
     if (!B200CTC_ABL(10) && q < nc2 && n < T) prefetch_other<SIDE>(c, q * K + hj, n, mbar + q);
   }
   auto landed = [&](int n, int slot, unsigned phase) {       // the copy for step n (if there was one) has arrived
-    if (!B200CTC_ABL(10) && !B200CTC_ABL(11) && n < T)
+    if (FETCH && !B200CTC_ABL(10) && !B200CTC_ABL(11) && n < T)
       if (!mbar_wait(mbar + slot, phase) && lane == 0) *cm.abort_flag = 1;   // never observed; the safe lattice would redo the utterance
   };
   landed(M_side + hj, 0, 0u);
@@ -1146,7 +1172,7 @@ __device__ void fast_side_helper(const CallParams& p, int b, const UttMeta& m, c
     float inv_mP; int eP; double log2P;
     if (!total_probability(c.sm, NW, inv_mP, eP, log2P)) return;
   }
-  const bool reduce = p.grads != nullptr && !B200CTC_ABL(9);   // ablation 9: helpers do not reduce (timing only)
+  const bool reduce = REDUCE && p.grads != nullptr && !B200CTC_ABL(9);   // ablation 9: helpers do not reduce (timing only)
 
   const int n_seg = *cm.ix.n_seg, max_n4 = cm.max_n4[0];
   ReducerLane rl;                                     // this lane's reducer groups (lane, lane + 32)
@@ -1199,12 +1225,12 @@ __device__ void fast_side_helper(const CallParams& p, int b, const UttMeta& m, c
   int k2 = 0;
   for (; k2 < nc2; ++k2, ++cc) {
     B200CTC_TRACE_EVENT(tc, 7);
-    if (staged < cc + 3 && staged < n_chunks) {       // chunk cc+2 (nothing to do while phase 1's look-ahead lasts)
+    if (FETCH && staged < cc + 3 && staged < n_chunks) {   // chunk cc+2 (nothing to do while phase 1's look-ahead lasts)
       if (st_n < T) stage_row_at<SIDE>(c, st_dst_hj + (unsigned)((staged & (RCH - 1)) * row_chunk * 4), st_src);   // a row past a short chunk is harmless
       ++staged; st_n += K; st_src += st_adv;
     }
-    cp_async_commit();
-    if (!B200CTC_ABL(10) && rec_n < T && lane == 0) {
+    if (FETCH) cp_async_commit();
+    if (FETCH && !B200CTC_ABL(10) && rec_n < T && lane == 0) {
       unsigned long long* mb = mbar + f_slot;
       mbar_expect_tx(mb, (unsigned)c.FB);
       bulk_g2s(c.sm.oth + (size_t)(f_slot * K + hj) * c.FB, rec_src, (unsigned)c.FB, mb);
@@ -1219,7 +1245,7 @@ __device__ void fast_side_helper(const CallParams& p, int b, const UttMeta& m, c
       out += out_adv;
     }
     B200CTC_TRACE_EVENT(tc, 9);
-    cp_async_wait<1>();
+    if (FETCH) cp_async_wait<1>();
     landed(l_n, l_slot, l_phase);
     l_n += K;
     if (++l_slot == D) { l_slot = 0; l_phase ^= 1u; }
@@ -1252,7 +1278,7 @@ __device__ void lattice_fast_utterance(const CallParams& p, int b, unsigned char
   const int warp = NWMAX > 1 ? __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0) : (int)(threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   const int side = CL ? (int)cluster_ctarank() : warp / (NWMAX + kReducers);
-  int w = CL ? warp : warp - side * (NWMAX + kReducers);
+  int w = CL ? cluster_warp_role<NWMAX>(warp) : warp - side * (NWMAX + kReducers);
   // Scheduler balance: warp i issues on SM sub-partition i % 4.  Early in phase 1 (and late in phase 2)
   // only the lowest lattice windows of each side are inside the reachable band; giving the backward
   // side its windows in reverse warp order puts the two busy windows on different sub-partitions.
@@ -1441,23 +1467,37 @@ __device__ void lattice_fast_utterance(const CallParams& p, int b, unsigned char
     return;
   }
   unsigned char* side_smem = smem + common + (CL ? 0 : side) * side_bytes;
-  if (w < NW) {
+  if (w >= 0 && w < NW) {
     if (side == 0) fast_side_sweep<K, NWMAX, 0, NS, CL>(p, b, m, cm, side_smem, w, lane);
     else           fast_side_sweep<K, NWMAX, 1, NS, CL>(p, b, m, cm, side_smem, w, lane);
+  } else if (CL && w >= NWMAX) {
+    // cluster variant: helper warps NWMAX .. NWMAX + 3 fetch, NWMAX + 4 .. NWMAX + 7 reduce (frame hj of every chunk each)
+    const bool split = B200CTC_GROUP_SPLIT && __builtin_expect(cm.max_n4[2] > 1, 0);
+    const int hw = w - NWMAX;
+    if (hw < kReducers) {
+      if (side == 0) fast_side_helper<K, NWMAX, 0, NS, CL, false, kFetchOnly>(p, b, m, cm, side_smem, hw, lane);
+      else           fast_side_helper<K, NWMAX, 1, NS, CL, false, kFetchOnly>(p, b, m, cm, side_smem, hw, lane);
+    } else if (!split) {
+      if (side == 0) fast_side_helper<K, NWMAX, 0, NS, CL, false, kReduceOnly>(p, b, m, cm, side_smem, hw - kReducers, lane);
+      else           fast_side_helper<K, NWMAX, 1, NS, CL, false, kReduceOnly>(p, b, m, cm, side_smem, hw - kReducers, lane);
+    } else {
+      if (side == 0) fast_side_helper<K, NWMAX, 0, NS, CL, true, kReduceOnly>(p, b, m, cm, side_smem, hw - kReducers, lane);
+      else           fast_side_helper<K, NWMAX, 1, NS, CL, true, kReduceOnly>(p, b, m, cm, side_smem, hw - kReducers, lane);
+    }
   } else if (w >= NWMAX) {
     // (a second instantiation of the helper rather than a branch in its loop: the combination of split symbol
     // groups costs the unsplit case 5 % of the step by merely being in the loop body; out of line -- __noinline__ --
     // it costs every case 10-15 %: a 448-byte stack frame and the call ABI's register constraints)
     const bool split = B200CTC_GROUP_SPLIT && __builtin_expect(cm.max_n4[2] > 1, 0);
     if (!split) {
-      if (side == 0) fast_side_helper<K, NWMAX, 0, NS, CL, false>(p, b, m, cm, side_smem, w - NWMAX, lane);
-      else           fast_side_helper<K, NWMAX, 1, NS, CL, false>(p, b, m, cm, side_smem, w - NWMAX, lane);
+      if (side == 0) fast_side_helper<K, NWMAX, 0, NS, CL, false, kFetchAndReduce>(p, b, m, cm, side_smem, w - NWMAX, lane);
+      else           fast_side_helper<K, NWMAX, 1, NS, CL, false, kFetchAndReduce>(p, b, m, cm, side_smem, w - NWMAX, lane);
     } else {
-      if (side == 0) fast_side_helper<K, NWMAX, 0, NS, CL, true>(p, b, m, cm, side_smem, w - NWMAX, lane);
-      else           fast_side_helper<K, NWMAX, 1, NS, CL, true>(p, b, m, cm, side_smem, w - NWMAX, lane);
+      if (side == 0) fast_side_helper<K, NWMAX, 0, NS, CL, true, kFetchAndReduce>(p, b, m, cm, side_smem, w - NWMAX, lane);
+      else           fast_side_helper<K, NWMAX, 1, NS, CL, true, kFetchAndReduce>(p, b, m, cm, side_smem, w - NWMAX, lane);
     }
   } else if (CL) {
-    cluster_sync_all();          // an idle lattice warp: the midpoint rendezvous counts every thread of the cluster
+    cluster_sync_all();          // an idle warp: the midpoint rendezvous counts every thread of the cluster
   }
   // idle warps wait at the caller's __syncthreads()
 }
