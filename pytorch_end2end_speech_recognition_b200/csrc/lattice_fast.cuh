@@ -692,9 +692,9 @@ __device__ __forceinline__ void run_chunk(const FastCtx<SIDE>& c, SweepState<NS>
 // Chunk boundary of the lattice warps: publish the halo lanes, ONE barrier with the side's lattice and
 // helper warps (after it the helpers' prefetch for the next chunk has landed and the posterior buffer
 // of the previous chunk is consumed), import the halo.
-template <int K, int NWMAX, int SIDE, int NS>
+template <int K, int NWMAX, int SIDE, int NS, int HW>   // HW: helper warps of the side
 __device__ __forceinline__ void chunk_boundary(const FastCtx<SIDE>& c, SweepState<NS>& ss, int cc, int* abort_flag, int& tc,
-                                               int nbar, bool exchange = true, bool sync = true) {
+                                               bool exchange = true, bool sync = true) {
   constexpr int NH = NS / 4, HL = 2 * exchange_frames<K, NS>() / NS;
   static_assert(HL * NS == 2 * exchange_frames<K, NS>() && HL >= 1, "the halo must be whole lanes");
   const int hb = cc & 1, NW = c.NW, w = c.w, lane = c.lane;
@@ -708,7 +708,7 @@ __device__ __forceinline__ void chunk_boundary(const FastCtx<SIDE>& c, SweepStat
   }
   if (ss.lc.owned && ss.maxbound > kLostBound) *abort_flag = 1;
   B200CTC_TRACE_EVENT(tc, 30);
-  if (sync) named_bar_sync(bar_chunk(SIDE), nbar);
+  if (sync) named_bar_sync(bar_chunk(SIDE), (NW + HW) * 32);
   B200CTC_TRACE_EVENT(tc, 31);
   if (exchange && w > 0 && lane < HL) {
     const int slot = (hb * NWMAX + (w - 1)) * HL + lane;
@@ -908,8 +908,8 @@ __device__ void fast_side_sweep(const CallParams& p, int b, const UttMeta& m, co
   // side's records) was fetched by the helper warps during the previous chunk.
   int rs = 0;
   B200CTC_TRACE_EVENT(tc, 1);
-  const int nbar = (NW + helper_warps<CL>()) * 32;              // lattice warps + the side's helper warps
-  named_bar_sync(bar_chunk(SIDE), nbar);                        // rows of chunk 0 staged, wr_tab visible
+  constexpr int HW = helper_warps<CL>();                        // barriers: lattice warps + the side's helper warps
+  named_bar_sync(bar_chunk(SIDE), (NW + HW) * 32);              // rows of chunk 0 staged, wr_tab visible
 
   // ================================ phase 1 ================================
   // KX/K chunks between two halo exchanges (one barrier with the helpers per exchange)
@@ -925,16 +925,16 @@ __device__ void fast_side_sweep(const CallParams& p, int b, const UttMeta& m, co
     rs = (rs + nch) & (RCH - 1);
     n0 += kc;
     cc += nch;
-    chunk_boundary<K, NWMAX, SIDE, NS>(c, ss, xc, abort_flag, tc, nbar);
+    chunk_boundary<K, NWMAX, SIDE, NS, HW>(c, ss, xc, abort_flag, tc);
   }
 
   // ================================ midpoint ================================
   // Lattice and helper warps of both sides meet here exactly once: everything phase 1 stored is
   // visible afterwards.
   B200CTC_TRACE_EVENT(tc, 4);
-  if (CL) cluster_sync_all(); else midpoint_sync(2 * nbar);
+  if (CL) cluster_sync_all(); else midpoint_sync(2 * (NW + HW) * 32);
   if (nc2 == 0) return;
-  named_bar_sync(bar_chunk(SIDE), nbar);                        // the helpers fetched the records of the first phase-2 chunk
+  named_bar_sync(bar_chunk(SIDE), (NW + HW) * 32);              // the helpers fetched the records of the first phase-2 chunk
 
   // ---- total probability P = sum_s alpha_t(s) beta'_t(s) at the first phase-2 frame (state copy) ----
   {
@@ -964,7 +964,7 @@ __device__ void fast_side_sweep(const CallParams& p, int b, const UttMeta& m, co
     float scaled = part * pow2_neg(pe - emax);
     scaled = warp_sum(scaled);
     if (lane == 0) { c.sm.red_m[w] = scaled; c.sm.red_e[w] = emax; }
-    named_bar_sync(bar_total(SIDE), nbar);                    // lattice warps + the side's helpers
+    named_bar_sync(bar_total(SIDE), (NW + HW) * 32);          // lattice warps + the side's helpers
     double log2P;
     if (!total_probability(c.sm, NW, ss.inv_mP, ss.eP, log2P)) {
       // zero / underflowed / garbage total probability: the safe lattice decides
@@ -986,7 +986,7 @@ __device__ void fast_side_sweep(const CallParams& p, int b, const UttMeta& m, co
     B200CTC_TRACE_EVENT(tc, 14);
     // the barrier with the helpers is per chunk; the halo is good for KX frames after an exchange
     const bool exchange = (k2 + 1) % (KX / K) == 0;
-    chunk_boundary<K, NWMAX, SIDE, NS>(c, ss, xc, abort_flag, tc, nbar, exchange, !B200CTC_ABL(7) || exchange);
+    chunk_boundary<K, NWMAX, SIDE, NS, HW>(c, ss, xc, abort_flag, tc, exchange, !B200CTC_ABL(7) || exchange);
     rs = (rs + 1) & (RCH - 1);
     xc += exchange ? 1 : 0;
   }
